@@ -1,0 +1,104 @@
+"""The oracle against vectors produced by the reference's own classes (tests/golden/make_golden.py).
+
+CPU only.  Pins both restatements in oracle/percnn_oracle.py: the ATen-op-sequence one must track
+the reference to rounding, the numpy one (fp64, written from the maths) to fp32/fp64 noise.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import percnn_oracle as po
+from tests.helpers import GOLDEN_CASES, load_golden, rel_l2, rel_linf
+
+
+@pytest.mark.parametrize("tag", list(GOLDEN_CASES))
+def test_torch_restatement_matches_reference_rollout(tag):
+    z, params, _ = load_golden(tag)
+    variant = GOLDEN_CASES[tag]
+    h0 = torch.from_numpy(z["h0"])
+    nstep = int(z["nstep"])
+    torch.set_num_threads(1)
+    outs, second_last = po.rollout_torch(h0, params, variant, nstep, range(nstep))
+    traj = torch.cat(outs, 0).numpy()
+    tol = 1e-13 if h0.dtype == torch.float64 else 2e-6
+    assert traj.shape == z["traj"].shape
+    assert rel_linf(traj, z["traj"]) <= tol
+    assert rel_linf(second_last.numpy(), z["second_last"]) <= tol
+    # the rollout actually moves the state (guards against a fixture where nothing happens)
+    assert rel_l2(z["traj"][-1], z["traj"][0]) > 1e-4
+
+
+@pytest.mark.parametrize("tag", list(GOLDEN_CASES))
+def test_numpy_restatement_matches_reference_step(tag):
+    z, params, _ = load_golden(tag)
+    variant = GOLDEN_CASES[tag]
+    h = z["traj"][0:1]
+    ref = z["traj"][1:2]
+    got = po.cell_step_np(h, params, variant)
+    tol = 1e-12 if z["h0"].dtype == np.float64 else 5e-6
+    assert rel_linf(got, ref) <= tol
+
+
+@pytest.mark.parametrize("tag", list(GOLDEN_CASES))
+def test_numpy_adjoint_matches_reference_autograd(tag):
+    """Hand-derived adjoint replayed over the recorded trajectory vs autograd grads."""
+    z, params, grads = load_golden(tag)
+    variant = GOLDEN_CASES[tag]
+    traj = z["traj"].astype(np.float64)
+    wts = z["loss_weights"].astype(np.float64)
+    nstep = int(z["nstep"])
+    G = wts[nstep:nstep + 1].copy()
+    acc = {}
+    for t in range(nstep - 1, -1, -1):
+        G, pg = po.cell_step_vjp_np(traj[t:t + 1], G, params, variant)
+        G = G + wts[t:t + 1]
+        for k, v in pg.items():
+            acc[k] = acc.get(k, 0) + v
+    tol = 1e-10 if z["h0"].dtype == np.float64 else 3e-4
+    assert rel_l2(G, z["g_h0"]) <= tol
+    assert set(grads) <= set(acc), (set(grads) - set(acc))
+    for k, ref in grads.items():
+        assert rel_l2(np.asarray(acc[k]).reshape(ref.shape), ref) <= tol, k
+
+
+def test_torch_autograd_of_oracle_matches_reference_grads():
+    z, params, grads = load_golden("gs2d")
+    p = {k: v.clone().requires_grad_(k in grads) for k, v in params.items()}
+    h0 = torch.from_numpy(z["h0"]).requires_grad_(True)
+    nstep = int(z["nstep"])
+    outs, _ = po.rollout_torch(h0, p, "gs2d", nstep, range(nstep))
+    loss = (torch.cat(outs, 0) * torch.from_numpy(z["loss_weights"])).sum()
+    loss.backward()
+    assert abs(loss.item() - float(z["loss"])) <= 1e-5 * abs(float(z["loss"]))
+    assert rel_l2(h0.grad.numpy(), z["g_h0"]) <= 1e-5
+    for k, ref in grads.items():
+        assert rel_l2(p[k].grad.numpy(), ref) <= 2e-4, k
+
+
+def test_stencil_tables_match_reference_weights():
+    z, params, _ = load_golden("gs3d")
+    w = params["W_laplace.weight"].numpy()
+    np.testing.assert_allclose(w, po.laplace_stencil(3) / (100 / 48) ** 2, rtol=1e-6)
+    assert np.count_nonzero(w) == 13
+    z, params, _ = load_golden("bur3")
+    np.testing.assert_array_equal(params["dx_op.filter.weight"].numpy(), po.dx_stencil_2d())
+    np.testing.assert_array_equal(params["dy_op.filter.weight"].numpy(), po.dy_stencil_2d())
+    np.testing.assert_array_equal(params["laplace_op.filter.weight"].numpy(), po.laplace_stencil(2))
+
+
+def test_fwd_checkpoint_known_answer():
+    """with rcnn_pde.pt the Pi-block reproduces the analytic lambda-omega reaction
+    (1-A)u + A v, -A u + (1-A) v with A = u^2+v^2 (to ~1e-7 max-abs in fp64)."""
+    from tests.helpers import load_weights
+    p = load_weights("fwd")
+    g = np.random.default_rng(0)
+    u = g.uniform(-1, 1, (16, 16))
+    v = g.uniform(-1, 1, (16, 16))
+    h = torch.tensor(np.stack((u, v))[None])
+    got = po.cell_step_np(h, p, "fwd")
+    lap = lambda a: po._apply_taps_np(a, po.laplace_stencil(2)[0, 0] / 0.2 ** 2)
+    A = u * u + v * v
+    fu = float(p["DA"]) * lap(u) + (1 - A) * u + A * v
+    fv = float(p["DB"]) * lap(v) - A * u + (1 - A) * v
+    want = np.stack((u + 0.0125 * fu, v + 0.0125 * fv))[None]
+    assert np.abs(got - want).max() < 1e-6
