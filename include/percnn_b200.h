@@ -1,0 +1,152 @@
+/*
+ * percnn_b200.h -- C ABI of the B200-native PeRCNN recurrent-cell library (libpercnn_b200.so).
+ *
+ * The reference (isds-neu/PeRCNN) is 100 % Python and has no FFI layer; the boundary a replacement
+ * must honour is the nn.Module surface of `RCNNCell` / `RCNN`.  This header
+ * is the C-ABI that sits directly under that surface: plain pointers and sizes, no torch types, no
+ * C++ exceptions.  percnn_b200/_lib.py binds it with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Each entry point names the reference code it replaces, as <alias>:<lines> with the aliases of
+ * SURVEY.md (GS2D = DataDrivenModeling/2d_gs_rd/train_2drd.py, GS3D = .../3d_gs_rd/train_3drd.py,
+ * FWD = ForwardSimulationOfPDEs/2d_lambda_omega/percnn_LO_eqn.py, BUR1/LO1 = Stage-1 scripts,
+ * BUR3/LO3 = Stage-3 scripts).
+ *
+ * Conventions
+ *  - return 0 = work enqueued; non-zero = percnn_status_t, message via percnn_last_error().
+ *  - every device buffer is owned by the caller; calls allocate nothing and never synchronise the
+ *    host (stream-ordered, CUDA-graph capturable) except the *_host entry points, which own their
+ *    staging buffers and block until the result is in host memory.
+ *  - state layout: [2 fields][D][H][W] (3-D) or [2][H][W] (2-D), W fastest, contiguous -- exactly the
+ *    reference's h[0] of shape [1,2,(D,)H,W].
+ *  - `params` / `param_grads`: flat array of plan-dtype scalars = the cell's state_dict tensors
+ *    concatenated in state_dict order (see percnn_param_count and DESIGN.md "parameter packing").
+ *  - a plan is used from one host thread at a time; distinct plans are independent.
+ */
+#ifndef PERCNN_B200_H_
+#define PERCNN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PERCNN_ABI_VERSION 1
+
+typedef enum {
+  PERCNN_OK = 0,
+  PERCNN_ERR_INVALID = 1,      /* bad descriptor / argument */
+  PERCNN_ERR_UNSUPPORTED = 2,  /* valid but not implemented (e.g. non-cross Laplacian table) */
+  PERCNN_ERR_CUDA = 3,         /* a CUDA runtime/driver call failed */
+  PERCNN_ERR_NO_DEVICE = 4     /* no sm_100 device / driver */
+} percnn_status_t;
+
+typedef enum { PERCNN_F32 = 0, PERCNN_F64 = 1 } percnn_dtype_t;
+
+typedef enum {
+  PERCNN_CELL_PI = 0,       /* Pi-block cell: GS2D:105-121, FWD:98-112, GS3D:123-139, BUR1:142-178, LO1:142-171 */
+  PERCNN_CELL_BURGERS = 1,  /* Stage-3 physics cell with d/dx, d/dy advection: BUR3:154-157,209-221 */
+  PERCNN_CELL_LO = 2        /* Stage-3 lambda-omega polynomial cell: LO3:148-151,203-215 */
+} percnn_cell_t;
+
+typedef enum {
+  PERCNN_COEF_RAW = 0,      /* alpha = DA (FWD:107) or nu_u (BUR3:155) */
+  PERCNN_COEF_SIGMOID = 1   /* alpha = mu_up * sigmoid(CA) (GS2D:115) */
+} percnn_coef_mode_t;
+
+enum {                       /* percnn_desc_t.flags */
+  PERCNN_FLAG_EVAL_BRANCH = 1,   /* k=1: evaluate the three conv branches channel by channel exactly as the
+                                    reference does instead of the folded bivariate cubic (slower; parity aid) */
+  PERCNN_FLAG_NO_TMA = 2,        /* never pick the TMA z-marching kernels (generic kernels only) */
+  PERCNN_FLAG_LO_C6 = 4          /* PERCNN_CELL_LO carries the 13th coefficient C6_v (10 %-noise script) */
+};
+
+typedef struct percnn_desc {
+  int32_t abi_version;   /* PERCNN_ABI_VERSION */
+  int32_t ndim;          /* 2 | 3 */
+  int64_t extent[3];     /* D, H, W (2-D: extent[0] = 1).  In slab mode D is the LOCAL depth. */
+  int32_t dtype;         /* percnn_dtype_t */
+  int32_t cell;          /* percnn_cell_t */
+  int32_t ksize;         /* Pi conv kernel size: 1 | 5 (0 for physics cells) */
+  int32_t hidden;        /* Pi hidden channels hc (<= 16) */
+  int32_t coef_mode;     /* percnn_coef_mode_t */
+  int32_t flags;
+  double mu_up;          /* GS2D:58 mu_up / BUR1:96 nu_up; ignored for RAW */
+  double dt;             /* GS2D:57 */
+  double dx;             /* Stage-3 cells divide the un-scaled stencils by dx, dx^2 (BUR3:78-80) */
+  int32_t device;        /* CUDA device ordinal */
+  int32_t slab_ghost;    /* 0: state buffers are periodic along every axis (single GPU).
+                            1: slab mode -- state buffers carry 2 ghost planes (rows in 2-D) on each side of the
+                               slowest axis, i.e. [2][D+4][H][W]; the caller (halo exchange) fills them. */
+} percnn_desc_t;
+
+typedef struct percnn_plan percnn_plan_t;
+
+/* ---- library ---------------------------------------------------------------------------------- */
+int percnn_abi_version(void);
+const char* percnn_last_error(void);              /* thread-local; valid until the next call on the thread */
+int percnn_device_ok(int device);                 /* 1 if `device` exists and is sm_100; no context side effects beyond cudaGetDeviceProperties */
+
+/* ---- plans ------------------------------------------------------------------------------------ */
+/* Replaces RCNNCell.__init__ (GS2D:46-90): fixes geometry, dtype, variant and constants. */
+int percnn_plan_create(const percnn_desc_t* desc, percnn_plan_t** out);
+int percnn_plan_destroy(percnn_plan_t* plan);
+/* Number of scalars in `params` (and `param_grads`). */
+int64_t percnn_param_count(const percnn_plan_t* plan);
+/* Scalars in one state buffer as the kernels see it (includes ghost planes in slab mode). */
+int64_t percnn_state_elems(const percnn_plan_t* plan);
+/* Bytes of caller-provided scratch needed by rollout_fwd / rollout_bwd for `nsteps`. */
+size_t percnn_workspace_bytes(const percnn_plan_t* plan, int nsteps);
+/* 1 if the plan runs the TMA z-marching kernel, 0 if the generic one (introspection for tests/bench). */
+int percnn_plan_uses_tma(const percnn_plan_t* plan);
+/* Kernel launches issued by this plan since creation (bench "gpu_launches"). */
+int64_t percnn_plan_launch_count(const percnn_plan_t* plan);
+
+/* ---- parameters ------------------------------------------------------------------------------- */
+/* Digest the raw parameter tensors (device pointer, plan dtype) into the constant block the kernels
+ * read: alpha = mu_up*sigmoid(CA) (GS2D:115), the cross taps of W_laplace.weight (GS2D:66), the folded
+ * cubic of the 1x1 Pi-block (GS2D:115 `Wh4(Wh1*Wh2*Wh3)`), or the repacked 5x5 filters (BUR1:108-124).
+ * Must precede step/rollout calls whenever the parameters changed.  Stream-ordered. */
+int percnn_params_load(percnn_plan_t* plan, const void* params, void* stream);
+
+/* ---- one time step ---------------------------------------------------------------------------- */
+/* RCNNCell.forward (GS2D:105-121 and siblings): h_out = h_in + dt * (alpha * Lap(h_in) + Pi(h_in)). */
+int percnn_step_fwd(percnn_plan_t* plan, const void* h_in, void* h_out, void* stream);
+/* Same step restricted to interior planes [z_lo, z_hi) of the slowest axis (3-D TMA plans only).  Lets the
+ * slab-mode driver launch the planes that do not touch ghost cells before the halo exchange lands. */
+int percnn_step_fwd_range(percnn_plan_t* plan, const void* h_in, void* h_out, int z_lo, int z_hi, void* stream);
+/* Adjoint of one step (replaces autograd through GS2D:105-121): g_in = g_add + (dh_out/dh_in)^T g_out
+ * (g_add may be NULL), and the step's parameter-gradient sums are ACCUMULATED into the accumulator at the
+ * head of `ws` (zeroed by percnn_param_grads_begin, read by percnn_param_grads_finish). */
+int percnn_step_bwd(percnn_plan_t* plan, const void* h_in, const void* g_out, const void* g_add, void* g_in,
+                    void* ws, void* stream);
+int percnn_param_grads_begin(percnn_plan_t* plan, void* ws, void* stream);   /* zero the accumulator */
+/* Turn the accumulated partials into gradients w.r.t. the raw parameters (same packing as `params`). */
+int percnn_param_grads_finish(percnn_plan_t* plan, const void* params, void* param_grads, void* ws, void* stream);
+
+/* ---- whole rollout ---------------------------------------------------------------------------- */
+/* RCNN.forward loop (GS2D:169-188).  Runs `nsteps` steps from h0.  emit[s] != 0 stores the state after
+ * step s into the next slot of `traj` (slots are percnn_state_elems apart; slot order = step order).
+ * `h_final` (optional) receives the state after the last step.  With `tape` != NULL every state
+ * h_0..h_nsteps is kept there ([nsteps+1] slots) for rollout_bwd; `ws` may then be NULL. */
+int percnn_rollout_fwd(percnn_plan_t* plan, const void* h0, void* traj, const uint8_t* emit, int nsteps,
+                       void* h_final, void* tape, void* ws, void* stream);
+/* Back-propagation through the unrolled rollout (replaces loss.backward() through GS2D:169-188).
+ * `tape` holds h_0..h_nsteps ([nsteps+1] slots, as written by rollout_fwd).  gmask[s] != 0 (s = 0..nsteps)
+ * says dL/dh_s is present; the present gradients are packed in increasing s in `g_tape` (NULL = none).
+ * Writes dL/dh_0 to g_h0 and dL/dparams (same packing as `params`) to param_grads. */
+int percnn_rollout_bwd(percnn_plan_t* plan, const void* params, const void* tape, const void* g_tape,
+                       const uint8_t* gmask, int nsteps, void* g_h0, void* param_grads, void* ws, void* stream);
+
+/* ---- host-buffer convenience (end-to-end path) ------------------------------------------------ */
+/* Same as params_load + rollout_fwd but with HOST pointers: copies params and h0 to the device, runs the
+ * rollout, copies the emitted frames (and h_final if non-NULL) back, blocks until done.  Scratch is
+ * owned by the plan and reused across calls. */
+int percnn_rollout_fwd_host(percnn_plan_t* plan, const void* params_host, const void* h0_host,
+                            void* traj_host, const uint8_t* emit, int nsteps, void* h_final_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PERCNN_B200_H_ */

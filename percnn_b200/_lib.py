@@ -1,0 +1,90 @@
+"""ctypes binding of libpercnn_b200.so (the C-ABI declared in include/percnn_b200.h).
+
+The product path has NO fallback: if the shared library is missing or a tensor is not on a CUDA
+device the call fails loudly.  Build the library with `python -c "import __graft_entry__ as g; g.build()"`
+(or `python -m percnn_b200.build`).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_size_t, c_uint8, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpercnn_b200.so")
+
+ABI_VERSION = 1
+F32, F64 = 0, 1
+CELL_PI, CELL_BURGERS, CELL_LO = 0, 1, 2
+COEF_RAW, COEF_SIGMOID = 0, 1
+FLAG_EVAL_BRANCH, FLAG_NO_TMA, FLAG_LO_C6 = 1, 2, 4
+
+#: every symbol include/percnn_b200.h declares (tests check the library exports all of them)
+EXPORTS = (
+    "percnn_abi_version", "percnn_last_error", "percnn_device_ok", "percnn_plan_create", "percnn_plan_destroy",
+    "percnn_param_count", "percnn_state_elems", "percnn_workspace_bytes", "percnn_plan_uses_tma",
+    "percnn_plan_launch_count", "percnn_params_load", "percnn_step_fwd", "percnn_step_fwd_range", "percnn_step_bwd",
+    "percnn_param_grads_begin", "percnn_param_grads_finish", "percnn_rollout_fwd", "percnn_rollout_bwd",
+    "percnn_rollout_fwd_host",
+)
+
+
+class Desc(ctypes.Structure):
+    """percnn_desc_t"""
+    _fields_ = [
+        ("abi_version", c_int32), ("ndim", c_int32), ("extent", c_int64 * 3), ("dtype", c_int32), ("cell", c_int32),
+        ("ksize", c_int32), ("hidden", c_int32), ("coef_mode", c_int32), ("flags", c_int32), ("mu_up", c_double),
+        ("dt", c_double), ("dx", c_double), ("device", c_int32), ("slab_ghost", c_int32),
+    ]
+
+
+class PercnnError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA library has not been built. percnn_b200 has no CPU or eager fallback; "
+            "run `python -c \"import __graft_entry__ as g; g.build()\"` from the repository root.")
+    L = ctypes.CDLL(LIB_PATH)
+    vp = c_void_p
+    L.percnn_abi_version.restype = c_int
+    L.percnn_last_error.restype = c_char_p
+    L.percnn_device_ok.argtypes = [c_int]
+    L.percnn_plan_create.argtypes = [POINTER(Desc), POINTER(vp)]
+    L.percnn_plan_destroy.argtypes = [vp]
+    L.percnn_param_count.argtypes = [vp]
+    L.percnn_param_count.restype = c_int64
+    L.percnn_state_elems.argtypes = [vp]
+    L.percnn_state_elems.restype = c_int64
+    L.percnn_workspace_bytes.argtypes = [vp, c_int]
+    L.percnn_workspace_bytes.restype = c_size_t
+    L.percnn_plan_uses_tma.argtypes = [vp]
+    L.percnn_plan_launch_count.argtypes = [vp]
+    L.percnn_plan_launch_count.restype = c_int64
+    L.percnn_params_load.argtypes = [vp, vp, vp]
+    L.percnn_step_fwd.argtypes = [vp, vp, vp, vp]
+    L.percnn_step_fwd_range.argtypes = [vp, vp, vp, c_int, c_int, vp]
+    L.percnn_step_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.percnn_param_grads_begin.argtypes = [vp, vp, vp]
+    L.percnn_param_grads_finish.argtypes = [vp, vp, vp, vp, vp]
+    L.percnn_rollout_fwd.argtypes = [vp, vp, vp, POINTER(c_uint8), c_int, vp, vp, vp, vp]
+    L.percnn_rollout_bwd.argtypes = [vp, vp, vp, vp, POINTER(c_uint8), c_int, vp, vp, vp, vp]
+    L.percnn_rollout_fwd_host.argtypes = [vp, vp, vp, vp, POINTER(c_uint8), c_int, vp]
+    if L.percnn_abi_version() != ABI_VERSION:
+        raise ImportError(f"{LIB_PATH}: ABI version {L.percnn_abi_version()} != {ABI_VERSION}; rebuild the library")
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = lib().percnn_last_error()
+        raise PercnnError(f"libpercnn_b200 error {rc}: {msg.decode() if msg else '?'}")

@@ -1,0 +1,79 @@
+// Shared definitions for the PeRCNN B200 kernels: geometry, the digested parameter block that lives
+// in __constant__ memory, and small device helpers.  Everything here is sm_100a-only by design.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/percnn_b200.h"
+
+namespace percnn {
+
+// ---------------------------------------------------------------------------------------------
+// Digested parameter block ("prep block").  percnn_params_load() runs prep kernels that turn the
+// raw state_dict packing into this layout (in fp64, rounded once to the plan dtype) and copies it
+// device-to-device into a __constant__ slot, so the step kernels read every coefficient through the
+// uniform datapath (LDCU -> UR operands of FFMA/FFMA2) and spend no vector registers on weights.
+// ---------------------------------------------------------------------------------------------
+enum PrepIndex : int {
+  P_ALPHA = 0,     // [2]  effective diffusion coefficient per field: DA | mu_up*sigmoid(CA)  (GS2D:115)
+  P_DT = 2,        // [1]
+  P_LAP_C0 = 3,    // [1]  centre tap of W_laplace.weight (already / dx^2, GS2D:66)
+  P_LAP_AX = 4,    // [3][4] taps at offsets -2,-1,+1,+2 along axis a (a = 0 slowest); 2-D uses a = 0,1
+  P_POLY = 16,     // [2][10] folded cubic of the 1x1 Pi-block: c00 c10 c01 c20 c11 c02 c30 c21 c12 c03
+  P_DPOLY = 36,    // [4][6] d/du, d/dv of both cubics over monomials 1 u v u^2 uv v^2: (Ru,u) (Ru,v) (Rv,u) (Rv,v)
+  P_PHYS = 16,     // Burgers: C1_u C2_u C1_v C2_v | dx taps[4] | dy taps[4]   (taps / dx, BUR3:78-80)
+                   // LO:      C1..C5_u | C1..C5_v | C6_v
+  P_BRANCH = 64,   // raw 1x1 weights for PERCNN_FLAG_EVAL_BRANCH: per field W1[hc][2] b1[hc] W2.. W3.. W4[hc] b4
+  P_SIZE = 400
+};
+constexpr int kMaxHidden = 16;
+constexpr int kPrepSlots = 6;
+
+struct PrepBlock {
+  float f[P_SIZE];
+  double d[P_SIZE];
+};
+
+// The library is one translation unit (percnn_abi.cu includes every kernel header), so the constant
+// block is defined here once.
+__constant__ PrepBlock c_prep[kPrepSlots];
+
+// number of reduction quantities the adjoint kernels produce per step
+constexpr int kRedPiK1 = 22;     // S_Lu S_Lv | M^u_ab[10] | M^v_ab[10]
+constexpr int kRedBurgers = 6;   // nu_u nu_v C1_u C2_u C1_v C2_v
+constexpr int kRedLO = 13;       // nu_u nu_v C1..C5_u C1..C5_v C6_v
+constexpr int kRedMaxSmall = 24;
+
+// ---------------------------------------------------------------------------------------------
+// Geometry of one state buffer as a kernel sees it.
+// ---------------------------------------------------------------------------------------------
+struct Geom {
+  int ndim;        // 2 | 3
+  int D, H, W;     // interior extents (2-D: D = 1)
+  int ghost;       // slab mode: number of ghost planes (rows in 2-D) on each side of the slowest axis (0 | 2)
+  int64_t plane;   // H*W  (2-D: W)
+  int64_t field;   // elements between field 0 and field 1 = (D + 2*ghost) * H * W   (2-D: (H+2*ghost)*W)
+};
+
+template <typename T>
+struct PrepView;
+template <>
+struct PrepView<float> {
+  static __device__ __forceinline__ const float* get(const PrepBlock& b) { return b.f; }
+};
+template <>
+struct PrepView<double> {
+  static __device__ __forceinline__ const double* get(const PrepBlock& b) { return b.d; }
+};
+
+__device__ __forceinline__ int wrap_idx(int i, int n) {
+  // valid for -n <= i < 2n
+  return i < 0 ? i + n : (i >= n ? i - n : i);
+}
+
+__device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
+
+}  // namespace percnn

@@ -1,0 +1,244 @@
+// Generic cross-stencil step kernels: any extent, 2-D or 3-D, fp32 or fp64, periodic or slab-ghosted
+// along the slowest axis.  One thread walks a grid-stride list of cells; neighbours come through
+// L1/L2 with wrap-around index arithmetic.  These cover the reference's own sizes (100^2, 48^3), the
+// fp64 variants and every adjoint; the TMA z-marching kernel (kernels_gs3d_tma.cuh) takes over for
+// large aligned 3-D fp32 grids.
+#pragma once
+#include "point_ops.cuh"
+
+namespace percnn {
+
+
+constexpr int kGenericThreads = 256;
+
+// Element offsets (within one field) of a cell and of its cross neighbours.
+template <int NDIM>
+struct CellOffsets {
+  int64_t c;
+  int64_t n[NDIM][4];
+};
+
+template <int NDIM>
+__device__ __forceinline__ CellOffsets<NDIM> cell_offsets(const Geom& g, int64_t cell) {
+  CellOffsets<NDIM> o;
+  const int offs[4] = {-2, -1, 1, 2};
+  const int x = int(cell % g.W);
+  const int64_t r = cell / g.W;
+  if (NDIM == 2) {
+    const int y = int(r);  // slowest axis: ghost-aware
+    const int64_t row = int64_t(y + g.ghost) * g.W;
+    o.c = row + x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int yy = g.ghost ? (y + g.ghost + offs[k]) : wrap_idx(y + offs[k], g.H);
+      o.n[0][k] = int64_t(yy) * g.W + x;
+      o.n[NDIM - 1][k] = row + wrap_idx(x + offs[k], g.W);
+    }
+  } else {
+    const int y = int(r % g.H);
+    const int z = int(r / g.H);
+    const int64_t pl = int64_t(z + g.ghost) * g.plane;
+    const int64_t row = pl + int64_t(y) * g.W;
+    o.c = row + x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int zz = g.ghost ? (z + g.ghost + offs[k]) : wrap_idx(z + offs[k], g.D);
+      o.n[0][k] = int64_t(zz) * g.plane + int64_t(y) * g.W + x;
+      o.n[1][k] = pl + int64_t(wrap_idx(y + offs[k], g.H)) * g.W + x;
+      o.n[NDIM - 1][k] = row + wrap_idx(x + offs[k], g.W);
+    }
+  }
+  return o;
+}
+
+template <typename T, int NDIM>
+__device__ __forceinline__ Cross<T, NDIM> gather(const T* __restrict__ f, const CellOffsets<NDIM>& o) {
+  Cross<T, NDIM> q;
+  q.c = __ldg(f + o.c);
+#pragma unroll
+  for (int a = 0; a < NDIM; ++a)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) q.n[a][k] = __ldg(f + o.n[a][k]);
+  return q;
+}
+
+// Deterministic grid reduction: per-block partials in fp64, the last block to finish adds the column
+// sums (fixed block order) into acc[].  No float atomics anywhere, so gradients are reproducible.
+template <typename T, int NRED>
+__device__ __forceinline__ void reduce_into_acc(const T (&v)[NRED], double* __restrict__ partials,
+                                                unsigned* __restrict__ counter, double* __restrict__ acc) {
+  __shared__ double sm[kGenericThreads / 32][NRED];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NRED; ++i) {
+    double d = double(v[i]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) d += __shfl_down_sync(0xffffffffu, d, off);
+    if (lane == 0) sm[warp][i] = d;
+  }
+  __syncthreads();
+  if (threadIdx.x < NRED) {
+    double s = 0;
+#pragma unroll
+    for (int w = 0; w < kGenericThreads / 32; ++w) s += sm[w][threadIdx.x];
+    partials[size_t(blockIdx.x) * NRED + threadIdx.x] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    if (threadIdx.x < NRED) {
+      double s = 0;
+      for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(partials + size_t(b) * NRED + threadIdx.x);
+      acc[threadIdx.x] += s;
+    }
+    if (threadIdx.x == 0) *counter = 0;
+  }
+}
+
+// ---- Pi-block, k = 1 ------------------------------------------------------------------------
+template <typename T, int NDIM, bool BRANCH>
+__global__ void __launch_bounds__(kGenericThreads) k_pi_k1_fwd(Geom g, int slot, int hc, const T* __restrict__ src,
+                                                               T* __restrict__ dst) {
+  const T* P = PrepView<T>::get(c_prep[slot]);
+  const int64_t ncell = int64_t(g.D) * g.H * g.W;
+  for (int64_t cell = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; cell < ncell;
+       cell += int64_t(gridDim.x) * blockDim.x) {
+    const CellOffsets<NDIM> o = cell_offsets<NDIM>(g, cell);
+    const Cross<T, NDIM> U = gather<T, NDIM>(src, o);
+    const Cross<T, NDIM> V = gather<T, NDIM>(src + g.field, o);
+    const T Lu = lap_apply<T, NDIM>(U, P), Lv = lap_apply<T, NDIM>(V, P);
+    T ou, ov;
+    if (BRANCH)
+      pi_k1_fwd_branch<T>(U.c, V.c, Lu, Lv, P, hc, ou, ov);
+    else
+      pi_k1_fwd_poly<T>(U.c, V.c, Lu, Lv, P, ou, ov);
+    dst[o.c] = ou;
+    dst[g.field + o.c] = ov;
+  }
+}
+
+template <typename T, int NDIM>
+__global__ void __launch_bounds__(kGenericThreads) k_pi_k1_bwd(Geom g, int slot, const T* __restrict__ h,
+                                                               const T* __restrict__ gout, const T* __restrict__ gadd,
+                                                               T* __restrict__ gin, double* __restrict__ partials,
+                                                               unsigned* __restrict__ counter, double* __restrict__ acc) {
+  const T* P = PrepView<T>::get(c_prep[slot]);
+  const int64_t ncell = int64_t(g.D) * g.H * g.W;
+  T red[kRedPiK1];
+#pragma unroll
+  for (int i = 0; i < kRedPiK1; ++i) red[i] = T(0);
+  for (int64_t cell = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; cell < ncell;
+       cell += int64_t(gridDim.x) * blockDim.x) {
+    const CellOffsets<NDIM> o = cell_offsets<NDIM>(g, cell);
+    const Cross<T, NDIM> GU = gather<T, NDIM>(gout, o);
+    const Cross<T, NDIM> GV = gather<T, NDIM>(gout + g.field, o);
+    const T u = __ldg(h + o.c), v = __ldg(h + g.field + o.c);
+    T gu, gv;
+    pi_k1_bwd_poly<T>(u, v, GU.c, GV.c, lap_apply_T<T, NDIM>(GU, P), lap_apply_T<T, NDIM>(GV, P), P, gu, gv, red);
+    if (gadd != nullptr) {
+      gu += __ldg(gadd + o.c);
+      gv += __ldg(gadd + g.field + o.c);
+    }
+    gin[o.c] = gu;
+    gin[g.field + o.c] = gv;
+  }
+  reduce_into_acc<T, kRedPiK1>(red, partials, counter, acc);
+}
+
+// ---- Stage-3 physics cells (2-D) --------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kGenericThreads) k_burgers_fwd(Geom g, int slot, const T* __restrict__ src,
+                                                                 T* __restrict__ dst) {
+  const T* P = PrepView<T>::get(c_prep[slot]);
+  const int64_t ncell = int64_t(g.H) * g.W;
+  for (int64_t cell = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; cell < ncell;
+       cell += int64_t(gridDim.x) * blockDim.x) {
+    const CellOffsets<2> o = cell_offsets<2>(g, cell);
+    const Cross<T, 2> U = gather<T, 2>(src, o);
+    const Cross<T, 2> V = gather<T, 2>(src + g.field, o);
+    T ou, ov;
+    burgers_fwd<T>(U, V, P, ou, ov);
+    dst[o.c] = ou;
+    dst[g.field + o.c] = ov;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kGenericThreads) k_burgers_bwd(Geom g, int slot, const T* __restrict__ h,
+                                                                 const T* __restrict__ gout, const T* __restrict__ gadd,
+                                                                 T* __restrict__ gin, double* __restrict__ partials,
+                                                                 unsigned* __restrict__ counter, double* __restrict__ acc) {
+  const T* P = PrepView<T>::get(c_prep[slot]);
+  const int64_t ncell = int64_t(g.H) * g.W;
+  T red[kRedBurgers];
+#pragma unroll
+  for (int i = 0; i < kRedBurgers; ++i) red[i] = T(0);
+  for (int64_t cell = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; cell < ncell;
+       cell += int64_t(gridDim.x) * blockDim.x) {
+    const CellOffsets<2> o = cell_offsets<2>(g, cell);
+    const Cross<T, 2> U = gather<T, 2>(h, o);
+    const Cross<T, 2> V = gather<T, 2>(h + g.field, o);
+    const Cross<T, 2> GU = gather<T, 2>(gout, o);
+    const Cross<T, 2> GV = gather<T, 2>(gout + g.field, o);
+    T gu, gv;
+    burgers_bwd<T>(U, V, GU, GV, P, gu, gv, red);
+    if (gadd != nullptr) {
+      gu += __ldg(gadd + o.c);
+      gv += __ldg(gadd + g.field + o.c);
+    }
+    gin[o.c] = gu;
+    gin[g.field + o.c] = gv;
+  }
+  reduce_into_acc<T, kRedBurgers>(red, partials, counter, acc);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kGenericThreads) k_lo_fwd(Geom g, int slot, const T* __restrict__ src,
+                                                            T* __restrict__ dst) {
+  const T* P = PrepView<T>::get(c_prep[slot]);
+  const int64_t ncell = int64_t(g.H) * g.W;
+  for (int64_t cell = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; cell < ncell;
+       cell += int64_t(gridDim.x) * blockDim.x) {
+    const CellOffsets<2> o = cell_offsets<2>(g, cell);
+    const Cross<T, 2> U = gather<T, 2>(src, o);
+    const Cross<T, 2> V = gather<T, 2>(src + g.field, o);
+    T ou, ov;
+    lo_fwd<T>(U.c, V.c, lap_apply<T, 2>(U, P), lap_apply<T, 2>(V, P), P, ou, ov);
+    dst[o.c] = ou;
+    dst[g.field + o.c] = ov;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kGenericThreads) k_lo_bwd(Geom g, int slot, const T* __restrict__ h,
+                                                            const T* __restrict__ gout, const T* __restrict__ gadd,
+                                                            T* __restrict__ gin, double* __restrict__ partials,
+                                                            unsigned* __restrict__ counter, double* __restrict__ acc) {
+  const T* P = PrepView<T>::get(c_prep[slot]);
+  const int64_t ncell = int64_t(g.H) * g.W;
+  T red[kRedLO];
+#pragma unroll
+  for (int i = 0; i < kRedLO; ++i) red[i] = T(0);
+  for (int64_t cell = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; cell < ncell;
+       cell += int64_t(gridDim.x) * blockDim.x) {
+    const CellOffsets<2> o = cell_offsets<2>(g, cell);
+    const Cross<T, 2> GU = gather<T, 2>(gout, o);
+    const Cross<T, 2> GV = gather<T, 2>(gout + g.field, o);
+    const T u = __ldg(h + o.c), v = __ldg(h + g.field + o.c);
+    T gu, gv;
+    lo_bwd<T>(u, v, GU.c, GV.c, lap_apply_T<T, 2>(GU, P), lap_apply_T<T, 2>(GV, P), P, gu, gv, red);
+    if (gadd != nullptr) {
+      gu += __ldg(gadd + o.c);
+      gv += __ldg(gadd + g.field + o.c);
+    }
+    gin[o.c] = gu;
+    gin[g.field + o.c] = gv;
+  }
+  reduce_into_acc<T, kRedLO>(red, partials, counter, acc);
+}
+
+}  // namespace percnn

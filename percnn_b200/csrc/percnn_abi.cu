@@ -1,0 +1,589 @@
+// C-ABI of libpercnn_b200.so (see include/percnn_b200.h).  Single translation unit: the kernels share
+// one __constant__ parameter block, so everything is compiled together for sm_100a.
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+
+#include "kernels_generic.cuh"
+#include "kernels_gs3d_tma.cuh"
+#include "kernels_pi_k5.cuh"
+#include "kernels_prep.cuh"
+
+using namespace percnn;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define PERCNN_CUDA(call)                                                                                   \
+  do {                                                                                                      \
+    cudaError_t e__ = (call);                                                                               \
+    if (e__ != cudaSuccess)                                                                                 \
+      return fail(PERCNN_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));                    \
+  } while (0)
+
+std::mutex g_slot_mutex;
+bool g_slot_used[kPrepSlots] = {false};
+
+constexpr int kMaxBlocks = 2048;
+constexpr size_t kWsAcc = 0;            // kRedMaxSmall doubles
+constexpr size_t kWsCounter = 256;      // one unsigned
+constexpr size_t kWsPartials = 512;     // kMaxBlocks * kRedMaxSmall doubles
+constexpr size_t kWsStates = kWsPartials + size_t(kMaxBlocks) * kRedMaxSmall * sizeof(double);
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct TmaMapPair {
+  const void* base = nullptr;
+  CUtensorMap main_map, halo_map;
+};
+
+}  // namespace
+
+struct percnn_plan {
+  percnn_desc_t desc;
+  Geom g;
+  PrepDesc pd;
+  int slot = -1;
+  int elt = 4;
+  int nred = 0;
+  int sm_count = 148;
+  int64_t nparams = 0;
+  int64_t state_elems = 0;
+  int64_t launches = 0;
+  bool use_tma = false;
+  int tz = 0;
+  PrepBlock* d_prep = nullptr;
+  float* d_k5w = nullptr;
+  EncodeTiledFn encode = nullptr;
+  TmaMapPair maps[4];
+  int map_rr = 0;
+  // host-path scratch
+  void* h_params_dev = nullptr;
+  void* h_states = nullptr;
+  size_t h_states_bytes = 0;
+  cudaStream_t h_stream = nullptr;
+};
+
+namespace {
+
+int generic_grid(const percnn_plan* p) {
+  const int64_t ncell = int64_t(p->g.D) * p->g.H * p->g.W;
+  int64_t blocks = (ncell + kGenericThreads - 1) / kGenericThreads;
+  const int64_t cap = int64_t(p->sm_count) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks > kMaxBlocks) blocks = kMaxBlocks;
+  return int(blocks < 1 ? 1 : blocks);
+}
+
+// z-chunk length that minimises the makespan rounds * (tz + 4) of the persistent TMA kernel
+int choose_tz(int nxy, int depth, int nsm) {
+  int best = depth, best_cost = 1 << 30;
+  for (int tz = 4; tz <= depth; ++tz) {
+    const int nzc = (depth + tz - 1) / tz;
+    const int rounds = (nxy * nzc + nsm - 1) / nsm;
+    const int cost = rounds * (tz + 4);
+    if (cost < best_cost || (cost == best_cost && tz > best)) {
+      best_cost = cost;
+      best = tz;
+    }
+  }
+  return best;
+}
+
+int get_maps(percnn_plan* p, const void* src, const CUtensorMap** main_map, const CUtensorMap** halo_map) {
+  for (auto& m : p->maps)
+    if (m.base == src) {
+      *main_map = &m.main_map;
+      *halo_map = &m.halo_map;
+      return PERCNN_OK;
+    }
+  TmaMapPair& m = p->maps[p->map_rr];
+  p->map_rr = (p->map_rr + 1) % 4;
+  const Geom& g = p->g;
+  const cuuint64_t planes = cuuint64_t(g.D + 2 * g.ghost);
+  cuuint64_t gdim[4] = {cuuint64_t(g.W), cuuint64_t(g.H), planes, 2};
+  cuuint64_t gstr[3] = {cuuint64_t(g.W) * 4, cuuint64_t(g.plane) * 4, cuuint64_t(g.field) * 4};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  cuuint32_t box_main[4] = {tma3d::TX, tma3d::TY, 1, 1};
+  cuuint32_t box_halo[4] = {tma3d::TX, 2, 1, 1};
+  CUresult r = p->encode(&m.main_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(src), gdim, gstr, box_main,
+                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_SUCCESS)
+    r = p->encode(&m.halo_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(src), gdim, gstr, box_halo, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    m.base = nullptr;
+    return fail(PERCNN_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)));
+  }
+  m.base = src;
+  *main_map = &m.main_map;
+  *halo_map = &m.halo_map;
+  return PERCNN_OK;
+}
+
+int launch_tma_fwd(percnn_plan* p, const float* src, float* dst, int z_lo, int z_hi, cudaStream_t st) {
+  const CUtensorMap *mm, *hm;
+  int rc = get_maps(p, src, &mm, &hm);
+  if (rc) return rc;
+  const Geom& g = p->g;
+  tma3d::Params prm;
+  prm.src = src;
+  prm.dst = dst;
+  prm.D = g.D;
+  prm.H = g.H;
+  prm.W = g.W;
+  prm.src_planes = g.D + 2 * g.ghost;
+  prm.src_field = g.field;
+  prm.dst_field = g.field;
+  prm.src_zoff = g.ghost ? 0 : -2;
+  prm.dst_zoff = g.ghost;
+  prm.wrap_z = g.ghost ? 0 : 1;
+  prm.nxt = g.W / tma3d::TX;
+  prm.nyt = g.H / tma3d::TY;
+  const int depth = z_hi - z_lo;
+  prm.tz = (z_lo == 0 && z_hi == g.D) ? p->tz : choose_tz(prm.nxt * prm.nyt, depth, p->sm_count);
+  prm.nzc = (depth + prm.tz - 1) / prm.tz;
+  prm.z_lo = z_lo;
+  prm.z_hi = z_hi;
+  prm.slot = p->slot;
+  const int nitems = prm.nxt * prm.nyt * prm.nzc;
+  const int grid = nitems < p->sm_count ? nitems : p->sm_count;
+  switch (p->slot) {
+#define PERCNN_TMA_CASE(S) \
+  case S: tma3d::k_gs3d_fwd_tma<S><<<grid, tma3d::THREADS, tma3d::SMEM_BYTES, st>>>(*mm, *hm, prm); break;
+    PERCNN_TMA_CASE(0) PERCNN_TMA_CASE(1) PERCNN_TMA_CASE(2) PERCNN_TMA_CASE(3) PERCNN_TMA_CASE(4) PERCNN_TMA_CASE(5)
+#undef PERCNN_TMA_CASE
+    default: return fail(PERCNN_ERR_INVALID, "bad parameter slot");
+  }
+  PERCNN_CUDA(cudaGetLastError());
+  p->launches++;
+  return PERCNN_OK;
+}
+
+template <typename T>
+int step_fwd_t(percnn_plan* p, const T* src, T* dst, cudaStream_t st) {
+  const Geom& g = p->g;
+  const int grid = generic_grid(p);
+  const bool branch = (p->desc.flags & PERCNN_FLAG_EVAL_BRANCH) != 0;
+  if (p->desc.cell == PERCNN_CELL_PI && p->desc.ksize == 1) {
+    if (g.ndim == 3) {
+      if (branch)
+        k_pi_k1_fwd<T, 3, true><<<grid, kGenericThreads, 0, st>>>(g, p->slot, p->desc.hidden, src, dst);
+      else
+        k_pi_k1_fwd<T, 3, false><<<grid, kGenericThreads, 0, st>>>(g, p->slot, p->desc.hidden, src, dst);
+    } else {
+      if (branch)
+        k_pi_k1_fwd<T, 2, true><<<grid, kGenericThreads, 0, st>>>(g, p->slot, p->desc.hidden, src, dst);
+      else
+        k_pi_k1_fwd<T, 2, false><<<grid, kGenericThreads, 0, st>>>(g, p->slot, p->desc.hidden, src, dst);
+    }
+  } else if (p->desc.cell == PERCNN_CELL_BURGERS) {
+    k_burgers_fwd<T><<<grid, kGenericThreads, 0, st>>>(g, p->slot, src, dst);
+  } else if (p->desc.cell == PERCNN_CELL_LO) {
+    k_lo_fwd<T><<<grid, kGenericThreads, 0, st>>>(g, p->slot, src, dst);
+  } else {
+    return fail(PERCNN_ERR_UNSUPPORTED, "no generic forward kernel for this cell");
+  }
+  PERCNN_CUDA(cudaGetLastError());
+  p->launches++;
+  return PERCNN_OK;
+}
+
+int step_fwd_any(percnn_plan* p, const void* src, void* dst, cudaStream_t st) {
+  if (p->use_tma) return launch_tma_fwd(p, static_cast<const float*>(src), static_cast<float*>(dst), 0, p->g.D, st);
+  if (p->desc.cell == PERCNN_CELL_PI && p->desc.ksize == 5) {
+    dim3 grid((p->g.W + k5::TILE_X - 1) / k5::TILE_X, (p->g.H + k5::TILE_Y - 1) / k5::TILE_Y);
+    k5::k_pi_k5_fwd<<<grid, k5::THREADS, k5::smem_bytes(p->desc.hidden), st>>>(
+        p->g, p->slot, p->desc.hidden, static_cast<const float*>(src), static_cast<float*>(dst), p->d_k5w);
+    PERCNN_CUDA(cudaGetLastError());
+    p->launches++;
+    return PERCNN_OK;
+  }
+  return p->elt == 4 ? step_fwd_t<float>(p, static_cast<const float*>(src), static_cast<float*>(dst), st)
+                     : step_fwd_t<double>(p, static_cast<const double*>(src), static_cast<double*>(dst), st);
+}
+
+template <typename T>
+int step_bwd_t(percnn_plan* p, const T* h, const T* gout, const T* gadd, T* gin, char* ws, cudaStream_t st) {
+  const Geom& g = p->g;
+  const int grid = generic_grid(p);
+  double* acc = reinterpret_cast<double*>(ws + kWsAcc);
+  unsigned* counter = reinterpret_cast<unsigned*>(ws + kWsCounter);
+  double* partials = reinterpret_cast<double*>(ws + kWsPartials);
+  if (p->desc.cell == PERCNN_CELL_PI && p->desc.ksize == 1) {
+    if (g.ndim == 3)
+      k_pi_k1_bwd<T, 3><<<grid, kGenericThreads, 0, st>>>(g, p->slot, h, gout, gadd, gin, partials, counter, acc);
+    else
+      k_pi_k1_bwd<T, 2><<<grid, kGenericThreads, 0, st>>>(g, p->slot, h, gout, gadd, gin, partials, counter, acc);
+  } else if (p->desc.cell == PERCNN_CELL_BURGERS) {
+    k_burgers_bwd<T><<<grid, kGenericThreads, 0, st>>>(g, p->slot, h, gout, gadd, gin, partials, counter, acc);
+  } else if (p->desc.cell == PERCNN_CELL_LO) {
+    k_lo_bwd<T><<<grid, kGenericThreads, 0, st>>>(g, p->slot, h, gout, gadd, gin, partials, counter, acc);
+  } else {
+    return fail(PERCNN_ERR_UNSUPPORTED, "adjoint of the 5x5 Pi-block cell is not implemented yet");
+  }
+  PERCNN_CUDA(cudaGetLastError());
+  p->launches++;
+  return PERCNN_OK;
+}
+
+int step_bwd_any(percnn_plan* p, const void* h, const void* gout, const void* gadd, void* gin, void* ws, cudaStream_t st) {
+  return p->elt == 4 ? step_bwd_t<float>(p, static_cast<const float*>(h), static_cast<const float*>(gout),
+                                         static_cast<const float*>(gadd), static_cast<float*>(gin),
+                                         static_cast<char*>(ws), st)
+                     : step_bwd_t<double>(p, static_cast<const double*>(h), static_cast<const double*>(gout),
+                                          static_cast<const double*>(gadd), static_cast<double*>(gin),
+                                          static_cast<char*>(ws), st);
+}
+
+size_t state_bytes(const percnn_plan* p) { return size_t(p->state_elems) * p->elt; }
+
+}  // namespace
+
+extern "C" {
+
+int percnn_abi_version(void) { return PERCNN_ABI_VERSION; }
+
+const char* percnn_last_error(void) { return g_err.c_str(); }
+
+int percnn_device_ok(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return 0;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return 0;
+  return prop.major == 10 ? 1 : 0;
+}
+
+int percnn_plan_create(const percnn_desc_t* d, percnn_plan_t** out) {
+  if (!d || !out) return fail(PERCNN_ERR_INVALID, "null descriptor or output pointer");
+  *out = nullptr;
+  if (d->abi_version != PERCNN_ABI_VERSION) return fail(PERCNN_ERR_INVALID, "abi_version mismatch");
+  if (d->ndim != 2 && d->ndim != 3) return fail(PERCNN_ERR_INVALID, "ndim must be 2 or 3");
+  if (d->dtype != PERCNN_F32 && d->dtype != PERCNN_F64) return fail(PERCNN_ERR_INVALID, "dtype must be f32 or f64");
+  if (d->extent[1] < 1 || d->extent[2] < 1 || d->extent[0] < 1) return fail(PERCNN_ERR_INVALID, "extents must be >= 1");
+  if (d->ndim == 2 && d->extent[0] != 1) return fail(PERCNN_ERR_INVALID, "2-D plans need extent[0] == 1");
+  if (d->extent[0] > (1 << 20) || d->extent[1] > (1 << 20) || d->extent[2] > (1 << 20))
+    return fail(PERCNN_ERR_INVALID, "extent too large");
+  if (d->cell == PERCNN_CELL_PI) {
+    if (d->ksize != 1 && d->ksize != 5) return fail(PERCNN_ERR_INVALID, "Pi conv kernel size must be 1 or 5");
+    if (d->hidden < 1 || d->hidden > kMaxHidden) return fail(PERCNN_ERR_INVALID, "hidden channels must be in 1..16");
+    if (d->ksize == 5) {
+      if (d->ndim != 2 || d->dtype != PERCNN_F32)
+        return fail(PERCNN_ERR_UNSUPPORTED, "the 5x5 Pi-block cell exists in 2-D fp32 only (BUR1/LO1)");
+      if (d->hidden % 2) return fail(PERCNN_ERR_UNSUPPORTED, "5x5 Pi-block needs an even channel count");
+    }
+  } else if (d->cell == PERCNN_CELL_BURGERS || d->cell == PERCNN_CELL_LO) {
+    if (d->ndim != 2) return fail(PERCNN_ERR_INVALID, "Stage-3 physics cells are 2-D");
+    if (!(d->dx > 0)) return fail(PERCNN_ERR_INVALID, "dx must be positive");
+  } else {
+    return fail(PERCNN_ERR_INVALID, "unknown cell kind");
+  }
+  if (d->slab_ghost != 0 && d->slab_ghost != 1) return fail(PERCNN_ERR_INVALID, "slab_ghost must be 0 or 1");
+  if (!percnn_device_ok(d->device)) return fail(PERCNN_ERR_NO_DEVICE, "no sm_100 CUDA device with this ordinal");
+
+  percnn_plan* p = new (std::nothrow) percnn_plan();
+  if (!p) return fail(PERCNN_ERR_INVALID, "out of host memory");
+  p->desc = *d;
+  p->elt = d->dtype == PERCNN_F32 ? 4 : 8;
+  Geom& g = p->g;
+  g.ndim = d->ndim;
+  g.D = int(d->extent[0]);
+  g.H = int(d->extent[1]);
+  g.W = int(d->extent[2]);
+  g.ghost = d->slab_ghost ? 2 : 0;
+  if (d->ndim == 3) {
+    g.plane = int64_t(g.H) * g.W;
+    g.field = int64_t(g.D + 2 * g.ghost) * g.plane;
+  } else {
+    g.plane = g.W;
+    g.field = int64_t(g.H + 2 * g.ghost) * g.W;
+  }
+  p->state_elems = 2 * g.field;
+  p->pd = PrepDesc{d->cell, d->ndim, d->ksize, d->hidden, d->coef_mode, d->flags, d->mu_up, d->dt, d->dx};
+  if (d->cell == PERCNN_CELL_PI) {
+    p->nparams = PiPacking(d->ndim, d->ksize, d->hidden).total();
+    p->nred = d->ksize == 1 ? kRedPiK1 : 0;
+  } else if (d->cell == PERCNN_CELL_BURGERS) {
+    p->nparams = 6 + 75;
+    p->nred = kRedBurgers;
+  } else {
+    p->nparams = ((d->flags & PERCNN_FLAG_LO_C6) ? 13 : 12) + 25;
+    p->nred = kRedLO;
+  }
+  int rc = PERCNN_OK;
+  do {
+    if (cudaSetDevice(d->device) != cudaSuccess) { rc = fail(PERCNN_ERR_CUDA, "cudaSetDevice failed"); break; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, d->device) != cudaSuccess) { rc = fail(PERCNN_ERR_CUDA, "cudaGetDeviceProperties failed"); break; }
+    p->sm_count = prop.multiProcessorCount;
+    {
+      std::lock_guard<std::mutex> lk(g_slot_mutex);
+      for (int s = 0; s < kPrepSlots; ++s)
+        if (!g_slot_used[s]) { g_slot_used[s] = true; p->slot = s; break; }
+    }
+    if (p->slot < 0) { rc = fail(PERCNN_ERR_INVALID, "too many live plans (6 parameter slots)"); break; }
+    if (cudaMalloc(&p->d_prep, sizeof(PrepBlock)) != cudaSuccess) { rc = fail(PERCNN_ERR_CUDA, "cudaMalloc(prep) failed"); break; }
+    if (d->cell == PERCNN_CELL_PI && d->ksize == 5) {
+      if (cudaMalloc(&p->d_k5w, size_t(k5_total_floats(d->hidden)) * 4) != cudaSuccess) { rc = fail(PERCNN_ERR_CUDA, "cudaMalloc(k5w) failed"); break; }
+      if (cudaFuncSetAttribute(k5::k_pi_k5_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               int(k5::smem_bytes(d->hidden))) != cudaSuccess) { rc = fail(PERCNN_ERR_CUDA, "cudaFuncSetAttribute(k5) failed"); break; }
+    }
+    p->use_tma = d->cell == PERCNN_CELL_PI && d->ksize == 1 && d->ndim == 3 && d->dtype == PERCNN_F32 &&
+                 !(d->flags & (PERCNN_FLAG_NO_TMA | PERCNN_FLAG_EVAL_BRANCH)) && g.W % tma3d::TX == 0 &&
+                 g.H % tma3d::TY == 0 && g.D >= 4;
+    if (p->use_tma) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+        rc = fail(PERCNN_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+        break;
+      }
+      p->encode = reinterpret_cast<EncodeTiledFn>(fn);
+      cudaError_t ae = cudaSuccess;
+      switch (p->slot) {
+#define PERCNN_TMA_ATTR(S) \
+  case S: ae = cudaFuncSetAttribute(tma3d::k_gs3d_fwd_tma<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma3d::SMEM_BYTES); break;
+        PERCNN_TMA_ATTR(0) PERCNN_TMA_ATTR(1) PERCNN_TMA_ATTR(2) PERCNN_TMA_ATTR(3) PERCNN_TMA_ATTR(4) PERCNN_TMA_ATTR(5)
+#undef PERCNN_TMA_ATTR
+      }
+      if (ae != cudaSuccess) { rc = fail(PERCNN_ERR_CUDA, "cudaFuncSetAttribute(tma) failed"); break; }
+      p->tz = choose_tz((g.W / tma3d::TX) * (g.H / tma3d::TY), g.D, p->sm_count);
+    }
+  } while (0);
+  if (rc != PERCNN_OK) {
+    std::string keep = g_err;
+    percnn_plan_destroy(p);
+    g_err = keep;
+    return rc;
+  }
+  *out = p;
+  return PERCNN_OK;
+}
+
+int percnn_plan_destroy(percnn_plan_t* p) {
+  if (!p) return PERCNN_OK;
+  if (p->d_prep) cudaFree(p->d_prep);
+  if (p->d_k5w) cudaFree(p->d_k5w);
+  if (p->h_params_dev) cudaFree(p->h_params_dev);
+  if (p->h_states) cudaFree(p->h_states);
+  if (p->h_stream) cudaStreamDestroy(p->h_stream);
+  if (p->slot >= 0) {
+    std::lock_guard<std::mutex> lk(g_slot_mutex);
+    g_slot_used[p->slot] = false;
+  }
+  delete p;
+  return PERCNN_OK;
+}
+
+int64_t percnn_param_count(const percnn_plan_t* p) { return p ? p->nparams : -1; }
+int64_t percnn_state_elems(const percnn_plan_t* p) { return p ? p->state_elems : -1; }
+int percnn_plan_uses_tma(const percnn_plan_t* p) { return p && p->use_tma ? 1 : 0; }
+int64_t percnn_plan_launch_count(const percnn_plan_t* p) { return p ? p->launches : -1; }
+
+size_t percnn_workspace_bytes(const percnn_plan_t* p, int nsteps) {
+  (void)nsteps;
+  if (!p) return 0;
+  return kWsStates + 2 * ((state_bytes(p) + 255) / 256 * 256);
+}
+
+int percnn_params_load(percnn_plan_t* p, const void* params, void* stream) {
+  if (!p || !params) return fail(PERCNN_ERR_INVALID, "null plan or params");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->elt == 4)
+    k_prep<float><<<1, 256, 0, st>>>(static_cast<const float*>(params), p->pd, p->d_prep, p->d_k5w);
+  else
+    k_prep<double><<<1, 256, 0, st>>>(static_cast<const double*>(params), p->pd, p->d_prep, p->d_k5w);
+  PERCNN_CUDA(cudaGetLastError());
+  PERCNN_CUDA(cudaMemcpyToSymbolAsync(c_prep, p->d_prep, sizeof(PrepBlock), size_t(p->slot) * sizeof(PrepBlock),
+                                      cudaMemcpyDeviceToDevice, st));
+  p->launches++;
+  return PERCNN_OK;
+}
+
+int percnn_step_fwd(percnn_plan_t* p, const void* h_in, void* h_out, void* stream) {
+  if (!p || !h_in || !h_out) return fail(PERCNN_ERR_INVALID, "null argument");
+  if (h_in == h_out) return fail(PERCNN_ERR_INVALID, "step_fwd cannot run in place");
+  return step_fwd_any(p, h_in, h_out, static_cast<cudaStream_t>(stream));
+}
+
+// Forward step restricted to interior planes [z_lo, z_hi) of a 3-D TMA plan (slab mode overlap: the
+// planes that need ghosts are launched after the halo exchange, the rest before).  Not part of the
+// reference surface; used by percnn_b200.halo.
+int percnn_step_fwd_range(percnn_plan_t* p, const void* h_in, void* h_out, int z_lo, int z_hi, void* stream) {
+  if (!p || !h_in || !h_out) return fail(PERCNN_ERR_INVALID, "null argument");
+  if (!p->use_tma) return fail(PERCNN_ERR_UNSUPPORTED, "step_fwd_range needs a TMA plan");
+  if (z_lo < 0 || z_hi > p->g.D || z_lo >= z_hi) return fail(PERCNN_ERR_INVALID, "bad plane range");
+  return launch_tma_fwd(p, static_cast<const float*>(h_in), static_cast<float*>(h_out), z_lo, z_hi,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int percnn_param_grads_begin(percnn_plan_t* p, void* ws, void* stream) {
+  if (!p || !ws) return fail(PERCNN_ERR_INVALID, "null argument");
+  PERCNN_CUDA(cudaMemsetAsync(ws, 0, kWsPartials, static_cast<cudaStream_t>(stream)));
+  return PERCNN_OK;
+}
+
+int percnn_step_bwd(percnn_plan_t* p, const void* h_in, const void* g_out, const void* g_add, void* g_in, void* ws,
+                    void* stream) {
+  if (!p || !h_in || !g_out || !g_in || !ws) return fail(PERCNN_ERR_INVALID, "null argument");
+  if (g_out == g_in) return fail(PERCNN_ERR_INVALID, "step_bwd cannot run in place");
+  return step_bwd_any(p, h_in, g_out, g_add, g_in, ws, static_cast<cudaStream_t>(stream));
+}
+
+int percnn_param_grads_finish(percnn_plan_t* p, const void* params, void* param_grads, void* ws, void* stream) {
+  if (!p || !params || !param_grads || !ws) return fail(PERCNN_ERR_INVALID, "null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const double* acc = reinterpret_cast<const double*>(static_cast<char*>(ws) + kWsAcc);
+  if (p->desc.cell == PERCNN_CELL_PI && p->desc.ksize != 1)
+    return fail(PERCNN_ERR_UNSUPPORTED, "adjoint of the 5x5 Pi-block cell is not implemented yet");
+  if (p->elt == 4)
+    k_finish_small<float><<<1, 256, 0, st>>>(static_cast<const float*>(params), acc, p->pd, int(p->nparams),
+                                             static_cast<float*>(param_grads));
+  else
+    k_finish_small<double><<<1, 256, 0, st>>>(static_cast<const double*>(params), acc, p->pd, int(p->nparams),
+                                              static_cast<double*>(param_grads));
+  PERCNN_CUDA(cudaGetLastError());
+  p->launches++;
+  return PERCNN_OK;
+}
+
+int percnn_rollout_fwd(percnn_plan_t* p, const void* h0, void* traj, const uint8_t* emit, int nsteps, void* h_final,
+                       void* tape, void* ws, void* stream) {
+  if (!p || !h0) return fail(PERCNN_ERR_INVALID, "null plan or h0");
+  if (nsteps < 0) return fail(PERCNN_ERR_INVALID, "nsteps must be >= 0");
+  if (traj && !emit) return fail(PERCNN_ERR_INVALID, "traj given without an emit mask");
+  if (!tape && !ws) return fail(PERCNN_ERR_INVALID, "rollout_fwd needs a workspace unless a tape is given");
+  if (p->desc.slab_ghost) return fail(PERCNN_ERR_UNSUPPORTED, "slab-mode rollouts are driven step by step (halo exchange between steps)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t sb = state_bytes(p);
+  char* tp = static_cast<char*>(tape);
+  char* pp[2] = {nullptr, nullptr};
+  if (ws) {
+    pp[0] = static_cast<char*>(ws) + kWsStates;
+    pp[1] = pp[0] + (sb + 255) / 256 * 256;
+  }
+  if (tp && tp != h0) PERCNN_CUDA(cudaMemcpyAsync(tp, h0, sb, cudaMemcpyDeviceToDevice, st));
+  const char* cur = tp ? tp : static_cast<const char*>(h0);
+  int slot = 0, flip = 0;
+  for (int s = 0; s < nsteps; ++s) {
+    const bool emitted = traj && emit[s];
+    char* dst;
+    if (tp)
+      dst = tp + size_t(s + 1) * sb;
+    else if (emitted)
+      dst = static_cast<char*>(traj) + size_t(slot) * sb;
+    else if (s == nsteps - 1 && h_final)
+      dst = static_cast<char*>(h_final);
+    else {
+      dst = pp[flip];
+      flip ^= 1;
+    }
+    int rc = step_fwd_any(p, cur, dst, st);
+    if (rc) return rc;
+    if (emitted) {
+      if (tp) PERCNN_CUDA(cudaMemcpyAsync(static_cast<char*>(traj) + size_t(slot) * sb, dst, sb, cudaMemcpyDeviceToDevice, st));
+      ++slot;
+    }
+    cur = dst;
+  }
+  if (h_final && cur != h_final) PERCNN_CUDA(cudaMemcpyAsync(h_final, cur, sb, cudaMemcpyDeviceToDevice, st));
+  return PERCNN_OK;
+}
+
+int percnn_rollout_bwd(percnn_plan_t* p, const void* params, const void* tape, const void* g_tape, const uint8_t* gmask,
+                       int nsteps, void* g_h0, void* param_grads, void* ws, void* stream) {
+  if (!p || !params || !tape || !g_h0 || !param_grads || !ws) return fail(PERCNN_ERR_INVALID, "null argument");
+  if (nsteps < 1) return fail(PERCNN_ERR_INVALID, "nsteps must be >= 1");
+  if (g_tape && !gmask) return fail(PERCNN_ERR_INVALID, "g_tape given without a mask");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t sb = state_bytes(p);
+  char* w = static_cast<char*>(ws);
+  char* pp[2] = {w + kWsStates, w + kWsStates + (sb + 255) / 256 * 256};
+  int rc = percnn_param_grads_begin(p, ws, stream);
+  if (rc) return rc;
+  // compact slot index of each masked state
+  int nmasked = 0;
+  if (g_tape)
+    for (int s = 0; s <= nsteps; ++s) nmasked += gmask[s] ? 1 : 0;
+  int slot = nmasked;
+  const char* gt = static_cast<const char*>(g_tape);
+  // G_{nsteps}
+  const char* G;
+  if (g_tape && gmask[nsteps]) {
+    --slot;
+    G = gt + size_t(slot) * sb;
+  } else {
+    PERCNN_CUDA(cudaMemsetAsync(pp[0], 0, sb, st));
+    G = pp[0];
+  }
+  int flip = (G == pp[0]) ? 1 : 0;
+  for (int s = nsteps - 1; s >= 0; --s) {
+    const char* add = nullptr;
+    if (g_tape && gmask[s]) {
+      --slot;
+      add = gt + size_t(slot) * sb;
+    }
+    char* gin = (s == 0) ? static_cast<char*>(g_h0) : pp[flip];
+    if (s != 0) flip ^= 1;
+    rc = step_bwd_any(p, static_cast<const char*>(tape) + size_t(s) * sb, G, add, gin, ws, st);
+    if (rc) return rc;
+    G = gin;
+  }
+  return percnn_param_grads_finish(p, params, param_grads, ws, stream);
+}
+
+int percnn_rollout_fwd_host(percnn_plan_t* p, const void* params_host, const void* h0_host, void* traj_host,
+                            const uint8_t* emit, int nsteps, void* h_final_host) {
+  if (!p || !params_host || !h0_host) return fail(PERCNN_ERR_INVALID, "null argument");
+  if (traj_host && !emit) return fail(PERCNN_ERR_INVALID, "traj given without an emit mask");
+  PERCNN_CUDA(cudaSetDevice(p->desc.device));
+  const size_t sb = (state_bytes(p) + 255) / 256 * 256;
+  int nemit = 0;
+  if (traj_host)
+    for (int s = 0; s < nsteps; ++s) nemit += emit[s] ? 1 : 0;
+  const size_t need = kWsStates + sb * size_t(4 + nemit);
+  if (!p->h_stream) PERCNN_CUDA(cudaStreamCreateWithFlags(&p->h_stream, cudaStreamNonBlocking));
+  if (!p->h_params_dev) PERCNN_CUDA(cudaMalloc(&p->h_params_dev, size_t(p->nparams) * p->elt));
+  if (p->h_states_bytes < need) {
+    if (p->h_states) cudaFree(p->h_states);
+    p->h_states = nullptr;
+    p->h_states_bytes = 0;
+    PERCNN_CUDA(cudaMalloc(&p->h_states, need));
+    p->h_states_bytes = need;
+  }
+  cudaStream_t st = p->h_stream;
+  char* base = static_cast<char*>(p->h_states);
+  char* ws = base;                          // header + 2 ping-pong states
+  char* d_h0 = base + kWsStates + 2 * sb;
+  char* d_final = d_h0 + sb;
+  char* d_traj = d_final + sb;
+  const size_t raw_sb = state_bytes(p);
+  PERCNN_CUDA(cudaMemcpyAsync(p->h_params_dev, params_host, size_t(p->nparams) * p->elt, cudaMemcpyHostToDevice, st));
+  PERCNN_CUDA(cudaMemcpyAsync(d_h0, h0_host, raw_sb, cudaMemcpyHostToDevice, st));
+  int rc = percnn_params_load(p, p->h_params_dev, st);
+  if (rc) return rc;
+  // the device trajectory uses padded slots; rollout_fwd packs slots state_bytes apart, so run it on a
+  // tightly packed view when padding is zero (always the case for sizes that are multiples of 64 cells)
+  if (nemit > 0 && raw_sb != sb) {
+    // fall back to emitting one frame at a time through h_final
+    return fail(PERCNN_ERR_UNSUPPORTED, "host rollout with emitted frames needs state bytes to be a multiple of 256");
+  }
+  rc = percnn_rollout_fwd(p, d_h0, nemit ? d_traj : nullptr, emit, nsteps, h_final_host ? d_final : nullptr, nullptr, ws, st);
+  if (rc) return rc;
+  if (nemit) PERCNN_CUDA(cudaMemcpyAsync(traj_host, d_traj, raw_sb * size_t(nemit), cudaMemcpyDeviceToHost, st));
+  if (h_final_host) PERCNN_CUDA(cudaMemcpyAsync(h_final_host, d_final, raw_sb, cudaMemcpyDeviceToHost, st));
+  PERCNN_CUDA(cudaStreamSynchronize(st));
+  return PERCNN_OK;
+}
+
+}  // extern "C"

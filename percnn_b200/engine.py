@@ -1,0 +1,287 @@
+"""Host-side engine: plans, parameter packing and the autograd bridge to the C-ABI.
+
+Everything here is plumbing (PyTorch owns device memory and streams); the arithmetic happens in
+libpercnn_b200.so.  There is deliberately no CPU / eager fallback: a CPU tensor or a missing library
+raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import dataclasses
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import Desc, check
+
+
+@dataclasses.dataclass(frozen=True)
+class CellSpec:
+    """The constants the reference hard-codes in each RCNNCell constructor."""
+    cell: int                 # _lib.CELL_*
+    ndim: int
+    dtype: torch.dtype
+    ksize: int = 1
+    hidden: int = 0
+    coef_mode: int = _lib.COEF_SIGMOID
+    mu_up: float = 1.0
+    dt: float = 1.0
+    dx: float = 1.0
+    flags: int = 0
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"percnn_b200: {what} is on {t.device}; the fused cell runs on CUDA (sm_100a) only and has no CPU fallback")
+
+
+class Plan:
+    """percnn_plan_t wrapper bound to one (spec, spatial shape, device)."""
+
+    def __init__(self, spec: CellSpec, spatial: Sequence[int], device: torch.device, slab_ghost: bool = False):
+        L = _lib.lib()
+        if len(spatial) != spec.ndim:
+            raise ValueError(f"expected {spec.ndim} spatial dims, got {tuple(spatial)}")
+        self.spec = spec
+        self.spatial = tuple(int(s) for s in spatial)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("percnn_b200 plans need a CUDA device; there is no CPU fallback")
+        self.slab_ghost = bool(slab_ghost)
+        d = Desc()
+        d.abi_version = _lib.ABI_VERSION
+        d.ndim = spec.ndim
+        ext = (1,) + self.spatial if spec.ndim == 2 else self.spatial
+        for i in range(3):
+            d.extent[i] = ext[i]
+        d.dtype = _lib.F32 if spec.dtype == torch.float32 else _lib.F64
+        d.cell, d.ksize, d.hidden, d.coef_mode, d.flags = spec.cell, spec.ksize, spec.hidden, spec.coef_mode, spec.flags
+        d.mu_up, d.dt, d.dx = spec.mu_up, spec.dt, spec.dx
+        d.device = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        d.slab_ghost = 1 if slab_ghost else 0
+        self._h = ctypes.c_void_p()
+        self._L = L
+        with torch.cuda.device(self.device):
+            check(L.percnn_plan_create(ctypes.byref(d), ctypes.byref(self._h)))
+        self.nparams = int(L.percnn_param_count(self._h))
+        self.state_elems = int(L.percnn_state_elems(self._h))
+        self.uses_tma = bool(L.percnn_plan_uses_tma(self._h))
+        self._ws: Optional[torch.Tensor] = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                self._L.percnn_plan_destroy(h)
+            except Exception:
+                pass
+            self._h = ctypes.c_void_p()
+
+    # -- shapes ---------------------------------------------------------------------------------
+    @property
+    def buffer_shape(self) -> Tuple[int, ...]:
+        """Shape of one state buffer (2 fields; slowest axis carries the ghosts in slab mode)."""
+        s = list(self.spatial)
+        if self.slab_ghost:
+            s[0] += 4
+        return (2, *s)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.percnn_plan_launch_count(self._h))
+
+    def workspace(self) -> torch.Tensor:
+        if self._ws is None:
+            nbytes = int(self._L.percnn_workspace_bytes(self._h, 0))
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _check_state(self, t: torch.Tensor, what: str, slots: int = 1) -> None:
+        _require_cuda(t, what)
+        if t.dtype != self.spec.dtype:
+            raise TypeError(f"{what}: dtype {t.dtype} != plan dtype {self.spec.dtype}")
+        if not t.is_contiguous():
+            raise ValueError(f"{what} must be contiguous")
+        if t.numel() != slots * self.state_elems:
+            raise ValueError(f"{what}: {t.numel()} elements, expected {slots} x {self.state_elems}")
+
+    # -- calls ----------------------------------------------------------------------------------
+    def params_load(self, flat: torch.Tensor) -> None:
+        _require_cuda(flat, "params")
+        if flat.dtype != self.spec.dtype or flat.numel() != self.nparams or not flat.is_contiguous():
+            raise ValueError(f"params: need {self.nparams} contiguous {self.spec.dtype} scalars, got {flat.numel()} {flat.dtype}")
+        check(self._L.percnn_params_load(self._h, flat.data_ptr(), _stream_ptr(self.device)))
+
+    def step_fwd(self, h_in: torch.Tensor, h_out: torch.Tensor) -> None:
+        self._check_state(h_in, "h_in")
+        self._check_state(h_out, "h_out")
+        check(self._L.percnn_step_fwd(self._h, h_in.data_ptr(), h_out.data_ptr(), _stream_ptr(self.device)))
+
+    def step_fwd_range(self, h_in: torch.Tensor, h_out: torch.Tensor, z_lo: int, z_hi: int) -> None:
+        check(self._L.percnn_step_fwd_range(self._h, h_in.data_ptr(), h_out.data_ptr(), int(z_lo), int(z_hi),
+                                            _stream_ptr(self.device)))
+
+    def step_bwd(self, h_in, g_out, g_in, g_add=None) -> None:
+        for t, n in ((h_in, "h_in"), (g_out, "g_out"), (g_in, "g_in")):
+            self._check_state(t, n)
+        if g_add is not None:
+            self._check_state(g_add, "g_add")
+        check(self._L.percnn_step_bwd(self._h, h_in.data_ptr(), g_out.data_ptr(), _ptr(g_add), g_in.data_ptr(),
+                                      self.workspace().data_ptr(), _stream_ptr(self.device)))
+
+    def param_grads_begin(self) -> None:
+        check(self._L.percnn_param_grads_begin(self._h, self.workspace().data_ptr(), _stream_ptr(self.device)))
+
+    def param_grads_finish(self, flat: torch.Tensor) -> torch.Tensor:
+        out = torch.empty_like(flat)
+        check(self._L.percnn_param_grads_finish(self._h, flat.data_ptr(), out.data_ptr(), self.workspace().data_ptr(),
+                                                _stream_ptr(self.device)))
+        return out
+
+    def rollout_fwd(self, h0: torch.Tensor, nsteps: int, *, tape: Optional[torch.Tensor] = None,
+                    traj: Optional[torch.Tensor] = None, emit: Optional[Sequence[bool]] = None,
+                    h_final: Optional[torch.Tensor] = None) -> None:
+        self._check_state(h0, "h0")
+        if tape is not None:
+            self._check_state(tape, "tape", nsteps + 1)
+        emit_arr = None
+        if traj is not None:
+            if emit is None or len(emit) != nsteps:
+                raise ValueError("traj needs an emit mask with one entry per step")
+            self._check_state(traj, "traj", sum(1 for e in emit if e))
+            emit_arr = (ctypes.c_uint8 * nsteps)(*[1 if e else 0 for e in emit])
+        if h_final is not None:
+            self._check_state(h_final, "h_final")
+        check(self._L.percnn_rollout_fwd(self._h, h0.data_ptr(), _ptr(traj), emit_arr, int(nsteps), _ptr(h_final),
+                                         _ptr(tape), self.workspace().data_ptr(), _stream_ptr(self.device)))
+
+    def rollout_bwd(self, flat: torch.Tensor, tape: torch.Tensor, g_tape: Optional[torch.Tensor],
+                    gmask: Optional[Sequence[bool]], nsteps: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        self._check_state(tape, "tape", nsteps + 1)
+        mask_arr = None
+        if g_tape is not None:
+            if gmask is None or len(gmask) != nsteps + 1:
+                raise ValueError("g_tape needs a mask with nsteps+1 entries")
+            self._check_state(g_tape, "g_tape", sum(1 for e in gmask if e))
+            mask_arr = (ctypes.c_uint8 * (nsteps + 1))(*[1 if e else 0 for e in gmask])
+        g_h0 = torch.empty(self.buffer_shape, dtype=self.spec.dtype, device=self.device)
+        g_flat = torch.empty_like(flat)
+        check(self._L.percnn_rollout_bwd(self._h, flat.data_ptr(), tape.data_ptr(), _ptr(g_tape), mask_arr, int(nsteps),
+                                         g_h0.data_ptr(), g_flat.data_ptr(), self.workspace().data_ptr(),
+                                         _stream_ptr(self.device)))
+        return g_h0, g_flat
+
+    def rollout_fwd_host(self, flat_host: torch.Tensor, h0_host: torch.Tensor, nsteps: int,
+                         emit: Optional[Sequence[bool]] = None, want_final: bool = True):
+        """End-to-end call with HOST buffers (pinned or pageable): H2D, rollout, D2H, sync."""
+        if flat_host.is_cuda or h0_host.is_cuda:
+            raise ValueError("rollout_fwd_host takes host tensors")
+        nemit = 0 if emit is None else sum(1 for e in emit if e)
+        traj = torch.empty((nemit, *self.buffer_shape), dtype=self.spec.dtype).pin_memory() if nemit else None
+        fin = torch.empty(self.buffer_shape, dtype=self.spec.dtype).pin_memory() if want_final else None
+        emit_arr = None if emit is None else (ctypes.c_uint8 * nsteps)(*[1 if e else 0 for e in emit])
+        check(self._L.percnn_rollout_fwd_host(self._h, flat_host.data_ptr(), h0_host.data_ptr(), _ptr(traj), emit_arr,
+                                              int(nsteps), _ptr(fin)))
+        return traj, fin
+
+
+_PLAN_CACHE: Dict[tuple, Plan] = {}
+_PLAN_ORDER: List[tuple] = []
+_MAX_PLANS = 5  # the library has 6 constant-memory parameter slots
+
+
+def get_plan(spec: CellSpec, spatial: Sequence[int], device: torch.device, slab_ghost: bool = False) -> Plan:
+    device = torch.device(device)
+    if device.type == "cuda" and device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    key = (spec, tuple(int(s) for s in spatial), str(device), bool(slab_ghost))
+    plan = _PLAN_CACHE.get(key)
+    if plan is None:
+        while len(_PLAN_ORDER) >= _MAX_PLANS:
+            old = _PLAN_ORDER.pop(0)
+            _PLAN_CACHE.pop(old, None)
+        plan = Plan(spec, spatial, device, slab_ghost)
+        _PLAN_CACHE[key] = plan
+        _PLAN_ORDER.append(key)
+    return plan
+
+
+def clear_plans() -> None:
+    _PLAN_CACHE.clear()
+    _PLAN_ORDER.clear()
+
+
+def pack_params(tensors: Sequence[torch.Tensor], dtype: torch.dtype) -> torch.Tensor:
+    """Flat packing = the cell's state_dict tensors concatenated in state_dict order."""
+    return torch.cat([t.detach().reshape(-1).to(dtype) for t in tensors]).contiguous()
+
+
+class _Rollout(torch.autograd.Function):
+    """states[0] = h0, states[s+1] = cell(states[s]);  backward = the hand-derived adjoint kernels.
+
+    Only the states are stored (8 B per cell per step in fp32) -- the reference's autograd keeps
+    146-705 B per cell per step.
+    """
+
+    @staticmethod
+    def forward(ctx, plan: Plan, nsteps: int, h0: torch.Tensor, *params: torch.Tensor):
+        _require_cuda(h0, "state")
+        flat = pack_params(params, plan.spec.dtype)
+        plan.params_load(flat)
+        states = torch.empty((nsteps + 1, *plan.buffer_shape), dtype=plan.spec.dtype, device=h0.device)
+        plan.rollout_fwd(h0.detach().contiguous().view(plan.buffer_shape), nsteps, tape=states)
+        ctx.plan, ctx.nsteps = plan, nsteps
+        ctx.shapes = [tuple(p.shape) for p in params]
+        ctx.dtypes = [p.dtype for p in params]
+        ctx.save_for_backward(states, flat)
+        return states
+
+    @staticmethod
+    def backward(ctx, g_states: torch.Tensor):
+        states, flat = ctx.saved_tensors
+        plan, nsteps = ctx.plan, ctx.nsteps
+        g_states = g_states.contiguous()
+        plan.params_load(flat)
+        g_h0, g_flat = plan.rollout_bwd(flat, states, g_states, [True] * (nsteps + 1), nsteps)
+        grads: List[Optional[torch.Tensor]] = []
+        off = 0
+        for i, (shape, dt) in enumerate(zip(ctx.shapes, ctx.dtypes)):
+            n = 1
+            for s in shape:
+                n *= s
+            if ctx.needs_input_grad[3 + i]:
+                grads.append(g_flat[off:off + n].view(shape).to(dt))
+            else:
+                grads.append(None)
+            off += n
+        return (None, None, g_h0 if ctx.needs_input_grad[2] else None, *grads)
+
+
+def rollout_states(plan: Plan, nsteps: int, h0: torch.Tensor, params: Sequence[torch.Tensor]) -> torch.Tensor:
+    """All states of an nsteps rollout as one [nsteps+1, 2, ...] tensor (differentiable)."""
+    return _Rollout.apply(plan, nsteps, h0, *params)
+
+
+@torch.no_grad()
+def rollout_emit(plan: Plan, nsteps: int, h0: torch.Tensor, params: Sequence[torch.Tensor],
+                 emit: Sequence[bool], want_final: bool = False):
+    """Inference rollout that stores only the emitted states (ping-pong scratch for the rest)."""
+    _require_cuda(h0, "state")
+    flat = pack_params(params, plan.spec.dtype)
+    plan.params_load(flat)
+    nemit = sum(1 for e in emit if e)
+    traj = torch.empty((nemit, *plan.buffer_shape), dtype=plan.spec.dtype, device=h0.device)
+    fin = torch.empty(plan.buffer_shape, dtype=plan.spec.dtype, device=h0.device) if want_final else None
+    plan.rollout_fwd(h0.contiguous().view(plan.buffer_shape), nsteps, traj=traj if nemit else None,
+                     emit=emit if nemit else None, h_final=fin)
+    return traj, fin

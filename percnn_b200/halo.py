@@ -1,0 +1,193 @@
+"""Slab domain decomposition of the 3-D rollout over N GPUs.
+
+One process per GPU.  The grid is split along the slowest axis D; every rank keeps two ghosted state
+buffers [2][nz+4][H][W] (ping-pong) whose 2 ghost planes per side are the neighbours' boundary planes
+(periodic ring: neighbours are (rank +- 1) mod N).  Per time step
+
+    compute stream:  wait(ghosts of cur ready) -> boundary planes [0,2) and [nz-2,nz) of nxt
+    comm stream:     wait(boundary done)       -> send them / receive the neighbours' into nxt's ghosts
+    compute stream:  interior planes [2,nz-2) of nxt            (overlaps the exchange)
+
+so only the ghost cells cross NVLink (2 x 2 x H x W x 4 B per side per step) and the exchange hides
+behind the interior kernel.  Transport:
+
+  * "nccl": torch.distributed batch_isend_irecv (ncclSend/ncclRecv grouped) on the comm stream;
+  * "symm": peer-mapped buffers (torch.distributed._symmetric_memory): the boundary planes are copied
+    straight into the neighbour's ghost planes over NVLink and a stream-ordered signal replaces the
+    rendezvous -- no NCCL kernel, no host round trip; the whole multi-step loop is CUDA-graph capturable.
+
+`exchange_ghosts` is device-agnostic (it only moves planes with torch.distributed), which is what the
+world_size-2 gloo tests exercise on CPU; the step kernels themselves are CUDA-only.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import engine
+
+
+def slab_bounds(depth: int, rank: int, world: int):
+    """[z0, z0+nz) of `rank`; the depth must split evenly so every rank runs the same kernel shape."""
+    if depth % world:
+        raise ValueError(f"depth {depth} is not divisible by {world} ranks")
+    nz = depth // world
+    return rank * nz, nz
+
+
+def exchange_ghosts(buf: torch.Tensor, nz: int, rank: int, world: int, group=None) -> List:
+    """Fill the 2+2 ghost planes of `buf` ([2][nz+4][...]) from the ring neighbours' boundary planes.
+
+    Returns the outstanding work handles (empty when world == 1, where the wrap is a local copy).
+    Send order (top planes -> lower neighbour, bottom planes -> upper neighbour) and receive order (upper
+    neighbour first) are chosen so that world == 2, where both neighbours are the same peer, pairs up.
+    """
+    if world == 1:
+        buf[:, 0:2].copy_(buf[:, nz:nz + 2])
+        buf[:, nz + 2:nz + 4].copy_(buf[:, 2:4])
+        return []
+    lo, hi = (rank - 1) % world, (rank + 1) % world
+    ops = []
+    for f in range(2):
+        ops.append(dist.P2POp(dist.isend, buf[f, 2:4], lo, group))
+    for f in range(2):
+        ops.append(dist.P2POp(dist.isend, buf[f, nz:nz + 2], hi, group))
+    for f in range(2):
+        ops.append(dist.P2POp(dist.irecv, buf[f, nz + 2:nz + 4], hi, group))
+    for f in range(2):
+        ops.append(dist.P2POp(dist.irecv, buf[f, 0:2], lo, group))
+    return dist.batch_isend_irecv(ops)
+
+
+class SlabRollout:
+    """Forward rollout of a 3-D Pi-block cell on one slab of a slab-decomposed periodic grid."""
+
+    def __init__(self, cell, global_shape, device, rank: int, world: int, group=None, transport: str = "auto",
+                 use_graph: bool = True):
+        D, H, W = (int(s) for s in global_shape)
+        self.rank, self.world, self.group = rank, world, group
+        self.z0, self.nz = slab_bounds(D, rank, world)
+        if self.nz < 4:
+            raise ValueError("slabs need at least 4 planes per rank")
+        self.device = torch.device(device)
+        self.cell = cell
+        self.plan = engine.get_plan(cell._spec(), (self.nz, H, W), self.device, slab_ghost=True)
+        if not self.plan.uses_tma:
+            raise NotImplementedError("slab mode drives the TMA kernel (W % 128 == 0, H % 16 == 0, fp32, k = 1)")
+        self.flat = engine.pack_params(cell._packed_tensors(), torch.float32)
+        self.plan.params_load(self.flat)
+        self.transport = "nccl" if transport == "auto" else transport
+        self.symm = None
+        shape = self.plan.buffer_shape
+        if self.transport == "symm" and world > 1:
+            import torch.distributed._symmetric_memory as symm_mem
+            both = symm_mem.empty((2, *shape), dtype=torch.float32, device=self.device)
+            self.symm = symm_mem.rendezvous(both, group=group if group is not None else dist.group.WORLD)
+            both.zero_()
+            self.bufs = [both[0], both[1]]
+            lo, hi = (rank - 1) % world, (rank + 1) % world
+            self.peer_lo = self.symm.get_buffer(lo, (2, *shape), torch.float32)
+            self.peer_hi = self.symm.get_buffer(hi, (2, *shape), torch.float32)
+        else:
+            self.bufs = [torch.zeros(shape, dtype=torch.float32, device=self.device) for _ in range(2)]
+        self.cur = 0
+        self.comm_stream = torch.cuda.Stream(self.device)
+        self.ev_boundary = torch.cuda.Event()
+        self.ev_ghosts = torch.cuda.Event()
+        self.use_graph = use_graph and (self.transport == "symm" or world == 1)
+        self._graphs = {}
+        self._extra_launches = 0
+
+    # -- state ----------------------------------------------------------------------------------
+    def set_state(self, interior: torch.Tensor) -> None:
+        """interior: [2][nz][H][W] slab of the global field (planes z0 .. z0+nz)."""
+        b = self.bufs[self.cur]
+        b[:, 2:self.nz + 2].copy_(interior)
+        self._exchange_blocking(self.cur)
+
+    def interior(self) -> torch.Tensor:
+        return self.bufs[self.cur][:, 2:self.nz + 2]
+
+    @property
+    def launch_count(self) -> int:
+        return self.plan.launch_count + self._extra_launches
+
+    def describe(self):
+        H, W = self.plan.spatial[1:]
+        return {"transport": self.transport, "planes_per_rank": self.nz, "ghost_bytes_per_side_per_step": 2 * 2 * H * W * 4,
+                "cuda_graph": bool(self.use_graph), "overlap": "boundary planes first, exchange on a second stream under the interior kernel"}
+
+    # -- exchange -------------------------------------------------------------------------------
+    def _exchange_blocking(self, b: int) -> None:
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            dist.barrier(self.group)
+        if self.symm is not None:
+            self._symm_push(b)
+            self._symm_wait()
+        else:
+            for w in exchange_ghosts(self.bufs[b], self.nz, self.rank, self.world, self.group):
+                w.wait()
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            dist.barrier(self.group)
+
+    def _symm_push(self, b: int) -> None:
+        """Copy my boundary planes of buffer b into the neighbours' ghost planes, then raise their signals."""
+        nz = self.nz
+        me = self.bufs[b]
+        self.peer_lo[b][:, nz + 2:nz + 4].copy_(me[:, 2:4])       # my top planes = lower neighbour's upper ghosts
+        self.peer_hi[b][:, 0:2].copy_(me[:, nz:nz + 2])           # my bottom planes = upper neighbour's lower ghosts
+        lo, hi = (self.rank - 1) % self.world, (self.rank + 1) % self.world
+        self.symm.put_signal(lo, channel=0)
+        self.symm.put_signal(hi, channel=1)
+        self._extra_launches += 4
+
+    def _symm_wait(self) -> None:
+        lo, hi = (self.rank - 1) % self.world, (self.rank + 1) % self.world
+        self.symm.wait_signal(hi, channel=0)
+        self.symm.wait_signal(lo, channel=1)
+        self._extra_launches += 2
+
+    # -- stepping -------------------------------------------------------------------------------
+    def _step(self, first: bool) -> None:
+        cur, nxt = self.bufs[self.cur], self.bufs[self.cur ^ 1]
+        nz = self.nz
+        main = torch.cuda.current_stream(self.device)
+        if self.world > 1 and not first:        # ghosts of `cur` were pushed during the previous step
+            if self.symm is not None:
+                self._symm_wait()
+            else:
+                main.wait_event(self.ev_ghosts)
+        self.plan.step_fwd_range(cur, nxt, 0, 2)
+        self.plan.step_fwd_range(cur, nxt, nz - 2, nz)
+        if self.world == 1:
+            self.plan.step_fwd_range(cur, nxt, 2, nz - 2)
+            exchange_ghosts(nxt, nz, 0, 1)
+        else:
+            self.ev_boundary.record(main)
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(self.ev_boundary)
+                if self.symm is not None:
+                    self._symm_push(self.cur ^ 1)
+                else:
+                    for w in exchange_ghosts(nxt, nz, self.rank, self.world, self.group):
+                        w.wait()                 # stream-level wait: comm_stream now depends on the NCCL stream
+                    self.ev_ghosts.record(self.comm_stream)
+            self.plan.step_fwd_range(cur, nxt, 2, nz - 2)
+        self.cur ^= 1
+
+    def run(self, nsteps: int) -> None:
+        """Advance the slab by nsteps time steps.  Invariant on entry and exit: the ghosts of the current
+        buffer are valid and every exchange signal has been consumed (set_state() establishes it)."""
+        for i in range(nsteps):
+            self._step(first=(i == 0))
+        if self.world > 1 and nsteps > 0:
+            main = torch.cuda.current_stream(self.device)
+            if self.symm is not None:
+                main.wait_stream(self.comm_stream)
+                self._symm_wait()
+            else:
+                main.wait_event(self.ev_ghosts)

@@ -1,0 +1,58 @@
+"""Drop-in for the classes of DataDrivenModeling/2d_gs_rd/train_2drd.py (GS2D:26-190)."""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from ..cells import FusedRCNN, PiCell
+
+
+class upscaler(nn.Module):
+    """Low-res -> full-res initial-state generator (GS2D:26-41): two stride-2 transposed convs.
+
+    Runs once per rollout and is outside the fused hot path: stock PyTorch modules,
+    registered so that the state_dict keys are `convnet.{0,2,3}.*` like the reference's.
+    """
+
+    def __init__(self):
+        super().__init__()
+        self.layers = [
+            nn.ConvTranspose2d(2, 8, kernel_size=5, padding=2, stride=2, output_padding=1, bias=True),
+            nn.Sigmoid(),
+            nn.ConvTranspose2d(8, 8, kernel_size=5, padding=2, stride=2, output_padding=1, bias=True),
+            nn.Conv2d(8, 2, 1, 1, padding=0, bias=True),
+        ]
+        self.convnet = nn.Sequential(*self.layers)
+
+    def forward(self, h):
+        return self.convnet(h)
+
+
+class RCNNCell(PiCell):
+    """GS2D:43-121: fp32, 1x1 Pi convs, alpha = mu_up * sigmoid(CA)."""
+
+    def __init__(self, input_channels, hidden_channels, input_kernel_size):
+        super().__init__()
+        self.input_channels = input_channels
+        self.hidden_channels = hidden_channels
+        self.input_kernel_size = 5       # GS2D:53 ignores the argument
+        self.input_stride = 1
+        self.mu_up = 3.99e-5
+        np.random.seed(1234)             # GS2D:60 -- constructor side effect kept on purpose
+        ca, cb = (np.random.rand() - 0.5) * 2, (np.random.rand() - 0.5) * 2
+        self._build(ndim=2, dtype=torch.float32, ksize=1, hidden=hidden_channels, dx=0.01, dt=0.5,
+                    coef_mode=_lib.COEF_SIGMOID, mu_up=self.mu_up, coef_names=("CA", "CB"), coef_init=(ca, cb),
+                    init_scale=0.02, init_kind="xavier")
+
+
+class RCNN(FusedRCNN):
+    def __init__(self, input_channels, hidden_channels, init_state_low, input_kernel_size, step=1, effective_step=[1]):
+        super().__init__()
+        self.input_channels = input_channels
+        self.hidden_channels = hidden_channels
+        self.input_kernel_size = input_kernel_size
+        self.init_state_low = init_state_low
+        self.init_state = []
+        self.UpconvBlock = upscaler()
+        self._setup(RCNNCell(input_channels=input_channels, hidden_channels=hidden_channels,
+                             input_kernel_size=input_kernel_size), step, effective_step)

@@ -35,3 +35,33 @@ def rel_linf(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def make_cell(tag):
+    """Construct the percnn_b200 drop-in cell that corresponds to a golden tag / oracle variant."""
+    from percnn_b200.variants import (burgers_stage1, burgers_stage3, gs2d, gs3d, lambda_omega_fwd, lo_stage1,
+                                      lo_stage3)
+    if tag == "fwd":
+        return lambda_omega_fwd.RCNNCell(input_kernel_size=1, input_stride=1, input_padding=0)
+    if tag == "gs2d":
+        return gs2d.RCNNCell(input_channels=2, hidden_channels=8, input_kernel_size=5)
+    if tag in ("gs3d", "gs3d_tma"):
+        return gs3d.RCNNCell(input_channels=2, hidden_channels=2, input_kernel_size=5)
+    kw = dict(input_channels=2, hidden_channels=4, output_channels=2, input_kernel_size=5, input_stride=1,
+              input_padding=2)
+    if tag == "bur1":
+        return burgers_stage1.RCNNCell(**kw)
+    if tag == "lo1":
+        return lo_stage1.RCNNCell(**kw)
+    if tag == "bur3":
+        return burgers_stage3.RCNNCell(**kw)
+    if tag == "lo3":
+        return lo_stage3.RCNNCell(**kw)
+    if tag == "lo3n":
+        return lo_stage3.RCNNCellNoisy(**kw)
+    raise KeyError(tag)
+
+
+def cell_params_dict(cell):
+    """{state_dict key: tensor on CPU} -- the oracle's parameter format."""
+    return {k: v.detach().cpu() for k, v in cell.state_dict().items()}

@@ -1,0 +1,128 @@
+"""CPU-only checks of the boundary: the C-ABI library loads and exports what the header declares, the
+drop-in modules expose the reference's parameter names/shapes, and nothing silently falls back to CPU."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from percnn_b200 import _lib, engine
+from tests.helpers import GOLDEN_CASES, load_golden, make_cell
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "percnn_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(percnn_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    L = _lib.lib()
+    declared = _header_functions()
+    assert declared, "no functions parsed from the header"
+    assert sorted(_lib.EXPORTS) == declared
+    for name in declared:
+        assert hasattr(L, name), name
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (percnn_[a-z0-9_]+)", out))
+    assert set(declared) <= exported
+    assert L.percnn_abi_version() == _lib.ABI_VERSION
+
+
+def test_library_does_not_link_torch_or_the_oracle():
+    out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "torch" not in out and "c10" not in out
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU error path")
+def test_plan_create_fails_loudly_without_a_gpu():
+    L = _lib.lib()
+    assert L.percnn_device_ok(0) == 0
+    d = _lib.Desc()
+    d.abi_version, d.ndim, d.dtype, d.cell, d.ksize, d.hidden = 1, 2, 0, 0, 1, 4
+    d.extent[0], d.extent[1], d.extent[2] = 1, 8, 8
+    d.dt, d.dx, d.mu_up = 0.1, 0.1, 1.0
+    h = ctypes.c_void_p()
+    rc = L.percnn_plan_create(ctypes.byref(d), ctypes.byref(h))
+    assert rc == 4 and not h.value
+    assert b"sm_100" in L.percnn_last_error()
+
+
+def test_descriptor_validation_messages():
+    L = _lib.lib()
+    d = _lib.Desc()
+    h = ctypes.c_void_p()
+    d.abi_version = 99
+    assert L.percnn_plan_create(ctypes.byref(d), ctypes.byref(h)) == 1
+    assert b"abi_version" in L.percnn_last_error()
+    d.abi_version, d.ndim = 1, 4
+    assert L.percnn_plan_create(ctypes.byref(d), ctypes.byref(h)) == 1
+    assert L.percnn_plan_create(None, ctypes.byref(h)) == 1
+    assert L.percnn_param_count(None) == -1
+
+
+@pytest.mark.parametrize("tag", list(GOLDEN_CASES))
+def test_dropin_cell_has_reference_parameter_names_and_shapes(tag):
+    """strict load_state_dict of the parameters recorded from the reference class."""
+    _, params, grads = load_golden(tag)
+    cell = make_cell(tag)
+    sd = cell.state_dict()
+    assert list(sd.keys()) == list(params.keys())
+    for k, v in params.items():
+        assert tuple(sd[k].shape) == tuple(v.shape), k
+        assert sd[k].dtype == v.dtype, k
+    cell.load_state_dict(params, strict=True)
+    trainable = {n for n, p in cell.named_parameters() if p.requires_grad}
+    assert trainable == set(grads.keys())
+
+
+def test_constructor_side_effects_match_reference():
+    """np.random.seed(1234) inside the constructor and the CA/CB draw (GS2D:60-62, BUR1:98-100)."""
+    from percnn_b200.variants import burgers_stage1, gs2d
+    c = gs2d.RCNNCell(2, 8, 5)
+    np.random.seed(1234)
+    ca, cb = (np.random.rand() - 0.5) * 2, (np.random.rand() - 0.5) * 2
+    assert c.CA.item() == pytest.approx(np.float32(ca)) and c.CB.item() == pytest.approx(np.float32(cb))
+    assert c.input_kernel_size == 5 and c.mu_up == 3.99e-5 and c.dt == 0.5 and c.dx == 0.01
+    assert all(float(f.bias.abs().max()) == 0.0 for f in c.filter_list) and len(c.filter_list) == 8
+    b = burgers_stage1.RCNNCell(2, 4, 2, 5, 1, 2)
+    np.random.seed(1234)
+    assert b.CA.item() == pytest.approx(np.float32(np.random.rand()))
+    assert b.Wh1_u.weight.shape == (16, 2, 5, 5) and b.nu_up == 0.01
+
+
+def test_laplacian_tables_match_golden():
+    from percnn_b200.cells import derivative_table, laplace_table
+    _, p3, _ = load_golden("gs3d")
+    np.testing.assert_allclose(p3["W_laplace.weight"].numpy(), laplace_table(3) / (100 / 48) ** 2, rtol=1e-6)
+    _, pb, _ = load_golden("bur3")
+    np.testing.assert_array_equal(pb["dx_op.filter.weight"].numpy(), derivative_table(0))
+    np.testing.assert_array_equal(pb["dy_op.filter.weight"].numpy(), derivative_table(1))
+    np.testing.assert_array_equal(pb["laplace_op.filter.weight"].numpy(), laplace_table(2))
+
+
+def test_cpu_tensors_are_rejected_not_silently_computed():
+    cell = make_cell("gs2d")
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        cell(torch.zeros(1, 2, 8, 8))
+
+
+def test_fwd_checkpoint_prefix_shim():
+    from percnn_b200.variants import lambda_omega_fwd
+    from tests.helpers import load_weights
+    w = load_weights("fwd")
+    m = lambda_omega_fwd.RCNN(1, torch.zeros(1, 2, 8, 8), 1, 0, step=2, effective_step=[0, 1])
+    m.load_state_dict({"crnn_cell." + k: v for k, v in w.items()}, strict=True)
+    assert torch.equal(m.rcnn_cell.DA.detach(), w["DA"])
+
+
+def test_pack_params_is_state_dict_order():
+    cell = make_cell("gs3d")
+    flat = engine.pack_params(cell._packed_tensors(), torch.float32)
+    assert flat.numel() == 2 + 125 + 2 * (3 * (2 * 2 + 2) + 2 + 1)
+    assert flat[0] == cell.CA.detach() and flat[2 + 62] == cell.W_laplace.weight.detach()[0, 0, 2, 2, 2]
