@@ -24,13 +24,18 @@ namespace percnn {
 namespace tma3d {
 
 constexpr int TX = 128;        // tile width  = one warp x 4 cells per lane
-constexpr int TY = 16;         // tile height = consumer warps
+constexpr int TY = 16;         // MAXIMUM tile height = consumer warps; the actual height is Params::ty
 constexpr int STAGES = 8;      // planes in the ring
 constexpr int ROWS = TY + 4;   // rows per field per stage (2 halo rows above and below)
 constexpr int STAGE_FLOATS = 2 * ROWS * TX;
 constexpr int STAGE_BYTES = STAGE_FLOATS * 4;
 constexpr int CONSUMER_THREADS = TY * 32;
-constexpr int THREADS = CONSUMER_THREADS + 32;
+// 16 consumer warps + one producer warp-group (4 warps, of which one lane works).  The kernel is launched at
+// the register count 640 threads allow (96); setmaxnreg then moves registers from the idle producer
+// warp-group to the consumers, whose 5-plane window wants ~120.
+constexpr int THREADS = CONSUMER_THREADS + 128;
+constexpr int CONSUMER_REGS = 112;   // 512 * 112 + 128 * 24 <= 640 * 96: setmaxnreg only redistributes the CTA's own allocation
+constexpr int PRODUCER_REGS = 24;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 128;
 
 struct Params {
@@ -43,10 +48,12 @@ struct Params {
   int src_zoff;       // plane index of interior plane z - 2 is (z + src_zoff) [wrapped if wrap_z]
   int dst_zoff;       // interior plane z of dst is stored at plane z + dst_zoff
   int wrap_z;         // 1: periodic along z inside this buffer; 0: ghost planes present
+  int ty;             // rows per tile (<= TY); tiles start at min(j * ty, H - ty), so only the last may overlap
   int tz;             // planes per z-chunk
   int nxt, nyt, nzc;  // tiles along x, y; chunks along z
   int z_lo, z_hi;     // only interior planes [z_lo, z_hi) are computed (halo/interior split for overlap)
   int slot;
+  int mode;           // experiment switches (0 in production): 1 = copy skeleton (no math), 2 = no stores, 4 = streaming stores
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -147,7 +154,7 @@ __device__ __forceinline__ ItemCoord decode_item(const Params& p, int item) {
   const int yt = r % p.nyt;
   const int zc = r / p.nyt;
   c.x0 = xt * TX;
-  c.y0 = yt * TY;
+  c.y0 = min(yt * p.ty, p.H - p.ty);
   c.z0 = p.z_lo + zc * p.tz;
   c.nz = min(p.tz, p.z_hi - c.z0);
   return c;
@@ -160,91 +167,128 @@ __device__ __forceinline__ int src_plane(const Params& p, int z0, int j) {
   return pz;
 }
 
-// One consumer iteration with the register window rotated by R (compile-time), so the 5-plane
-// window never moves between registers.
+// Predicated 8-byte read-only load (no branch): only the two seam lanes of a warp touch global memory.
+__device__ __forceinline__ void ldg_f2_if(bool pred, const float* ptr, float2& v) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t"
+      "@p ld.global.nc.v2.f32 {%0, %1}, [%3];\n\t}"
+      : "+f"(v.x), "+f"(v.y)
+      : "r"(uint32_t(pred)), "l"(ptr));
+}
+
+// Per-warp consumer state that survives across planes and items.
+struct Consumer {
+  const float* P;        // coefficients (__constant__)
+  float* ring;
+  uint64_t* full;
+  uint64_t* empty;
+  uint32_t s;            // ring stage of the plane arriving next
+  uint32_t parity;       // its mbarrier phase parity
+  int row, lane;
+  uint32_t toff;         // row * W + 4 * lane: this lane's quad inside a tile plane (elements)
+  bool is_seam;          // lane 0 or 31
+};
+
+__device__ __forceinline__ void advance_stage(Consumer& c) {
+  c.s = (c.s + 1) & (STAGES - 1);
+  c.parity ^= (c.s == 0);
+}
+
+// Warm-up plane (local index 0..3 of an item): only enters the register window.
 template <int R>
-__device__ __forceinline__ void consume_plane(const Params& p, const float* __restrict__ P, float* ring, uint64_t* full,
-                                              uint64_t* empty, const ItemCoord& ic, int k, uint32_t& it, int row, int lane,
-                                              float4 (&wu)[5], float4 (&wv)[5], float2 (&seam_next)[2]) {
-  const int s = it % STAGES;
-  mbar_wait(&full[s], (it / STAGES) & 1);
-  const float* st = ring + s * STAGE_FLOATS;
-  // newest plane into window slot (R + 4) % 5
-  wu[(R + 4) % 5] = lds128(st + (row + 2) * TX + 4 * lane);
-  wv[(R + 4) % 5] = lds128(st + ROWS * TX + (row + 2) * TX + 4 * lane);
-  const bool edge_plane = (k < 2) || (k >= ic.nz + 2);
-  if (edge_plane) {
+__device__ __forceinline__ void warm_plane(Consumer& c, bool release_now, float4 (&wu)[5], float4 (&wv)[5]) {
+  mbar_wait(&c.full[c.s], c.parity);
+  const float* st = c.ring + c.s * STAGE_FLOATS + (c.row + 2) * TX + 4 * c.lane;
+  wu[(R + 4) % 5] = lds128(st);
+  wv[(R + 4) % 5] = lds128(st + ROWS * TX);
+  if (release_now) {
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);
+    if (c.lane == 0) mbar_arrive(&c.empty[c.s]);
   }
-  float2 seam_cur[2] = {seam_next[0], seam_next[1]};
-  // prefetch the seam cells of plane k-1 (in-plane source of the next iteration)
-  if (k >= 3 && k <= ic.nz + 2 && (lane == 0 || lane == 31)) {
-    const int pz = src_plane(p, ic.z0, k - 1);
-    int xs = (lane == 0) ? ic.x0 - 2 : ic.x0 + TX;
-    xs = xs < 0 ? xs + p.W : (xs >= p.W ? xs - p.W : xs);
-    const float* g = p.src + (int64_t(pz) * p.H + (ic.y0 + row)) * p.W + xs;
-    seam_next[0] = __ldg(reinterpret_cast<const float2*>(g));
-    seam_next[1] = __ldg(reinterpret_cast<const float2*>(g + p.src_field));
+  advance_stage(c);
+}
+
+// Steady-state plane: local plane k arrives, output plane k-2 is produced.
+//   seam_ptr : this lane's seam cells in the source plane that will be the in-plane source NEXT iteration
+//   out      : this lane's quad in the output plane
+template <int R, bool STREAM_STORES>
+__device__ __forceinline__ void steady_plane(Consumer& c, bool drain, bool prefetch_seam, const float* seam_ptr,
+                                             int64_t src_field, float* out, int64_t dst_field, int mode,
+                                             float4 (&wu)[5], float4 (&wv)[5], float2 (&seam_next)[2]) {
+  const float* P = c.P;
+  mbar_wait(&c.full[c.s], c.parity);
+  {
+    const float* st = c.ring + c.s * STAGE_FLOATS + (c.row + 2) * TX + 4 * c.lane;
+    wu[(R + 4) % 5] = lds128(st);
+    wv[(R + 4) % 5] = lds128(st + ROWS * TX);
   }
-  if (k >= 4) {
-    const int s2 = (s + STAGES - 2) % STAGES;
-    const float* sp = ring + s2 * STAGE_FLOATS + 4 * lane;
-    float4 ou, ov;
-    {
-      // window in logical order z-2..z+2
-      const float4 wl_u[5] = {wu[(R + 0) % 5], wu[(R + 1) % 5], wu[(R + 2) % 5], wu[(R + 3) % 5], wu[(R + 4) % 5]};
-      const float4 wl_v[5] = {wv[(R + 0) % 5], wv[(R + 1) % 5], wv[(R + 2) % 5], wv[(R + 3) % 5], wv[(R + 4) % 5]};
-      const float4 cu = wl_u[2], cv = wl_v[2];
-      float2 Lu_lo, Lu_hi, Lv_lo, Lv_hi;
-      {
-        const float4 y[4] = {lds128(sp + (row + 0) * TX), lds128(sp + (row + 1) * TX), lds128(sp + (row + 3) * TX),
-                             lds128(sp + (row + 4) * TX)};
-        float Lz = __shfl_up_sync(0xffffffffu, cu.z, 1), Lw = __shfl_up_sync(0xffffffffu, cu.w, 1);
-        float Rx = __shfl_down_sync(0xffffffffu, cu.x, 1), Ry = __shfl_down_sync(0xffffffffu, cu.y, 1);
-        if (lane == 0) { Lz = seam_cur[0].x; Lw = seam_cur[0].y; }
-        if (lane == 31) { Rx = seam_cur[0].x; Ry = seam_cur[0].y; }
-        lap_quad(P, wl_u, y, Lz, Lw, Rx, Ry, Lu_lo, Lu_hi);
-      }
-      {
-        const float* spv = sp + ROWS * TX;
-        const float4 y[4] = {lds128(spv + (row + 0) * TX), lds128(spv + (row + 1) * TX), lds128(spv + (row + 3) * TX),
-                             lds128(spv + (row + 4) * TX)};
-        float Lz = __shfl_up_sync(0xffffffffu, cv.z, 1), Lw = __shfl_up_sync(0xffffffffu, cv.w, 1);
-        float Rx = __shfl_down_sync(0xffffffffu, cv.x, 1), Ry = __shfl_down_sync(0xffffffffu, cv.y, 1);
-        if (lane == 0) { Lz = seam_cur[1].x; Lw = seam_cur[1].y; }
-        if (lane == 31) { Rx = seam_cur[1].x; Ry = seam_cur[1].y; }
-        lap_quad(P, wl_v, y, Lz, Lw, Rx, Ry, Lv_lo, Lv_hi);
-      }
-      // the y-neighbour rows of plane k-2 are no longer needed
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s2]);
-      const float au = P[P_ALPHA + 0], av = P[P_ALPHA + 1], dt = P[P_DT];
-      float2 r;
-      r = fma2(Lu_lo, au, cubic2(P + P_POLY, lo(cu), lo(cv)));
-      r = fma2(r, dt, lo(cu));
-      ou.x = r.x; ou.y = r.y;
-      r = fma2(Lu_hi, au, cubic2(P + P_POLY, hi(cu), hi(cv)));
-      r = fma2(r, dt, hi(cu));
-      ou.z = r.x; ou.w = r.y;
-      r = fma2(Lv_lo, av, cubic2(P + P_POLY + 10, lo(cu), lo(cv)));
-      r = fma2(r, dt, lo(cv));
-      ov.x = r.x; ov.y = r.y;
-      r = fma2(Lv_hi, av, cubic2(P + P_POLY + 10, hi(cu), hi(cv)));
-      r = fma2(r, dt, hi(cv));
-      ov.z = r.x; ov.w = r.y;
+  if (drain) {  // planes past the chunk end are z-neighbours only
+    __syncwarp();
+    if (c.lane == 0) mbar_arrive(&c.empty[c.s]);
+  }
+  const float2 seam_u = seam_next[0], seam_v = seam_next[1];
+  if (prefetch_seam) {
+    ldg_f2_if(c.is_seam, seam_ptr, seam_next[0]);
+    ldg_f2_if(c.is_seam, seam_ptr + src_field, seam_next[1]);
+  }
+  const uint32_t s2 = (c.s + STAGES - 2) & (STAGES - 1);
+  const float* sp = c.ring + s2 * STAGE_FLOATS + c.row * TX + 4 * c.lane;
+  const float4 wl_u[5] = {wu[(R + 0) % 5], wu[(R + 1) % 5], wu[(R + 2) % 5], wu[(R + 3) % 5], wu[(R + 4) % 5]};
+  const float4 wl_v[5] = {wv[(R + 0) % 5], wv[(R + 1) % 5], wv[(R + 2) % 5], wv[(R + 3) % 5], wv[(R + 4) % 5]};
+  const float4 cu = wl_u[2], cv = wl_v[2];
+  if (mode & 1) {   // experiment: memory skeleton only (TMA in, STG out, no arithmetic)
+    __syncwarp();
+    if (c.lane == 0) mbar_arrive(&c.empty[s2]);
+    if (!(mode & 2)) {
+      *reinterpret_cast<float4*>(out) = cu;
+      *reinterpret_cast<float4*>(out + dst_field) = cv;
     }
-    const int zo = ic.z0 + (k - 4) + p.dst_zoff;
-    float* o = p.dst + (int64_t(zo) * p.H + (ic.y0 + row)) * p.W + ic.x0 + 4 * lane;
-    *reinterpret_cast<float4*>(o) = ou;
-    *reinterpret_cast<float4*>(o + p.dst_field) = ov;
+    advance_stage(c);
+    return;
   }
-  ++it;
+  float2 Lu_lo, Lu_hi, Lv_lo, Lv_hi;
+  {
+    const float4 y[4] = {lds128(sp), lds128(sp + TX), lds128(sp + 3 * TX), lds128(sp + 4 * TX)};
+    float Lz = __shfl_up_sync(0xffffffffu, cu.z, 1), Lw = __shfl_up_sync(0xffffffffu, cu.w, 1);
+    float Rx = __shfl_down_sync(0xffffffffu, cu.x, 1), Ry = __shfl_down_sync(0xffffffffu, cu.y, 1);
+    if (c.lane == 0) { Lz = seam_u.x; Lw = seam_u.y; }
+    if (c.lane == 31) { Rx = seam_u.x; Ry = seam_u.y; }
+    lap_quad(P, wl_u, y, Lz, Lw, Rx, Ry, Lu_lo, Lu_hi);
+  }
+  {
+    const float* spv = sp + ROWS * TX;
+    const float4 y[4] = {lds128(spv), lds128(spv + TX), lds128(spv + 3 * TX), lds128(spv + 4 * TX)};
+    float Lz = __shfl_up_sync(0xffffffffu, cv.z, 1), Lw = __shfl_up_sync(0xffffffffu, cv.w, 1);
+    float Rx = __shfl_down_sync(0xffffffffu, cv.x, 1), Ry = __shfl_down_sync(0xffffffffu, cv.y, 1);
+    if (c.lane == 0) { Lz = seam_v.x; Lw = seam_v.y; }
+    if (c.lane == 31) { Rx = seam_v.x; Ry = seam_v.y; }
+    lap_quad(P, wl_v, y, Lz, Lw, Rx, Ry, Lv_lo, Lv_hi);
+  }
+  // the y-neighbour rows of plane k-2 are no longer needed
+  __syncwarp();
+  if (c.lane == 0) mbar_arrive(&c.empty[s2]);
+  const float au = P[P_ALPHA + 0], av = P[P_ALPHA + 1], dt = P[P_DT];
+  const float2 ou_lo = fma2(fma2(Lu_lo, au, cubic2(P + P_POLY, lo(cu), lo(cv))), dt, lo(cu));
+  const float2 ou_hi = fma2(fma2(Lu_hi, au, cubic2(P + P_POLY, hi(cu), hi(cv))), dt, hi(cu));
+  const float2 ov_lo = fma2(fma2(Lv_lo, av, cubic2(P + P_POLY + 10, lo(cu), lo(cv))), dt, lo(cv));
+  const float2 ov_hi = fma2(fma2(Lv_hi, av, cubic2(P + P_POLY + 10, hi(cu), hi(cv))), dt, hi(cv));
+  const float4 ou = make_float4(ou_lo.x, ou_lo.y, ou_hi.x, ou_hi.y);
+  const float4 ov = make_float4(ov_lo.x, ov_lo.y, ov_hi.x, ov_hi.y);
+  if (mode & 2) {
+    if (ou.x == 123.456f && ov.y == 654.321f) *reinterpret_cast<float4*>(out) = ou;   // keeps the math alive
+  } else if (STREAM_STORES) {
+    __stcs(reinterpret_cast<float4*>(out), ou);
+    __stcs(reinterpret_cast<float4*>(out + dst_field), ov);
+  } else {
+    *reinterpret_cast<float4*>(out) = ou;
+    *reinterpret_cast<float4*>(out + dst_field) = ov;
+  }
+  advance_stage(c);
 }
 
 // SLOT is a template parameter so that every coefficient is a compile-time constant-bank address
 // (c[3][imm] / hoisted LDCU) instead of an indexed LDC per use.
-template <int SLOT>
+template <int SLOT, bool STREAM_STORES>
 __global__ void __launch_bounds__(THREADS, 1)
 k_gs3d_fwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_halo,
                const __grid_constant__ Params p) {
@@ -256,39 +300,42 @@ k_gs3d_fwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], TY);
+      mbar_init(&empty[s], p.ty);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   const int nitems = p.nxt * p.nyt * p.nzc;
 
-  if (warp == TY) {
-    // ===== producer warp: one elected lane issues every TMA =====
-    if (lane == 0) {
+  if (warp >= TY) {
+    // ===== producer warp-group: one elected lane issues every TMA =====
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PRODUCER_REGS));
+    if (warp == TY && lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_main)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_halo)) : "memory");
       uint32_t it = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const ItemCoord ic = decode_item(p, item);
-        int yt = ic.y0 - 2;
-        if (yt < 0) yt += p.H;
-        int yb = ic.y0 + TY;
-        if (yb >= p.H) yb -= p.H;
+        int yh[4] = {ic.y0 - 2, ic.y0 - 1, ic.y0 + p.ty, ic.y0 + p.ty + 1};   // periodic halo rows
+#pragma unroll
+        for (int h = 0; h < 4; ++h) yh[h] = yh[h] < 0 ? yh[h] + p.H : (yh[h] >= p.H ? yh[h] - p.H : yh[h]);
+        const uint32_t bytes_main = 2u * uint32_t(p.ty) * TX * 4u, bytes_halo = 2u * 4u * TX * 4u;
         for (int k = 0; k < ic.nz + 4; ++k, ++it) {
           const int s = it % STAGES;
           if (it >= STAGES) mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
           const bool with_halo = (k >= 2) && (k < ic.nz + 2);
           const int pz = src_plane(p, ic.z0, k);
           float* st = ring + s * STAGE_FLOATS;
-          mbar_expect_tx(&full[s], with_halo ? 2u * ROWS * TX * 4u : 2u * TY * TX * 4u);
+          mbar_expect_tx(&full[s], with_halo ? bytes_main + bytes_halo : bytes_main);
 #pragma unroll
           for (int f = 0; f < 2; ++f) {
             float* sf = st + f * ROWS * TX;
             tma_load_4d(sf + 2 * TX, &tm_main, &full[s], ic.x0, ic.y0, pz, f);
             if (with_halo) {
-              tma_load_4d(sf, &tm_halo, &full[s], ic.x0, yt, pz, f);
-              tma_load_4d(sf + (TY + 2) * TX, &tm_halo, &full[s], ic.x0, yb, pz, f);
+              tma_load_4d(sf, &tm_halo, &full[s], ic.x0, yh[0], pz, f);
+              tma_load_4d(sf + TX, &tm_halo, &full[s], ic.x0, yh[1], pz, f);
+              tma_load_4d(sf + (p.ty + 2) * TX, &tm_halo, &full[s], ic.x0, yh[2], pz, f);
+              tma_load_4d(sf + (p.ty + 3) * TX, &tm_halo, &full[s], ic.x0, yh[3], pz, f);
             }
           }
         }
@@ -298,27 +345,58 @@ k_gs3d_fwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
   }
 
   // ===== consumer warps =====
-  const float* P = c_prep[SLOT].f;
-  const int row = warp;
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONSUMER_REGS));
+  if (warp >= p.ty) return;   // tile shorter than 16 rows: the spare warps are done (after the aligned setmaxnreg)
+  Consumer c;
+  c.P = c_prep[SLOT].f;
+  c.ring = ring;
+  c.full = full;
+  c.empty = empty;
+  c.s = 0;
+  c.parity = 0;
+  c.row = warp;
+  c.lane = lane;
+  c.toff = uint32_t(warp) * uint32_t(p.W) + 4u * uint32_t(lane);
+  c.is_seam = (lane == 0) || (lane == 31);
+  const int64_t plane = int64_t(p.H) * p.W;
   float4 wu[5], wv[5];
   float2 seam_next[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-  uint32_t it = 0;
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
     const ItemCoord ic = decode_item(p, item);
-    const int nk = ic.nz + 4;
-    int k = 0;
-    for (; k + 5 <= nk; k += 5) {
-      consume_plane<0>(p, P, ring, full, empty, ic, k + 0, it, row, lane, wu, wv, seam_next);
-      consume_plane<1>(p, P, ring, full, empty, ic, k + 1, it, row, lane, wu, wv, seam_next);
-      consume_plane<2>(p, P, ring, full, empty, ic, k + 2, it, row, lane, wu, wv, seam_next);
-      consume_plane<3>(p, P, ring, full, empty, ic, k + 3, it, row, lane, wu, wv, seam_next);
-      consume_plane<4>(p, P, ring, full, empty, ic, k + 4, it, row, lane, wu, wv, seam_next);
+    // uniform per-item bases; the per-lane part (toff / seam_off) never changes
+    const float* src_xy = p.src + int64_t(ic.y0) * p.W + ic.x0;
+    float* out = p.dst + (int64_t(ic.z0 + p.dst_zoff) * p.H + ic.y0) * p.W + ic.x0 + c.toff;
+    int xs = (lane == 0) ? ic.x0 - 2 : ic.x0 + TX;
+    xs = xs < 0 ? xs + p.W : (xs >= p.W ? xs - p.W : xs);
+    const int seam_off = warp * p.W + xs - ic.x0;
+    int pz = src_plane(p, ic.z0, 2);   // source plane whose seam cells are fetched next (local plane 2 first)
+
+    warm_plane<0>(c, true, wu, wv);
+    warm_plane<1>(c, true, wu, wv);
+    warm_plane<2>(c, false, wu, wv);
+    warm_plane<3>(c, false, wu, wv);
+    ldg_f2_if(c.is_seam, src_xy + int64_t(pz) * plane + seam_off, seam_next[0]);
+    ldg_f2_if(c.is_seam, src_xy + int64_t(pz) * plane + seam_off + p.src_field, seam_next[1]);
+
+    const int nk = ic.nz + 4;   // local planes 0 .. nz+3; outputs for k = 4 .. nz+3
+#define PERCNN_STEADY(RR)                                                                                     \
+  {                                                                                                           \
+    pz = (p.wrap_z && pz + 1 >= p.D) ? pz + 1 - p.D : pz + 1;                                                 \
+    steady_plane<RR, STREAM_STORES>(c, k >= ic.nz + 2, k <= ic.nz + 2, src_xy + int64_t(pz) * plane + seam_off, p.src_field, \
+                     out, p.dst_field, p.mode, wu, wv, seam_next);                                                    \
+    out += plane;                                                                                             \
+    ++k;                                                                                                      \
+  }
+    int k = 4;
+    PERCNN_STEADY(4)
+    while (k + 5 <= nk) {
+      PERCNN_STEADY(0) PERCNN_STEADY(1) PERCNN_STEADY(2) PERCNN_STEADY(3) PERCNN_STEADY(4)
     }
-    // tail (nk % 5 planes); the window rotation restarts with the next item, which refills it anyway
-    if (k < nk) { consume_plane<0>(p, P, ring, full, empty, ic, k, it, row, lane, wu, wv, seam_next); ++k; }
-    if (k < nk) { consume_plane<1>(p, P, ring, full, empty, ic, k, it, row, lane, wu, wv, seam_next); ++k; }
-    if (k < nk) { consume_plane<2>(p, P, ring, full, empty, ic, k, it, row, lane, wu, wv, seam_next); ++k; }
-    if (k < nk) { consume_plane<3>(p, P, ring, full, empty, ic, k, it, row, lane, wu, wv, seam_next); ++k; }
+    if (k < nk) PERCNN_STEADY(0)
+    if (k < nk) PERCNN_STEADY(1)
+    if (k < nk) PERCNN_STEADY(2)
+    if (k < nk) PERCNN_STEADY(3)
+#undef PERCNN_STEADY
   }
 }
 

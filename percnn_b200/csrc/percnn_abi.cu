@@ -1,6 +1,7 @@
 // C-ABI of libpercnn_b200.so (see include/percnn_b200.h).  Single translation unit: the kernels share
 // one __constant__ parameter block, so everything is compiled together for sm_100a.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -59,7 +60,8 @@ struct percnn_plan {
   int64_t state_elems = 0;
   int64_t launches = 0;
   bool use_tma = false;
-  int tz = 0;
+  int ty = 16, tz = 0;
+  int tma_mode = 0, tz_override = 0, grid_override = 0;   // experiment knobs (PERCNN_TMA_MODE / _TZ / _GRID env)
   PrepBlock* d_prep = nullptr;
   float* d_k5w = nullptr;
   EncodeTiledFn encode = nullptr;
@@ -83,16 +85,37 @@ int generic_grid(const percnn_plan* p) {
   return int(blocks < 1 ? 1 : blocks);
 }
 
-// z-chunk length that minimises the makespan rounds * (tz + 4) of the persistent TMA kernel
-int choose_tz(int nxy, int depth, int nsm) {
-  int best = depth, best_cost = 1 << 30;
-  for (int tz = 4; tz <= depth; ++tz) {
-    const int nzc = (depth + tz - 1) / tz;
-    const int rounds = (nxy * nzc + nsm - 1) / nsm;
-    const int cost = rounds * (tz + 4);
-    if (cost < best_cost || (cost == best_cost && tz > best)) {
-      best_cost = cost;
-      best = tz;
+// Work decomposition of the persistent TMA kernel.  A tile is 128 x ty cells, an item is a tile marched over
+// tz planes (+4 halo planes).  Measured on B200 (profiles/r01_sweep_tma.txt): it pays to keep every CTA on the
+// same planes at the same time (one item per CTA, all items in one round) -- 128 CTAs in lock-step beat 148
+// CTAs on staggered z-chunks by 23 % -- so the cost model charges extra for multi-round schedules.
+struct TmaTiling {
+  int ty, tz, nyt, nzc;
+};
+double tiling_cost(int nxt, int H, int depth, int nsm, int ty, int nzc, TmaTiling* out) {
+  const int nyt = (H + ty - 1) / ty;
+  const int tz = (depth + nzc - 1) / nzc;
+  const int nz_chunks = (depth + tz - 1) / tz;
+  const long items = long(nxt) * nyt * nz_chunks;
+  const long rounds = (items + nsm - 1) / nsm;
+  double cost = double(rounds) * (tz + 4) * (8.0 + 2.0 * ty + 4.0);   // fixed per-plane latency + rows in + rows out
+  if (rounds > 1) cost *= 1.25;
+  if (out) *out = TmaTiling{ty, tz, nyt, nz_chunks};
+  return cost;
+}
+TmaTiling choose_tiling(int nxt, int H, int depth, int nsm, int fixed_ty) {
+  TmaTiling best{16, depth, (H + 15) / 16, 1};
+  double best_cost = 1e300;
+  for (int ty = (fixed_ty ? fixed_ty : 1); ty <= (fixed_ty ? fixed_ty : tma3d::TY); ++ty) {
+    if (ty > H) break;
+    for (int nzc = 1; nzc <= depth; ++nzc) {
+      TmaTiling t;
+      const double c = tiling_cost(nxt, H, depth, nsm, ty, nzc, &t);
+      if (c < best_cost) {
+        best_cost = c;
+        best = t;
+      }
+      if ((depth + nzc - 1) / nzc <= 2) break;
     }
   }
   return best;
@@ -112,8 +135,8 @@ int get_maps(percnn_plan* p, const void* src, const CUtensorMap** main_map, cons
   cuuint64_t gdim[4] = {cuuint64_t(g.W), cuuint64_t(g.H), planes, 2};
   cuuint64_t gstr[3] = {cuuint64_t(g.W) * 4, cuuint64_t(g.plane) * 4, cuuint64_t(g.field) * 4};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  cuuint32_t box_main[4] = {tma3d::TX, tma3d::TY, 1, 1};
-  cuuint32_t box_halo[4] = {tma3d::TX, 2, 1, 1};
+  cuuint32_t box_main[4] = {tma3d::TX, cuuint32_t(p->ty), 1, 1};
+  cuuint32_t box_halo[4] = {tma3d::TX, 1, 1, 1};   // halo rows go one by one so any tile origin wraps correctly
   CUresult r = p->encode(&m.main_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(src), gdim, gstr, box_main,
                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -149,18 +172,30 @@ int launch_tma_fwd(percnn_plan* p, const float* src, float* dst, int z_lo, int z
   prm.dst_zoff = g.ghost;
   prm.wrap_z = g.ghost ? 0 : 1;
   prm.nxt = g.W / tma3d::TX;
-  prm.nyt = g.H / tma3d::TY;
   const int depth = z_hi - z_lo;
-  prm.tz = (z_lo == 0 && z_hi == g.D) ? p->tz : choose_tz(prm.nxt * prm.nyt, depth, p->sm_count);
-  prm.nzc = (depth + prm.tz - 1) / prm.tz;
+  TmaTiling til = (z_lo == 0 && z_hi == g.D) ? TmaTiling{p->ty, p->tz, (g.H + p->ty - 1) / p->ty, (g.D + p->tz - 1) / p->tz}
+                                             : choose_tiling(prm.nxt, g.H, depth, p->sm_count, p->ty);
+  if (p->tz_override > 0) {
+    til.tz = p->tz_override < depth ? p->tz_override : depth;
+    til.nzc = (depth + til.tz - 1) / til.tz;
+  }
+  prm.ty = p->ty;
+  prm.nyt = til.nyt;
+  prm.tz = til.tz;
+  prm.nzc = til.nzc;
   prm.z_lo = z_lo;
   prm.z_hi = z_hi;
   prm.slot = p->slot;
+  prm.mode = p->tma_mode;
   const int nitems = prm.nxt * prm.nyt * prm.nzc;
-  const int grid = nitems < p->sm_count ? nitems : p->sm_count;
+  int grid = nitems < p->sm_count ? nitems : p->sm_count;
+  if (p->grid_override > 0 && p->grid_override < grid) grid = p->grid_override;
   switch (p->slot) {
 #define PERCNN_TMA_CASE(S) \
-  case S: tma3d::k_gs3d_fwd_tma<S><<<grid, tma3d::THREADS, tma3d::SMEM_BYTES, st>>>(*mm, *hm, prm); break;
+  case S:                                                                                                   \
+    if (prm.mode & 4) tma3d::k_gs3d_fwd_tma<S, true><<<grid, tma3d::THREADS, tma3d::SMEM_BYTES, st>>>(*mm, *hm, prm); \
+    else tma3d::k_gs3d_fwd_tma<S, false><<<grid, tma3d::THREADS, tma3d::SMEM_BYTES, st>>>(*mm, *hm, prm);   \
+    break;
     PERCNN_TMA_CASE(0) PERCNN_TMA_CASE(1) PERCNN_TMA_CASE(2) PERCNN_TMA_CASE(3) PERCNN_TMA_CASE(4) PERCNN_TMA_CASE(5)
 #undef PERCNN_TMA_CASE
     default: return fail(PERCNN_ERR_INVALID, "bad parameter slot");
@@ -340,7 +375,7 @@ int percnn_plan_create(const percnn_desc_t* d, percnn_plan_t** out) {
     }
     p->use_tma = d->cell == PERCNN_CELL_PI && d->ksize == 1 && d->ndim == 3 && d->dtype == PERCNN_F32 &&
                  !(d->flags & (PERCNN_FLAG_NO_TMA | PERCNN_FLAG_EVAL_BRANCH)) && g.W % tma3d::TX == 0 &&
-                 g.H % tma3d::TY == 0 && g.D >= 4;
+                 g.H >= 4 && g.D >= 4;
     if (p->use_tma) {
       void* fn = nullptr;
       cudaDriverEntryPointQueryResult qres;
@@ -352,12 +387,24 @@ int percnn_plan_create(const percnn_desc_t* d, percnn_plan_t** out) {
       cudaError_t ae = cudaSuccess;
       switch (p->slot) {
 #define PERCNN_TMA_ATTR(S) \
-  case S: ae = cudaFuncSetAttribute(tma3d::k_gs3d_fwd_tma<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma3d::SMEM_BYTES); break;
+  case S:                                                                                                              \
+    ae = cudaFuncSetAttribute(tma3d::k_gs3d_fwd_tma<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma3d::SMEM_BYTES); \
+    if (ae == cudaSuccess)                                                                                               \
+      ae = cudaFuncSetAttribute(tma3d::k_gs3d_fwd_tma<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma3d::SMEM_BYTES); \
+    break;
         PERCNN_TMA_ATTR(0) PERCNN_TMA_ATTR(1) PERCNN_TMA_ATTR(2) PERCNN_TMA_ATTR(3) PERCNN_TMA_ATTR(4) PERCNN_TMA_ATTR(5)
 #undef PERCNN_TMA_ATTR
       }
       if (ae != cudaSuccess) { rc = fail(PERCNN_ERR_CUDA, "cudaFuncSetAttribute(tma) failed"); break; }
-      p->tz = choose_tz((g.W / tma3d::TX) * (g.H / tma3d::TY), g.D, p->sm_count);
+      int fixed_ty = 0;
+      if (const char* e = getenv("PERCNN_TMA_TY")) fixed_ty = atoi(e);
+      if (fixed_ty < 0 || fixed_ty > tma3d::TY || fixed_ty > g.H) fixed_ty = 0;
+      const TmaTiling til = choose_tiling(g.W / tma3d::TX, g.H, g.D, p->sm_count, fixed_ty);
+      p->ty = til.ty;
+      p->tz = til.tz;
+      if (const char* e = getenv("PERCNN_TMA_MODE")) p->tma_mode = atoi(e);
+      if (const char* e = getenv("PERCNN_TMA_TZ")) p->tz_override = atoi(e);
+      if (const char* e = getenv("PERCNN_TMA_GRID")) p->grid_override = atoi(e);
     }
   } while (0);
   if (rc != PERCNN_OK) {

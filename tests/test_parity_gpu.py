@@ -15,6 +15,9 @@ import torch
 
 from oracle import percnn_oracle as po
 from percnn_b200 import _lib, engine
+
+torch.backends.cudnn.allow_tf32 = False      # the stock upscaler convs must not silently run in TF32
+torch.backends.cuda.matmul.allow_tf32 = False
 from tests.helpers import (GOLDEN_CASES, cell_params_dict, load_golden, load_weights, make_cell, rel_l2, rel_linf)
 
 pytestmark = pytest.mark.gpu
@@ -134,7 +137,6 @@ def test_branch_evaluation_agrees_with_folded_cubic(tag):
     step_tol, roll_tol, _ = _tols(z["h0"].dtype)
     assert rel_l2(b, z["traj"]) <= roll_tol
     assert rel_l2(a, b) <= roll_tol
-    assert not np.array_equal(a, b) or z["h0"].dtype == np.float64 or True
 
 
 def test_k5_backward_is_a_loud_error_not_a_fallback():
@@ -146,7 +148,7 @@ def test_k5_backward_is_a_loud_error_not_a_fallback():
         states.sum().backward()
 
 
-@pytest.mark.parametrize("shape", [(8, 16, 128), (5, 32, 256), (12, 48, 128)])
+@pytest.mark.parametrize("shape", [(8, 16, 128), (5, 32, 256), (12, 48, 128), (9, 37, 256), (6, 20, 128), (7, 5, 128)])
 def test_tma_kernel_matches_oracle_and_generic_kernel(shape):
     """Sizes that select the TMA z-marching kernel; oracle = the reference's ATen op sequence on CPU."""
     params = load_weights("gs3d")
