@@ -80,12 +80,12 @@ class Plan:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h is not None and h.value:
-            try:
+        try:
+            if h is not None and h.value:
                 self._L.percnn_plan_destroy(h)
-            except Exception:
-                pass
-            self._h = ctypes.c_void_p()
+                h.value = None
+        except Exception:       # interpreter shutdown: module globals may already be gone
+            pass
 
     # -- shapes ---------------------------------------------------------------------------------
     @property

@@ -78,19 +78,33 @@ class SlabRollout:
             raise NotImplementedError("slab mode drives the TMA kernel (W % 128 == 0, H % 16 == 0, fp32, k = 1)")
         self.flat = engine.pack_params(cell._packed_tensors(), torch.float32)
         self.plan.params_load(self.flat)
-        self.transport = "nccl" if transport == "auto" else transport
+        self.transport = transport
         self.symm = None
         shape = self.plan.buffer_shape
-        if self.transport == "symm" and world > 1:
-            import torch.distributed._symmetric_memory as symm_mem
-            both = symm_mem.empty((2, *shape), dtype=torch.float32, device=self.device)
-            self.symm = symm_mem.rendezvous(both, group=group if group is not None else dist.group.WORLD)
+        if transport in ("auto", "symm") and world > 1:
+            # peer-mapped buffers over NVLink; every rank must take the same branch, so agree on the outcome
+            ok, both = 1, None
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                both = symm_mem.empty((2, *shape), dtype=torch.float32, device=self.device)
+                self.symm = symm_mem.rendezvous(both, group=group if group is not None else dist.group.WORLD)
+            except Exception as e:  # noqa: BLE001
+                if transport == "symm":
+                    raise
+                ok, self.symm, self._symm_error = 0, None, repr(e)[:200]
+            flag = torch.tensor([ok], device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) == 0:
+                self.symm = None
+        if self.symm is not None:
+            self.transport = "symm"
             both.zero_()
             self.bufs = [both[0], both[1]]
             lo, hi = (rank - 1) % world, (rank + 1) % world
             self.peer_lo = self.symm.get_buffer(lo, (2, *shape), torch.float32)
             self.peer_hi = self.symm.get_buffer(hi, (2, *shape), torch.float32)
         else:
+            self.transport = "nccl" if world > 1 else "local"
             self.bufs = [torch.zeros(shape, dtype=torch.float32, device=self.device) for _ in range(2)]
         self.cur = 0
         self.comm_stream = torch.cuda.Stream(self.device)
