@@ -76,10 +76,29 @@ struct percnn_plan {
 
 namespace {
 
-int generic_grid(const percnn_plan* p) {
+size_t state_bytes(const percnn_plan* p) { return size_t(p->state_elems) * p->elt; }
+
+bool is_k5(const percnn_plan* p) { return p->desc.cell == PERCNN_CELL_PI && p->desc.ksize == 5; }
+int k5_blocks(const percnn_plan* p) {
+  return ((p->g.W + k5::BT_X - 1) / k5::BT_X) * ((p->g.H + k5::BT_Y - 1) / k5::BT_Y);
+}
+// workspace: [accumulators | counter | per-block partials | two state-sized scratch buffers]
+size_t ws_header_bytes(const percnn_plan* p) {   // bytes zeroed by param_grads_begin
+  return is_k5(p) ? (size_t(p->nparams) * sizeof(double) + 255) / 256 * 256 : kWsPartials;
+}
+size_t ws_states_off(const percnn_plan* p) {
+  if (!is_k5(p)) return kWsStates;
+  const size_t part = size_t(k5_blocks(p)) * size_t(p->nparams) * sizeof(float);
+  return ws_header_bytes(p) + (part + 255) / 256 * 256;
+}
+
+
+// per_sm: resident blocks per SM to aim for.  The adjoint kernels end in a 6..22-value block reduction, so they
+// get fewer, longer-running blocks (more cells per thread to amortise it).
+int generic_grid(const percnn_plan* p, int per_sm = 8) {
   const int64_t ncell = int64_t(p->g.D) * p->g.H * p->g.W;
   int64_t blocks = (ncell + kGenericThreads - 1) / kGenericThreads;
-  const int64_t cap = int64_t(p->sm_count) * 8;
+  const int64_t cap = int64_t(p->sm_count) * per_sm;
   if (blocks > cap) blocks = cap;
   if (blocks > kMaxBlocks) blocks = kMaxBlocks;
   return int(blocks < 1 ? 1 : blocks);
@@ -251,7 +270,7 @@ int step_fwd_any(percnn_plan* p, const void* src, void* dst, cudaStream_t st) {
 template <typename T>
 int step_bwd_t(percnn_plan* p, const T* h, const T* gout, const T* gadd, T* gin, char* ws, cudaStream_t st) {
   const Geom& g = p->g;
-  const int grid = generic_grid(p);
+  const int grid = generic_grid(p, 2);
   double* acc = reinterpret_cast<double*>(ws + kWsAcc);
   unsigned* counter = reinterpret_cast<unsigned*>(ws + kWsCounter);
   double* partials = reinterpret_cast<double*>(ws + kWsPartials);
@@ -273,6 +292,21 @@ int step_bwd_t(percnn_plan* p, const T* h, const T* gout, const T* gadd, T* gin,
 }
 
 int step_bwd_any(percnn_plan* p, const void* h, const void* gout, const void* gadd, void* gin, void* ws, cudaStream_t st) {
+  if (is_k5(p)) {
+    char* w = static_cast<char*>(ws);
+    double* acc = reinterpret_cast<double*>(w);
+    float* partials = reinterpret_cast<float*>(w + ws_header_bytes(p));
+    dim3 grid((p->g.W + k5::BT_X - 1) / k5::BT_X, (p->g.H + k5::BT_Y - 1) / k5::BT_Y);
+    const int np = int(p->nparams);
+    k5::k_pi_k5_bwd<<<grid, k5::BTHREADS, k5::bwd_smem_floats(p->desc.hidden, np) * sizeof(float), st>>>(
+        p->g, p->slot, p->desc.hidden, np, static_cast<const float*>(h), static_cast<const float*>(gout),
+        static_cast<const float*>(gadd), static_cast<float*>(gin), p->d_k5w, partials);
+    PERCNN_CUDA(cudaGetLastError());
+    k5::k5_reduce_partials<<<(np + 255) / 256, 256, 0, st>>>(partials, int(grid.x * grid.y), np, acc);
+    PERCNN_CUDA(cudaGetLastError());
+    p->launches += 2;
+    return PERCNN_OK;
+  }
   return p->elt == 4 ? step_bwd_t<float>(p, static_cast<const float*>(h), static_cast<const float*>(gout),
                                          static_cast<const float*>(gadd), static_cast<float*>(gin),
                                          static_cast<char*>(ws), st)
@@ -280,8 +314,6 @@ int step_bwd_any(percnn_plan* p, const void* h, const void* gout, const void* ga
                                           static_cast<const double*>(gadd), static_cast<double*>(gin),
                                           static_cast<char*>(ws), st);
 }
-
-size_t state_bytes(const percnn_plan* p) { return size_t(p->state_elems) * p->elt; }
 
 }  // namespace
 
@@ -372,6 +404,8 @@ int percnn_plan_create(const percnn_desc_t* d, percnn_plan_t** out) {
       if (cudaMalloc(&p->d_k5w, size_t(k5_total_floats(d->hidden)) * 4) != cudaSuccess) { rc = fail(PERCNN_ERR_CUDA, "cudaMalloc(k5w) failed"); break; }
       if (cudaFuncSetAttribute(k5::k_pi_k5_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                int(k5::smem_bytes(d->hidden))) != cudaSuccess) { rc = fail(PERCNN_ERR_CUDA, "cudaFuncSetAttribute(k5) failed"); break; }
+      if (cudaFuncSetAttribute(k5::k_pi_k5_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               int(k5::bwd_smem_floats(d->hidden, int(p->nparams)) * sizeof(float))) != cudaSuccess) { rc = fail(PERCNN_ERR_CUDA, "cudaFuncSetAttribute(k5 bwd) failed"); break; }
     }
     p->use_tma = d->cell == PERCNN_CELL_PI && d->ksize == 1 && d->ndim == 3 && d->dtype == PERCNN_F32 &&
                  !(d->flags & (PERCNN_FLAG_NO_TMA | PERCNN_FLAG_EVAL_BRANCH)) && g.W % tma3d::TX == 0 &&
@@ -440,7 +474,7 @@ int64_t percnn_plan_launch_count(const percnn_plan_t* p) { return p ? p->launche
 size_t percnn_workspace_bytes(const percnn_plan_t* p, int nsteps) {
   (void)nsteps;
   if (!p) return 0;
-  return kWsStates + 2 * ((state_bytes(p) + 255) / 256 * 256);
+  return ws_states_off(p) + 2 * ((state_bytes(p) + 255) / 256 * 256);
 }
 
 int percnn_params_load(percnn_plan_t* p, const void* params, void* stream) {
@@ -476,7 +510,7 @@ int percnn_step_fwd_range(percnn_plan_t* p, const void* h_in, void* h_out, int z
 
 int percnn_param_grads_begin(percnn_plan_t* p, void* ws, void* stream) {
   if (!p || !ws) return fail(PERCNN_ERR_INVALID, "null argument");
-  PERCNN_CUDA(cudaMemsetAsync(ws, 0, kWsPartials, static_cast<cudaStream_t>(stream)));
+  PERCNN_CUDA(cudaMemsetAsync(ws, 0, ws_header_bytes(p), static_cast<cudaStream_t>(stream)));
   return PERCNN_OK;
 }
 
@@ -491,8 +525,14 @@ int percnn_param_grads_finish(percnn_plan_t* p, const void* params, void* param_
   if (!p || !params || !param_grads || !ws) return fail(PERCNN_ERR_INVALID, "null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const double* acc = reinterpret_cast<const double*>(static_cast<char*>(ws) + kWsAcc);
-  if (p->desc.cell == PERCNN_CELL_PI && p->desc.ksize != 1)
-    return fail(PERCNN_ERR_UNSUPPORTED, "adjoint of the 5x5 Pi-block cell is not implemented yet");
+  if (is_k5(p)) {
+    const int np = int(p->nparams);
+    k5::k5_finish<<<(np + 255) / 256, 256, 0, st>>>(static_cast<const float*>(params), acc, p->pd, np,
+                                                     static_cast<float*>(param_grads));
+    PERCNN_CUDA(cudaGetLastError());
+    p->launches++;
+    return PERCNN_OK;
+  }
   if (p->elt == 4)
     k_finish_small<float><<<1, 256, 0, st>>>(static_cast<const float*>(params), acc, p->pd, int(p->nparams),
                                              static_cast<float*>(param_grads));
@@ -516,7 +556,7 @@ int percnn_rollout_fwd(percnn_plan_t* p, const void* h0, void* traj, const uint8
   char* tp = static_cast<char*>(tape);
   char* pp[2] = {nullptr, nullptr};
   if (ws) {
-    pp[0] = static_cast<char*>(ws) + kWsStates;
+    pp[0] = static_cast<char*>(ws) + ws_states_off(p);
     pp[1] = pp[0] + (sb + 255) / 256 * 256;
   }
   if (tp && tp != h0) PERCNN_CUDA(cudaMemcpyAsync(tp, h0, sb, cudaMemcpyDeviceToDevice, st));
@@ -555,7 +595,7 @@ int percnn_rollout_bwd(percnn_plan_t* p, const void* params, const void* tape, c
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t sb = state_bytes(p);
   char* w = static_cast<char*>(ws);
-  char* pp[2] = {w + kWsStates, w + kWsStates + (sb + 255) / 256 * 256};
+  char* pp[2] = {w + ws_states_off(p), w + ws_states_off(p) + (sb + 255) / 256 * 256};
   int rc = percnn_param_grads_begin(p, ws, stream);
   if (rc) return rc;
   // compact slot index of each masked state
@@ -598,7 +638,7 @@ int percnn_rollout_fwd_host(percnn_plan_t* p, const void* params_host, const voi
   int nemit = 0;
   if (traj_host)
     for (int s = 0; s < nsteps; ++s) nemit += emit[s] ? 1 : 0;
-  const size_t need = kWsStates + sb * size_t(4 + nemit);
+  const size_t need = ws_states_off(p) + sb * size_t(4 + nemit);
   if (!p->h_stream) PERCNN_CUDA(cudaStreamCreateWithFlags(&p->h_stream, cudaStreamNonBlocking));
   if (!p->h_params_dev) PERCNN_CUDA(cudaMalloc(&p->h_params_dev, size_t(p->nparams) * p->elt));
   if (p->h_states_bytes < need) {
@@ -611,7 +651,7 @@ int percnn_rollout_fwd_host(percnn_plan_t* p, const void* params_host, const voi
   cudaStream_t st = p->h_stream;
   char* base = static_cast<char*>(p->h_states);
   char* ws = base;                          // header + 2 ping-pong states
-  char* d_h0 = base + kWsStates + 2 * sb;
+  char* d_h0 = base + ws_states_off(p) + 2 * sb;
   char* d_final = d_h0 + sb;
   char* d_traj = d_final + sb;
   const size_t raw_sb = state_bytes(p);

@@ -68,7 +68,7 @@ def test_python_step_loop_equals_fused_rollout(tag):
             assert torch.equal(h[0], states[s + 1])
 
 
-@pytest.mark.parametrize("tag", K1_TAGS)
+@pytest.mark.parametrize("tag", K1_TAGS + K5_TAGS)
 def test_gradients_match_reference_autograd(tag):
     z, params, grads = load_golden(tag)
     cell = _cell(tag, params)
@@ -139,13 +139,29 @@ def test_branch_evaluation_agrees_with_folded_cubic(tag):
     assert rel_l2(a, b) <= roll_tol
 
 
-def test_k5_backward_is_a_loud_error_not_a_fallback():
-    z, params, _ = load_golden("bur1")
-    cell = _cell("bur1", params)
-    h0 = torch.from_numpy(z["h0"]).to(DEV).requires_grad_(True)
-    states = cell.rollout(h0, 2)
-    with pytest.raises(_lib.PercnnError, match="5x5"):
-        states.sum().backward()
+@pytest.mark.parametrize("tag,shape", [("bur1", (40, 72)), ("lo1", (33, 50)), ("gs2d", (37, 41)), ("gs3d", (9, 12, 20))])
+def test_gradients_match_fp64_oracle_autograd_on_ragged_sizes(tag, shape):
+    """Sizes that are not multiples of any tile: CUDA adjoint (fp32) vs torch autograd through the oracle in fp64."""
+    alias = tag
+    params32 = load_weights(alias)
+    cell = _cell(tag, params32)
+    g = torch.Generator().manual_seed(11)
+    h0 = (torch.rand((1, 2, *shape), generator=g, dtype=torch.float64) - 0.5)
+    nstep = 3
+    w = torch.randn((nstep + 1, 2, *shape), generator=g, dtype=torch.float64)
+    hd = h0.float().to(DEV).requires_grad_(True)
+    (cell.rollout(hd, nstep) * w.float().to(DEV)).sum().backward()
+    p64 = {k: v.double().requires_grad_(v.dtype.is_floating_point and "laplace" not in k.lower()) for k, v in params32.items()}
+    h64 = h0.float().double().requires_grad_(True)
+    outs, _ = po.rollout_torch(h64, p64, tag, nstep, range(nstep))
+    (torch.cat(outs, 0) * w.float().double()).sum().backward()
+    assert rel_l2(hd.grad.cpu().numpy(), h64.grad.numpy()) <= 1e-5
+    named = dict(cell.named_parameters())
+    for k, v in p64.items():
+        if v.grad is None or not named[k].requires_grad:
+            continue
+        err = rel_l2(named[k].grad.cpu().numpy(), v.grad.numpy())
+        assert err <= (2e-4 if v.dim() == 0 else 2e-5), (k, err)
 
 
 @pytest.mark.parametrize("shape", [(8, 16, 128), (5, 32, 256), (12, 48, 128), (9, 37, 256), (6, 20, 128), (7, 5, 128)])
