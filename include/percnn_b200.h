@@ -116,6 +116,22 @@ int percnn_step_fwd(percnn_plan_t* plan, const void* h_in, void* h_out, void* st
 /* Same step restricted to interior planes [z_lo, z_hi) of the slowest axis (3-D TMA plans only).  Lets the
  * slab-mode driver launch the planes that do not touch ghost cells before the halo exchange lands. */
 int percnn_step_fwd_range(percnn_plan_t* plan, const void* h_in, void* h_out, int z_lo, int z_hi, void* stream);
+/* Slab-mode step with the halo exchange fused into the kernel (multi-GPU, peer-mapped buffers over NVLink):
+ * the kernel computes the 2+2 boundary planes first and stores them both locally and into the neighbours'
+ * ghost planes, raises the neighbours' flags (release, system scope) when all of them have landed, then
+ * computes the interior.  Before touching its own ghost planes it waits (acquire) for my_flags >= epoch.
+ * No NCCL call and no host round trip per step.  All pointers are device pointers; peer_* are peer mappings. */
+typedef struct percnn_slab_link {
+  void* peer_lo_out;        /* lower ring neighbour's h_out buffer (same [2][D+4][H][W] layout) */
+  void* peer_hi_out;        /* upper ring neighbour's h_out buffer */
+  const uint32_t* my_flags; /* [0]: epoch up to which my LOWER ghosts are valid, [1]: same for the UPPER ghosts */
+  uint32_t* peer_lo_flags;  /* the lower neighbour's flags array (its [1] is raised by this step) */
+  uint32_t* peer_hi_flags;  /* the upper neighbour's flags array (its [0] is raised by this step) */
+  uint32_t* scratch;        /* 2 local words, zero-initialised: CTA arrival counter, error word (spin deadline) */
+  uint32_t epoch;           /* waits for flags >= epoch, publishes epoch + 1 */
+} percnn_slab_link_t;
+int percnn_step_fwd_fused_halo(percnn_plan_t* plan, const void* h_in, void* h_out, const percnn_slab_link_t* link,
+                               void* stream);
 /* Adjoint of one step (replaces autograd through GS2D:105-121): g_in = g_add + (dh_out/dh_in)^T g_out
  * (g_add may be NULL), and the step's parameter-gradient sums are ACCUMULATED into the accumulator at the
  * head of `ws` (zeroed by percnn_param_grads_begin, read by percnn_param_grads_finish). */

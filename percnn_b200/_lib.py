@@ -23,7 +23,8 @@ FLAG_EVAL_BRANCH, FLAG_NO_TMA, FLAG_LO_C6 = 1, 2, 4
 EXPORTS = (
     "percnn_abi_version", "percnn_last_error", "percnn_device_ok", "percnn_plan_create", "percnn_plan_destroy",
     "percnn_param_count", "percnn_state_elems", "percnn_workspace_bytes", "percnn_plan_uses_tma",
-    "percnn_plan_launch_count", "percnn_params_load", "percnn_step_fwd", "percnn_step_fwd_range", "percnn_step_bwd",
+    "percnn_plan_launch_count", "percnn_params_load", "percnn_step_fwd", "percnn_step_fwd_range",
+    "percnn_step_fwd_fused_halo", "percnn_step_bwd",
     "percnn_param_grads_begin", "percnn_param_grads_finish", "percnn_rollout_fwd", "percnn_rollout_bwd",
     "percnn_rollout_fwd_host",
 )
@@ -35,6 +36,14 @@ class Desc(ctypes.Structure):
         ("abi_version", c_int32), ("ndim", c_int32), ("extent", c_int64 * 3), ("dtype", c_int32), ("cell", c_int32),
         ("ksize", c_int32), ("hidden", c_int32), ("coef_mode", c_int32), ("flags", c_int32), ("mu_up", c_double),
         ("dt", c_double), ("dx", c_double), ("device", c_int32), ("slab_ghost", c_int32),
+    ]
+
+
+class SlabLink(ctypes.Structure):
+    """percnn_slab_link_t"""
+    _fields_ = [
+        ("peer_lo_out", c_void_p), ("peer_hi_out", c_void_p), ("my_flags", c_void_p), ("peer_lo_flags", c_void_p),
+        ("peer_hi_flags", c_void_p), ("scratch", c_void_p), ("epoch", ctypes.c_uint32),
     ]
 
 
@@ -72,6 +81,7 @@ def lib() -> ctypes.CDLL:
     L.percnn_params_load.argtypes = [vp, vp, vp]
     L.percnn_step_fwd.argtypes = [vp, vp, vp, vp]
     L.percnn_step_fwd_range.argtypes = [vp, vp, vp, c_int, c_int, vp]
+    L.percnn_step_fwd_fused_halo.argtypes = [vp, vp, vp, POINTER(SlabLink), vp]
     L.percnn_step_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.percnn_param_grads_begin.argtypes = [vp, vp, vp]
     L.percnn_param_grads_finish.argtypes = [vp, vp, vp, vp, vp]

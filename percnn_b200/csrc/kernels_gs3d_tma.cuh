@@ -49,11 +49,22 @@ struct Params {
   int dst_zoff;       // interior plane z of dst is stored at plane z + dst_zoff
   int wrap_z;         // 1: periodic along z inside this buffer; 0: ghost planes present
   int ty;             // rows per tile (<= TY); tiles start at min(j * ty, H - ty), so only the last may overlap
-  int tz;             // planes per z-chunk
-  int nxt, nyt, nzc;  // tiles along x, y; chunks along z
-  int z_lo, z_hi;     // only interior planes [z_lo, z_hi) are computed (halo/interior split for overlap)
+  int nxt, nyt;       // tiles along x, y
+  // Work is a list of up to 3 z-segments, processed in order by every CTA.  A plain step has one segment
+  // [0, D); the fused slab step has [0,2) (needs the lower ghosts, mirrored to the lower neighbour),
+  // [D-2, D) (upper ghosts / upper neighbour) and the interior [2, D-2).
+  int nseg;
+  int seg_lo[3], seg_hi[3], seg_tz[3], seg_nzc[3];
   int slot;
-  int mode;           // experiment switches (0 in production): 1 = copy skeleton (no math), 2 = no stores, 4 = streaming stores
+  // ---- fused halo exchange over peer memory (slab mode; all null/0 otherwise) ----
+  int fused;
+  float* peer_lo_dst;        // lower neighbour's destination buffer (same layout as dst), mapped over NVLink
+  float* peer_hi_dst;
+  const uint32_t* my_flags;  // [0] epoch up to which my lower ghosts are valid, [1] same for the upper ghosts
+  uint32_t* post_lo_flag;    // lower neighbour's flags[1] (I write its upper ghosts)
+  uint32_t* post_hi_flag;    // upper neighbour's flags[0]
+  uint32_t* scratch;         // [0] CTA arrival counter, [1] error word (spin deadline exceeded)
+  uint32_t epoch_wait, epoch_post;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -113,51 +124,85 @@ __device__ __forceinline__ float2 cubic2(const float* __restrict__ c, float2 u, 
 __device__ __forceinline__ void lap_quad(const float* __restrict__ P, const float4 (&win)[5], const float4 (&y)[4], float Lz,
                                          float Lw, float Rx, float Ry, float2& acc_lo, float2& acc_hi) {
   const float4& c = win[2];
-  acc_lo = mul2(lo(c), P[P_LAP_C0]);
-  acc_hi = mul2(hi(c), P[P_LAP_C0]);
-  // z taps (axis 0)
-  acc_lo = fma2(lo(win[0]), P[P_LAP_AX + 0], acc_lo);
-  acc_hi = fma2(hi(win[0]), P[P_LAP_AX + 0], acc_hi);
-  acc_lo = fma2(lo(win[1]), P[P_LAP_AX + 1], acc_lo);
-  acc_hi = fma2(hi(win[1]), P[P_LAP_AX + 1], acc_hi);
-  acc_lo = fma2(lo(win[3]), P[P_LAP_AX + 2], acc_lo);
-  acc_hi = fma2(hi(win[3]), P[P_LAP_AX + 2], acc_hi);
-  acc_lo = fma2(lo(win[4]), P[P_LAP_AX + 3], acc_lo);
-  acc_hi = fma2(hi(win[4]), P[P_LAP_AX + 3], acc_hi);
+  // two independent partial sums per register pair (z-part and in-plane part) halve the dependent-FMA chain
+  float2 za_lo = mul2(lo(c), P[P_LAP_C0]);
+  float2 za_hi = mul2(hi(c), P[P_LAP_C0]);
+  za_lo = fma2(lo(win[0]), P[P_LAP_AX + 0], za_lo);
+  za_hi = fma2(hi(win[0]), P[P_LAP_AX + 0], za_hi);
+  za_lo = fma2(lo(win[1]), P[P_LAP_AX + 1], za_lo);
+  za_hi = fma2(hi(win[1]), P[P_LAP_AX + 1], za_hi);
+  za_lo = fma2(lo(win[3]), P[P_LAP_AX + 2], za_lo);
+  za_hi = fma2(hi(win[3]), P[P_LAP_AX + 2], za_hi);
+  za_lo = fma2(lo(win[4]), P[P_LAP_AX + 3], za_lo);
+  za_hi = fma2(hi(win[4]), P[P_LAP_AX + 3], za_hi);
   // y taps (axis 1)
+  float2 pa_lo = mul2(lo(y[0]), P[P_LAP_AX + 4]);
+  float2 pa_hi = mul2(hi(y[0]), P[P_LAP_AX + 4]);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    acc_lo = fma2(lo(y[k]), P[P_LAP_AX + 4 + k], acc_lo);
-    acc_hi = fma2(hi(y[k]), P[P_LAP_AX + 4 + k], acc_hi);
+  for (int k = 1; k < 4; ++k) {
+    pa_lo = fma2(lo(y[k]), P[P_LAP_AX + 4 + k], pa_lo);
+    pa_hi = fma2(hi(y[k]), P[P_LAP_AX + 4 + k], pa_hi);
   }
   // x taps (axis 2): +-2 are register-pair aligned, +-1 straddle pairs -> scalar FFMA
-  acc_lo = fma2(make_float2(Lz, Lw), P[P_LAP_AX + 8], acc_lo);
-  acc_hi = fma2(lo(c), P[P_LAP_AX + 8], acc_hi);
-  acc_lo = fma2(hi(c), P[P_LAP_AX + 11], acc_lo);
-  acc_hi = fma2(make_float2(Rx, Ry), P[P_LAP_AX + 11], acc_hi);
+  pa_lo = fma2(make_float2(Lz, Lw), P[P_LAP_AX + 8], pa_lo);
+  pa_hi = fma2(lo(c), P[P_LAP_AX + 8], pa_hi);
+  pa_lo = fma2(hi(c), P[P_LAP_AX + 11], pa_lo);
+  pa_hi = fma2(make_float2(Rx, Ry), P[P_LAP_AX + 11], pa_hi);
   const float m1 = P[P_LAP_AX + 9], p1 = P[P_LAP_AX + 10];
-  acc_lo.x = fmaf(p1, c.y, fmaf(m1, Lw, acc_lo.x));
-  acc_lo.y = fmaf(p1, c.z, fmaf(m1, c.x, acc_lo.y));
-  acc_hi.x = fmaf(p1, c.w, fmaf(m1, c.y, acc_hi.x));
-  acc_hi.y = fmaf(p1, Rx, fmaf(m1, c.z, acc_hi.y));
+  pa_lo.x = fmaf(p1, c.y, fmaf(m1, Lw, pa_lo.x));
+  pa_lo.y = fmaf(p1, c.z, fmaf(m1, c.x, pa_lo.y));
+  pa_hi.x = fmaf(p1, c.w, fmaf(m1, c.y, pa_hi.x));
+  pa_hi.y = fmaf(p1, Rx, fmaf(m1, c.z, pa_hi.y));
+  acc_lo = __fadd2_rn(za_lo, pa_lo);
+  acc_hi = __fadd2_rn(za_hi, pa_hi);
 }
 
 __device__ __forceinline__ float4 lds128(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
 struct ItemCoord {
-  int x0, y0, z0, nz;
+  int x0, y0, z0, nz, seg;
 };
+__device__ __forceinline__ int total_items(const Params& p) {
+  int n = 0;
+  for (int s = 0; s < p.nseg; ++s) n += p.nxt * p.nyt * p.seg_nzc[s];
+  return n;
+}
 __device__ __forceinline__ ItemCoord decode_item(const Params& p, int item) {
   ItemCoord c;
+  int seg = 0;
+  const int tiles = p.nxt * p.nyt;
+  while (seg + 1 < p.nseg && item >= tiles * p.seg_nzc[seg]) {
+    item -= tiles * p.seg_nzc[seg];
+    ++seg;
+  }
   const int xt = item % p.nxt;
   const int r = item / p.nxt;
   const int yt = r % p.nyt;
   const int zc = r / p.nyt;
+  c.seg = seg;
   c.x0 = xt * TX;
   c.y0 = min(yt * p.ty, p.H - p.ty);
-  c.z0 = p.z_lo + zc * p.tz;
-  c.nz = min(p.tz, p.z_hi - c.z0);
+  c.z0 = p.seg_lo[seg] + zc * p.seg_tz[seg];
+  c.nz = min(p.seg_tz[seg], p.seg_hi[seg] - c.z0);
   return c;
+}
+
+// ---- cross-GPU flags (system scope) ----
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Spin until *flag >= epoch (wrap-safe).  Bounded: a lost peer sets the error word instead of hanging the GPU.
+__device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t epoch, uint32_t* err) {
+  for (uint32_t spins = 0; spins < (1u << 26); ++spins) {
+    if (int32_t(ld_acquire_sys(flag) - epoch) >= 0) return;
+    __nanosleep(64);
+  }
+  atomicExch(err, 1u);
 }
 __device__ __forceinline__ int src_plane(const Params& p, int z0, int j) {
   // z0 + j + src_zoff lies in [-2, D + 1]; the host only picks this kernel for D >= 4, so one
@@ -211,9 +256,9 @@ __device__ __forceinline__ void warm_plane(Consumer& c, bool release_now, float4
 // Steady-state plane: local plane k arrives, output plane k-2 is produced.
 //   seam_ptr : this lane's seam cells in the source plane that will be the in-plane source NEXT iteration
 //   out      : this lane's quad in the output plane
-template <int R, bool STREAM_STORES>
+template <int R, bool FUSED>
 __device__ __forceinline__ void steady_plane(Consumer& c, bool drain, bool prefetch_seam, const float* seam_ptr,
-                                             int64_t src_field, float* out, int64_t dst_field, int mode,
+                                             int64_t src_field, float* out, float* mirror, int64_t dst_field,
                                              float4 (&wu)[5], float4 (&wv)[5], float2 (&seam_next)[2]) {
   const float* P = c.P;
   mbar_wait(&c.full[c.s], c.parity);
@@ -236,16 +281,6 @@ __device__ __forceinline__ void steady_plane(Consumer& c, bool drain, bool prefe
   const float4 wl_u[5] = {wu[(R + 0) % 5], wu[(R + 1) % 5], wu[(R + 2) % 5], wu[(R + 3) % 5], wu[(R + 4) % 5]};
   const float4 wl_v[5] = {wv[(R + 0) % 5], wv[(R + 1) % 5], wv[(R + 2) % 5], wv[(R + 3) % 5], wv[(R + 4) % 5]};
   const float4 cu = wl_u[2], cv = wl_v[2];
-  if (mode & 1) {   // experiment: memory skeleton only (TMA in, STG out, no arithmetic)
-    __syncwarp();
-    if (c.lane == 0) mbar_arrive(&c.empty[s2]);
-    if (!(mode & 2)) {
-      *reinterpret_cast<float4*>(out) = cu;
-      *reinterpret_cast<float4*>(out + dst_field) = cv;
-    }
-    advance_stage(c);
-    return;
-  }
   float2 Lu_lo, Lu_hi, Lv_lo, Lv_hi;
   {
     const float4 y[4] = {lds128(sp), lds128(sp + TX), lds128(sp + 3 * TX), lds128(sp + 4 * TX)};
@@ -274,21 +309,18 @@ __device__ __forceinline__ void steady_plane(Consumer& c, bool drain, bool prefe
   const float2 ov_hi = fma2(fma2(Lv_hi, av, cubic2(P + P_POLY + 10, hi(cu), hi(cv))), dt, hi(cv));
   const float4 ou = make_float4(ou_lo.x, ou_lo.y, ou_hi.x, ou_hi.y);
   const float4 ov = make_float4(ov_lo.x, ov_lo.y, ov_hi.x, ov_hi.y);
-  if (mode & 2) {
-    if (ou.x == 123.456f && ov.y == 654.321f) *reinterpret_cast<float4*>(out) = ou;   // keeps the math alive
-  } else if (STREAM_STORES) {
-    __stcs(reinterpret_cast<float4*>(out), ou);
-    __stcs(reinterpret_cast<float4*>(out + dst_field), ov);
-  } else {
-    *reinterpret_cast<float4*>(out) = ou;
-    *reinterpret_cast<float4*>(out + dst_field) = ov;
+  *reinterpret_cast<float4*>(out) = ou;
+  *reinterpret_cast<float4*>(out + dst_field) = ov;
+  if (FUSED && mirror != nullptr) {   // boundary plane: also the neighbour GPU's ghost plane (peer store over NVLink)
+    *reinterpret_cast<float4*>(mirror) = ou;
+    *reinterpret_cast<float4*>(mirror + dst_field) = ov;
   }
   advance_stage(c);
 }
 
 // SLOT is a template parameter so that every coefficient is a compile-time constant-bank address
 // (c[3][imm] / hoisted LDCU) instead of an indexed LDC per use.
-template <int SLOT, bool STREAM_STORES>
+template <int SLOT, bool FUSED>
 __global__ void __launch_bounds__(THREADS, 1)
 k_gs3d_fwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_halo,
                const __grid_constant__ Params p) {
@@ -305,7 +337,7 @@ k_gs3d_fwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const int nitems = p.nxt * p.nyt * p.nzc;
+  const int nitems = total_items(p);
 
   if (warp >= TY) {
     // ===== producer warp-group: one elected lane issues every TMA =====
@@ -316,6 +348,12 @@ k_gs3d_fwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
       uint32_t it = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const ItemCoord ic = decode_item(p, item);
+        if (FUSED && ic.seg < 2) {
+          // the ghost planes this item reads are written by a neighbour GPU: wait for its flag, then order
+          // the TMA (async proxy) reads after the acquire
+          wait_flag(p.my_flags + ic.seg, p.epoch_wait, p.scratch + 1);
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+        }
         int yh[4] = {ic.y0 - 2, ic.y0 - 1, ic.y0 + p.ty, ic.y0 + p.ty + 1};   // periodic halo rows
 #pragma unroll
         for (int h = 0; h < 4; ++h) yh[h] = yh[h] < 0 ? yh[h] + p.H : (yh[h] >= p.H ? yh[h] - p.H : yh[h]);
@@ -361,8 +399,34 @@ k_gs3d_fwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
   const int64_t plane = int64_t(p.H) * p.W;
   float4 wu[5], wv[5];
   float2 seam_next[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+  bool posted = !FUSED;
+  // Tell the neighbours that every boundary plane of this step has landed in their ghost planes: the consumer
+  // warps of this CTA meet, one thread publishes (release, system scope); the last CTA raises the flags.
+  auto post_boundary_done = [&]() {
+    asm volatile("bar.sync 1, %0;" ::"r"(p.ty * 32) : "memory");
+    if (warp == 0 && lane == 0) {
+      __threadfence_system();
+      const unsigned old = atomicAdd(p.scratch, 1u);
+      if (old == gridDim.x - 1) {
+        atomicExch(p.scratch, 0u);
+        __threadfence_system();
+        st_release_sys(p.post_lo_flag, p.epoch_post);
+        st_release_sys(p.post_hi_flag, p.epoch_post);
+      }
+    }
+  };
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
     const ItemCoord ic = decode_item(p, item);
+    if (FUSED && !posted && ic.seg == 2) {
+      post_boundary_done();
+      posted = true;
+    }
+    float* mirror = nullptr;
+    if (FUSED && ic.seg < 2) {
+      float* base = ic.seg == 0 ? p.peer_lo_dst : p.peer_hi_dst;
+      const int mz = ic.seg == 0 ? p.D + 2 + ic.z0 : ic.z0 - (p.D - 2);
+      mirror = base + (int64_t(mz) * p.H + ic.y0) * p.W + ic.x0 + c.toff;
+    }
     // uniform per-item bases; the per-lane part (toff / seam_off) never changes
     const float* src_xy = p.src + int64_t(ic.y0) * p.W + ic.x0;
     float* out = p.dst + (int64_t(ic.z0 + p.dst_zoff) * p.H + ic.y0) * p.W + ic.x0 + c.toff;
@@ -370,21 +434,28 @@ k_gs3d_fwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
     xs = xs < 0 ? xs + p.W : (xs >= p.W ? xs - p.W : xs);
     const int seam_off = warp * p.W + xs - ic.x0;
     int pz = src_plane(p, ic.z0, 2);   // source plane whose seam cells are fetched next (local plane 2 first)
+    const float* seam_ptr = src_xy + int64_t(pz) * plane + seam_off;   // advanced by one plane per iteration
+    const int64_t wrap_back = int64_t(p.D) * plane;
 
     warm_plane<0>(c, true, wu, wv);
     warm_plane<1>(c, true, wu, wv);
     warm_plane<2>(c, false, wu, wv);
     warm_plane<3>(c, false, wu, wv);
-    ldg_f2_if(c.is_seam, src_xy + int64_t(pz) * plane + seam_off, seam_next[0]);
-    ldg_f2_if(c.is_seam, src_xy + int64_t(pz) * plane + seam_off + p.src_field, seam_next[1]);
+    ldg_f2_if(c.is_seam, seam_ptr, seam_next[0]);
+    ldg_f2_if(c.is_seam, seam_ptr + p.src_field, seam_next[1]);
 
     const int nk = ic.nz + 4;   // local planes 0 .. nz+3; outputs for k = 4 .. nz+3
 #define PERCNN_STEADY(RR)                                                                                     \
   {                                                                                                           \
-    pz = (p.wrap_z && pz + 1 >= p.D) ? pz + 1 - p.D : pz + 1;                                                 \
-    steady_plane<RR, STREAM_STORES>(c, k >= ic.nz + 2, k <= ic.nz + 2, src_xy + int64_t(pz) * plane + seam_off, p.src_field, \
-                     out, p.dst_field, p.mode, wu, wv, seam_next);                                                    \
+    seam_ptr += plane;                                                                                        \
+    if (p.wrap_z && ++pz >= p.D) {                                                                            \
+      pz -= p.D;                                                                                              \
+      seam_ptr -= wrap_back;                                                                                  \
+    }                                                                                                         \
+    steady_plane<RR, FUSED>(c, k >= ic.nz + 2, k <= ic.nz + 2, seam_ptr, p.src_field, out, mirror, p.dst_field, \
+                            wu, wv, seam_next);                                                               \
     out += plane;                                                                                             \
+    if (FUSED && mirror != nullptr) mirror += plane;                                                          \
     ++k;                                                                                                      \
   }
     int k = 4;
@@ -398,6 +469,7 @@ k_gs3d_fwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
     if (k < nk) PERCNN_STEADY(3)
 #undef PERCNN_STEADY
   }
+  if (FUSED && !posted) post_boundary_done();
 }
 
 }  // namespace tma3d

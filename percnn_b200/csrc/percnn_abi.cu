@@ -61,7 +61,7 @@ struct percnn_plan {
   int64_t launches = 0;
   bool use_tma = false;
   int ty = 16, tz = 0;
-  int tma_mode = 0, tz_override = 0, grid_override = 0;   // experiment knobs (PERCNN_TMA_MODE / _TZ / _GRID env)
+  int tz_override = 0, grid_override = 0;   // experiment knobs (PERCNN_TMA_TY / _TZ / _GRID environment variables)
   PrepBlock* d_prep = nullptr;
   float* d_k5w = nullptr;
   EncodeTiledFn encode = nullptr;
@@ -173,12 +173,24 @@ int get_maps(percnn_plan* p, const void* src, const CUtensorMap** main_map, cons
   return PERCNN_OK;
 }
 
-int launch_tma_fwd(percnn_plan* p, const float* src, float* dst, int z_lo, int z_hi, cudaStream_t st) {
+struct SlabLink {   // mirrors percnn_slab_link_t
+  float* peer_lo_dst = nullptr;
+  float* peer_hi_dst = nullptr;
+  const uint32_t* my_flags = nullptr;
+  uint32_t* post_lo_flag = nullptr;
+  uint32_t* post_hi_flag = nullptr;
+  uint32_t* scratch = nullptr;
+  uint32_t epoch_wait = 0, epoch_post = 0;
+};
+
+int launch_tma_fwd(percnn_plan* p, const float* src, float* dst, int z_lo, int z_hi, cudaStream_t st,
+                   const SlabLink* link = nullptr) {
   const CUtensorMap *mm, *hm;
   int rc = get_maps(p, src, &mm, &hm);
   if (rc) return rc;
   const Geom& g = p->g;
   tma3d::Params prm;
+  memset(&prm, 0, sizeof(prm));
   prm.src = src;
   prm.dst = dst;
   prm.D = g.D;
@@ -191,28 +203,47 @@ int launch_tma_fwd(percnn_plan* p, const float* src, float* dst, int z_lo, int z
   prm.dst_zoff = g.ghost;
   prm.wrap_z = g.ghost ? 0 : 1;
   prm.nxt = g.W / tma3d::TX;
-  const int depth = z_hi - z_lo;
-  TmaTiling til = (z_lo == 0 && z_hi == g.D) ? TmaTiling{p->ty, p->tz, (g.H + p->ty - 1) / p->ty, (g.D + p->tz - 1) / p->tz}
-                                             : choose_tiling(prm.nxt, g.H, depth, p->sm_count, p->ty);
-  if (p->tz_override > 0) {
-    til.tz = p->tz_override < depth ? p->tz_override : depth;
-    til.nzc = (depth + til.tz - 1) / til.tz;
-  }
   prm.ty = p->ty;
-  prm.nyt = til.nyt;
-  prm.tz = til.tz;
-  prm.nzc = til.nzc;
-  prm.z_lo = z_lo;
-  prm.z_hi = z_hi;
+  prm.nyt = (g.H + p->ty - 1) / p->ty;
+  auto add_segment = [&](int lo, int hi) {
+    const int depth = hi - lo;
+    TmaTiling til = (lo == 0 && hi == g.D) ? TmaTiling{p->ty, p->tz, prm.nyt, (g.D + p->tz - 1) / p->tz}
+                                           : choose_tiling(prm.nxt, g.H, depth, p->sm_count, p->ty);
+    if (p->tz_override > 0) {
+      til.tz = p->tz_override < depth ? p->tz_override : depth;
+      til.nzc = (depth + til.tz - 1) / til.tz;
+    }
+    const int s = prm.nseg++;
+    prm.seg_lo[s] = lo;
+    prm.seg_hi[s] = hi;
+    prm.seg_tz[s] = til.tz;
+    prm.seg_nzc[s] = til.nzc;
+  };
+  if (link) {
+    add_segment(0, 2);
+    add_segment(g.D - 2, g.D);
+    add_segment(2, g.D - 2);
+    prm.fused = 1;
+    prm.peer_lo_dst = link->peer_lo_dst;
+    prm.peer_hi_dst = link->peer_hi_dst;
+    prm.my_flags = link->my_flags;
+    prm.post_lo_flag = link->post_lo_flag;
+    prm.post_hi_flag = link->post_hi_flag;
+    prm.scratch = link->scratch;
+    prm.epoch_wait = link->epoch_wait;
+    prm.epoch_post = link->epoch_post;
+  } else {
+    add_segment(z_lo, z_hi);
+  }
   prm.slot = p->slot;
-  prm.mode = p->tma_mode;
-  const int nitems = prm.nxt * prm.nyt * prm.nzc;
+  int nitems = 0;
+  for (int s = 0; s < prm.nseg; ++s) nitems += prm.nxt * prm.nyt * prm.seg_nzc[s];
   int grid = nitems < p->sm_count ? nitems : p->sm_count;
   if (p->grid_override > 0 && p->grid_override < grid) grid = p->grid_override;
   switch (p->slot) {
 #define PERCNN_TMA_CASE(S) \
   case S:                                                                                                   \
-    if (prm.mode & 4) tma3d::k_gs3d_fwd_tma<S, true><<<grid, tma3d::THREADS, tma3d::SMEM_BYTES, st>>>(*mm, *hm, prm); \
+    if (prm.fused) tma3d::k_gs3d_fwd_tma<S, true><<<grid, tma3d::THREADS, tma3d::SMEM_BYTES, st>>>(*mm, *hm, prm); \
     else tma3d::k_gs3d_fwd_tma<S, false><<<grid, tma3d::THREADS, tma3d::SMEM_BYTES, st>>>(*mm, *hm, prm);   \
     break;
     PERCNN_TMA_CASE(0) PERCNN_TMA_CASE(1) PERCNN_TMA_CASE(2) PERCNN_TMA_CASE(3) PERCNN_TMA_CASE(4) PERCNN_TMA_CASE(5)
@@ -436,7 +467,6 @@ int percnn_plan_create(const percnn_desc_t* d, percnn_plan_t** out) {
       const TmaTiling til = choose_tiling(g.W / tma3d::TX, g.H, g.D, p->sm_count, fixed_ty);
       p->ty = til.ty;
       p->tz = til.tz;
-      if (const char* e = getenv("PERCNN_TMA_MODE")) p->tma_mode = atoi(e);
       if (const char* e = getenv("PERCNN_TMA_TZ")) p->tz_override = atoi(e);
       if (const char* e = getenv("PERCNN_TMA_GRID")) p->grid_override = atoi(e);
     }
@@ -506,6 +536,27 @@ int percnn_step_fwd_range(percnn_plan_t* p, const void* h_in, void* h_out, int z
   if (z_lo < 0 || z_hi > p->g.D || z_lo >= z_hi) return fail(PERCNN_ERR_INVALID, "bad plane range");
   return launch_tma_fwd(p, static_cast<const float*>(h_in), static_cast<float*>(h_out), z_lo, z_hi,
                         static_cast<cudaStream_t>(stream));
+}
+
+// One fused slab step: boundary planes first (each also stored into the neighbour's ghost planes through the
+// peer mapping), flags raised from inside the kernel, interior last.  See percnn_slab_link_t.
+int percnn_step_fwd_fused_halo(percnn_plan_t* p, const void* h_in, void* h_out, const percnn_slab_link_t* link, void* stream) {
+  if (!p || !h_in || !h_out || !link) return fail(PERCNN_ERR_INVALID, "null argument");
+  if (!p->use_tma || !p->desc.slab_ghost) return fail(PERCNN_ERR_UNSUPPORTED, "fused halo steps need a slab-mode TMA plan");
+  if (p->g.D < 5) return fail(PERCNN_ERR_UNSUPPORTED, "fused halo steps need at least 5 planes per rank");
+  if (!link->peer_lo_out || !link->peer_hi_out || !link->my_flags || !link->peer_lo_flags || !link->peer_hi_flags || !link->scratch)
+    return fail(PERCNN_ERR_INVALID, "incomplete slab link");
+  SlabLink l;
+  l.peer_lo_dst = static_cast<float*>(link->peer_lo_out);
+  l.peer_hi_dst = static_cast<float*>(link->peer_hi_out);
+  l.my_flags = link->my_flags;
+  l.post_lo_flag = link->peer_lo_flags + 1;   // I provide the lower neighbour's UPPER ghosts
+  l.post_hi_flag = link->peer_hi_flags + 0;   // and the upper neighbour's LOWER ghosts
+  l.scratch = link->scratch;
+  l.epoch_wait = link->epoch;
+  l.epoch_post = link->epoch + 1;
+  return launch_tma_fwd(p, static_cast<const float*>(h_in), static_cast<float*>(h_out), 0, p->g.D,
+                        static_cast<cudaStream_t>(stream), &l);
 }
 
 int percnn_param_grads_begin(percnn_plan_t* p, void* ws, void* stream) {

@@ -131,6 +131,10 @@ class Plan:
         check(self._L.percnn_step_fwd_range(self._h, h_in.data_ptr(), h_out.data_ptr(), int(z_lo), int(z_hi),
                                             _stream_ptr(self.device)))
 
+    def step_fwd_fused_halo(self, h_in: torch.Tensor, h_out: torch.Tensor, link) -> None:
+        check(self._L.percnn_step_fwd_fused_halo(self._h, h_in.data_ptr(), h_out.data_ptr(), ctypes.byref(link),
+                                                 _stream_ptr(self.device)))
+
     def step_bwd(self, h_in, g_out, g_in, g_add=None) -> None:
         for t, n in ((h_in, "h_in"), (g_out, "g_out"), (g_in, "g_in")):
             self._check_state(t, n)

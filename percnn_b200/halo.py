@@ -14,7 +14,11 @@ behind the interior kernel.  Transport:
   * "nccl": torch.distributed batch_isend_irecv (ncclSend/ncclRecv grouped) on the comm stream;
   * "symm": peer-mapped buffers (torch.distributed._symmetric_memory): the boundary planes are copied
     straight into the neighbour's ghost planes over NVLink and a stream-ordered signal replaces the
-    rendezvous -- no NCCL kernel, no host round trip; the whole multi-step loop is CUDA-graph capturable.
+    rendezvous -- no NCCL kernel, no host round trip;
+  * "fused" (default when peer mapping works): ONE kernel per step does the compute and the exchange -- it
+    computes the boundary planes first, stores them locally AND into the neighbour's ghost planes through the
+    peer mapping, raises the neighbour's flag from inside the kernel and then computes the interior; the next
+    step's kernel waits on its own flags before touching its ghost planes (percnn_step_fwd_fused_halo).
 
 `exchange_ghosts` is device-agnostic (it only moves planes with torch.distributed), which is what the
 world_size-2 gloo tests exercise on CPU; the step kernels themselves are CUDA-only.
@@ -81,28 +85,34 @@ class SlabRollout:
         self.transport = transport
         self.symm = None
         shape = self.plan.buffer_shape
-        if transport in ("auto", "symm") and world > 1:
+        if transport in ("auto", "symm", "fused") and world > 1:
             # peer-mapped buffers over NVLink; every rank must take the same branch, so agree on the outcome
             ok, both = 1, None
             try:
                 import torch.distributed._symmetric_memory as symm_mem
                 both = symm_mem.empty((2, *shape), dtype=torch.float32, device=self.device)
                 self.symm = symm_mem.rendezvous(both, group=group if group is not None else dist.group.WORLD)
+                self._words = symm_mem.empty((8,), dtype=torch.int32, device=self.device)
+                self._words_hdl = symm_mem.rendezvous(self._words, group=group if group is not None else dist.group.WORLD)
             except Exception as e:  # noqa: BLE001
-                if transport == "symm":
+                if transport in ("symm", "fused"):
                     raise
                 ok, self.symm, self._symm_error = 0, None, repr(e)[:200]
             flag = torch.tensor([ok], device=self.device)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
             if int(flag.item()) == 0:
                 self.symm = None
+        self.epoch = 1
         if self.symm is not None:
-            self.transport = "symm"
+            self.transport = "symm" if transport == "symm" or self.nz < 5 else "fused"
             both.zero_()
+            self._words.zero_()
             self.bufs = [both[0], both[1]]
             lo, hi = (rank - 1) % world, (rank + 1) % world
             self.peer_lo = self.symm.get_buffer(lo, (2, *shape), torch.float32)
             self.peer_hi = self.symm.get_buffer(hi, (2, *shape), torch.float32)
+            self._peer_lo_words = self._words_hdl.get_buffer(lo, (8,), torch.int32)
+            self._peer_hi_words = self._words_hdl.get_buffer(hi, (8,), torch.int32)
         else:
             self.transport = "nccl" if world > 1 else "local"
             self.bufs = [torch.zeros(shape, dtype=torch.float32, device=self.device) for _ in range(2)]
@@ -120,6 +130,12 @@ class SlabRollout:
         b = self.bufs[self.cur]
         b[:, 2:self.nz + 2].copy_(interior)
         self._exchange_blocking(self.cur)
+        if self.transport == "fused":
+            # ghosts of the current buffer are valid up to the current epoch on every rank
+            self._words[0:2].fill_(self.epoch)
+            self._words[2:4].zero_()
+            torch.cuda.synchronize(self.device)
+            dist.barrier(self.group)
 
     def interior(self) -> torch.Tensor:
         return self.bufs[self.cur][:, 2:self.nz + 2]
@@ -139,8 +155,10 @@ class SlabRollout:
         if self.world > 1:
             dist.barrier(self.group)
         if self.symm is not None:
-            self._symm_push(b)
-            self._symm_wait()
+            nz = self.nz
+            me = self.bufs[b]
+            self.peer_lo[b][:, nz + 2:nz + 4].copy_(me[:, 2:4])
+            self.peer_hi[b][:, 0:2].copy_(me[:, nz:nz + 2])
         else:
             for w in exchange_ghosts(self.bufs[b], self.nz, self.rank, self.world, self.group):
                 w.wait()
@@ -193,9 +211,32 @@ class SlabRollout:
             self.plan.step_fwd_range(cur, nxt, 2, nz - 2)
         self.cur ^= 1
 
+    def _step_fused(self) -> None:
+        from ._lib import SlabLink
+        nxt = self.cur ^ 1
+        link = SlabLink()
+        link.peer_lo_out = self.peer_lo[nxt].data_ptr()
+        link.peer_hi_out = self.peer_hi[nxt].data_ptr()
+        link.my_flags = self._words.data_ptr()
+        link.peer_lo_flags = self._peer_lo_words.data_ptr()
+        link.peer_hi_flags = self._peer_hi_words.data_ptr()
+        link.scratch = self._words.data_ptr() + 8
+        link.epoch = self.epoch & 0xFFFFFFFF
+        self.plan.step_fwd_fused_halo(self.bufs[self.cur], self.bufs[nxt], link)
+        self.epoch += 1
+        self.cur = nxt
+
+    def error_word(self) -> int:
+        """Non-zero if a fused step gave up waiting for a neighbour (device-side spin deadline)."""
+        return int(self._words[3].item()) if self.transport == "fused" else 0
+
     def run(self, nsteps: int) -> None:
         """Advance the slab by nsteps time steps.  Invariant on entry and exit: the ghosts of the current
         buffer are valid and every exchange signal has been consumed (set_state() establishes it)."""
+        if self.transport == "fused":
+            for _ in range(nsteps):
+                self._step_fused()
+            return
         for i in range(nsteps):
             self._step(first=(i == 0))
         if self.world > 1 and nsteps > 0:
