@@ -132,6 +132,9 @@ typedef struct percnn_slab_link {
 } percnn_slab_link_t;
 int percnn_step_fwd_fused_halo(percnn_plan_t* plan, const void* h_in, void* h_out, const percnn_slab_link_t* link,
                                void* stream);
+/* Adjoint of the fused slab step: g_in's boundary planes are mirrored into the neighbours' g_in ghost planes. */
+int percnn_step_bwd_fused_halo(percnn_plan_t* plan, const void* h_in, const void* g_out, const void* g_add, void* g_in,
+                               void* ws, const percnn_slab_link_t* link, void* stream);
 /* Adjoint of one step (replaces autograd through GS2D:105-121): g_in = g_add + (dh_out/dh_in)^T g_out
  * (g_add may be NULL), and the step's parameter-gradient sums are ACCUMULATED into the accumulator at the
  * head of `ws` (zeroed by percnn_param_grads_begin, read by percnn_param_grads_finish). */

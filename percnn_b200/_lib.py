@@ -24,7 +24,7 @@ EXPORTS = (
     "percnn_abi_version", "percnn_last_error", "percnn_device_ok", "percnn_plan_create", "percnn_plan_destroy",
     "percnn_param_count", "percnn_state_elems", "percnn_workspace_bytes", "percnn_plan_uses_tma",
     "percnn_plan_launch_count", "percnn_params_load", "percnn_step_fwd", "percnn_step_fwd_range",
-    "percnn_step_fwd_fused_halo", "percnn_step_bwd",
+    "percnn_step_fwd_fused_halo", "percnn_step_bwd_fused_halo", "percnn_step_bwd",
     "percnn_param_grads_begin", "percnn_param_grads_finish", "percnn_rollout_fwd", "percnn_rollout_bwd",
     "percnn_rollout_fwd_host",
 )
@@ -82,6 +82,7 @@ def lib() -> ctypes.CDLL:
     L.percnn_step_fwd.argtypes = [vp, vp, vp, vp]
     L.percnn_step_fwd_range.argtypes = [vp, vp, vp, c_int, c_int, vp]
     L.percnn_step_fwd_fused_halo.argtypes = [vp, vp, vp, POINTER(SlabLink), vp]
+    L.percnn_step_bwd_fused_halo.argtypes = [vp, vp, vp, vp, vp, vp, POINTER(SlabLink), vp]
     L.percnn_step_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.percnn_param_grads_begin.argtypes = [vp, vp, vp]
     L.percnn_param_grads_finish.argtypes = [vp, vp, vp, vp, vp]

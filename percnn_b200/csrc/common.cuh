@@ -26,6 +26,7 @@ enum PrepIndex : int {
   P_PHYS = 16,     // Burgers: C1_u C2_u C1_v C2_v | dx taps[4] | dy taps[4]   (taps / dx, BUR3:78-80)
                    // LO:      C1..C5_u | C1..C5_v | C6_v
   P_BRANCH = 64,   // raw 1x1 weights for PERCNN_FLAG_EVAL_BRANCH: per field W1[hc][2] b1[hc] W2.. W3.. W4[hc] b4
+  P_LAPT = 384,    // [13] Laplacian taps mirrored along every axis (the adjoint stencil): c0, then [3][4]
   P_SIZE = 400
 };
 constexpr int kMaxHidden = 16;
@@ -71,6 +72,22 @@ struct PrepView<double> {
 __device__ __forceinline__ int wrap_idx(int i, int n) {
   // valid for -n <= i < 2n
   return i < 0 ? i + n : (i >= n ? i - n : i);
+}
+
+// Last-block fold of per-block partial sums: acc[i] += scale * sum_b partials[b * nred + i].
+// Every warp of the calling block takes values i = warp, warp + nwarps, ...; its lanes stride over the blocks and
+// a fixed shuffle tree combines them, so the result is deterministic for a given grid and the loads are
+// independent (a serial loop over hundreds of blocks costs one L2 round trip per block).
+__device__ __forceinline__ void fold_partials(const double* __restrict__ partials, unsigned nblocks, int nred,
+                                              double* __restrict__ acc, double scale, int acc_offset = 0) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int i = warp; i < nred; i += nwarps) {
+    double s = 0;
+    for (unsigned b = lane; b < nblocks; b += 32) s += __ldcg(partials + size_t(b) * nred + i);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+    if (lane == 0) acc[acc_offset + i] += scale * s;
+  }
 }
 
 __device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }

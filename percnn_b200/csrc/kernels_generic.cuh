@@ -90,11 +90,7 @@ __device__ __forceinline__ void reduce_into_acc(const T (&v)[NRED], double* __re
   __syncthreads();
   if (s_last) {
     __threadfence();
-    if (threadIdx.x < NRED) {
-      double s = 0;
-      for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(partials + size_t(b) * NRED + threadIdx.x);
-      acc[threadIdx.x] += s;
-    }
+    fold_partials(partials, gridDim.x, NRED, acc, 1.0);
     if (threadIdx.x == 0) *counter = 0;
   }
 }

@@ -24,15 +24,16 @@ namespace percnn {
 namespace tma3d {
 
 constexpr int TX = 128;        // tile width  = one warp x 4 cells per lane
-constexpr int TY = 16;         // MAXIMUM tile height = consumer warps; the actual height is Params::ty
+constexpr int TY = 16;         // MAXIMUM tile height = consumer warps; the actual height is Params::ty (<= 15,
+                               // so that the adjoint kernel, which runs 15 consumer warps, can share the tiling)
 constexpr int STAGES = 8;      // planes in the ring
-constexpr int ROWS = TY + 4;   // rows per field per stage (2 halo rows above and below)
+constexpr int ROWS = TY + 4;   // rows per field per stage (2 halo rows above and below)   // rows per field per stage (2 halo rows above and below)
 constexpr int STAGE_FLOATS = 2 * ROWS * TX;
 constexpr int STAGE_BYTES = STAGE_FLOATS * 4;
 constexpr int CONSUMER_THREADS = TY * 32;
 // 16 consumer warps + one producer warp-group (4 warps, of which one lane works).  The kernel is launched at
 // the register count 640 threads allow (96); setmaxnreg then moves registers from the idle producer
-// warp-group to the consumers, whose 5-plane window wants ~120.
+// warp-group to the consumers, whose 5-plane window wants ~100.
 constexpr int THREADS = CONSUMER_THREADS + 128;
 constexpr int CONSUMER_REGS = 112;   // 512 * 112 + 128 * 24 <= 640 * 96: setmaxnreg only redistributes the CTA's own allocation
 constexpr int PRODUCER_REGS = 24;
@@ -160,7 +161,7 @@ __device__ __forceinline__ void lap_quad(const float* __restrict__ P, const floa
 __device__ __forceinline__ float4 lds128(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
 struct ItemCoord {
-  int x0, y0, z0, nz, seg;
+  int x0, y0, z0, nz, seg, ytile;
 };
 __device__ __forceinline__ int total_items(const Params& p) {
   int n = 0;
@@ -180,6 +181,7 @@ __device__ __forceinline__ ItemCoord decode_item(const Params& p, int item) {
   const int yt = r % p.nyt;
   const int zc = r / p.nyt;
   c.seg = seg;
+  c.ytile = yt;
   c.x0 = xt * TX;
   c.y0 = min(yt * p.ty, p.H - p.ty);
   c.z0 = p.seg_lo[seg] + zc * p.seg_tz[seg];

@@ -1,0 +1,397 @@
+// Adjoint of the fused 3-D Pi-block step (k = 1), same streaming structure as kernels_gs3d_tma.cuh:
+//
+//   g_u = g_add_u + Gu + dt (alpha_u Lap^T Gu + Gu dRu/du + Gv dRv/du)          
+//   g_v = g_add_v + Gv + dt (alpha_v Lap^T Gv + Gu dRu/dv + Gv dRv/dv)
+//   22 reductions per step: sum q dt Lap^T(Gq) (-> dL/dalpha_q) and sum dt G_f u^a v^b (-> the folded cubic)
+//
+// G (the incoming gradient) streams through the TMA ring exactly like the state does in the forward kernel
+// (5-plane register window, y-neighbours from shared memory, x-neighbours by shuffle, seam lanes from global);
+// the stored state h_t (centre only, no halo) and the injected loss gradient g_add are read with coalesced
+// 128-bit loads one plane ahead.  Algorithmic traffic: 24 B/cell (+8 with g_add).
+// Reductions: per-lane fp32 partial sums, flushed every 32 planes into per-warp fp64 accumulators in shared
+// memory; per-CTA results go to global memory and the last CTA folds them in fixed order (deterministic).
+#pragma once
+#include "kernels_gs3d_tma.cuh"
+
+namespace percnn {
+namespace tma3d {
+
+constexpr int BWD_FLUSH = 32;
+// The adjoint holds 22 running sums and the state on top of the 5-plane window: 15 consumer warps + 1 producer
+// warp = 512 threads = 128 registers per thread (a 17th warp would round the allocation down to 96).
+constexpr int BWD_WARPS = 15;
+constexpr int BWD_THREADS = (BWD_WARPS + 1) * 32;
+constexpr int SMEM_BYTES_BWD = SMEM_BYTES + 16 * 2 * 8 + 64;
+
+struct BwdExtra {
+  const float* h;        // stored state of this step, same layout as the G buffers
+  const float* gadd;     // injected gradient for this step (nullable)
+  double* partials;      // [gridDim.x][2]
+  unsigned* counter;
+  double* acc;           // [22] running sums over steps ([0..1] from this kernel, [2..21] from k_monomial_sums)
+};
+
+__device__ __forceinline__ float2 quad2(const float* __restrict__ d, float2 u, float2 v) {
+  float2 a0 = fma2(u, fma2(u, d[3], d[1]), d[0]);
+  float2 a1 = fma2(u, d[4], d[2]);
+  return fma2(v, fma2(v, d[5], a1), a0);
+}
+__device__ __forceinline__ float4 ldg128(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// One steady-state plane of the adjoint.  `valid`: this warp's row is not a duplicate of the previous tile's
+// rows (last tile of a column is shifted back), so it contributes to the reductions.
+template <int R, bool FUSED>
+__device__ __forceinline__ void steady_plane_bwd(Consumer& c, const float* __restrict__ TP, bool drain, bool prefetch_seam,
+                                                 const float* seam_ptr, int64_t field, int64_t plane, int64_t off,
+                                                 float* __restrict__ dst, float* mirror, const float* __restrict__ hbase,
+                                                 const float* __restrict__ gadd, bool prefetch_next, bool valid,
+                                                 float4 (&wu)[5], float4 (&wv)[5], float2 (&seam_next)[2],
+                                                 float (&aacc)[2]) {
+  const float* P = c.P;
+  mbar_wait(&c.full[c.s], c.parity);
+  {
+    const float* st = c.ring + c.s * STAGE_FLOATS + (c.row + 2) * TX + 4 * c.lane;
+    wu[(R + 4) % 5] = lds128(st);
+    wv[(R + 4) % 5] = lds128(st + ROWS * TX);
+  }
+  if (drain) {
+    __syncwarp();
+    if (c.lane == 0) mbar_arrive(&c.empty[c.s]);
+  }
+  const float2 seam_u = seam_next[0], seam_v = seam_next[1];
+  if (prefetch_seam) {
+    ldg_f2_if(c.is_seam, seam_ptr, seam_next[0]);
+    ldg_f2_if(c.is_seam, seam_ptr + field, seam_next[1]);
+  }
+  // stored state of this output plane (its lines were pulled into L2 one plane ago); then pull the next
+  // plane's h / g_add lines into L2 (one lane per 128-byte line) so no register is held across the iteration
+  const float4 hu = ldg128(hbase + off), hv = ldg128(hbase + off + field);
+  if (prefetch_next && (c.lane & 7) == 0) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(hbase + off + plane));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(hbase + off + plane + field));
+    if (gadd != nullptr) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(gadd + off + plane));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(gadd + off + plane + field));
+    }
+  }
+  const uint32_t s2 = (c.s + STAGES - 2) & (STAGES - 1);
+  const float* sp = c.ring + s2 * STAGE_FLOATS + c.row * TX + 4 * c.lane;
+  const float4 wl_u[5] = {wu[(R + 0) % 5], wu[(R + 1) % 5], wu[(R + 2) % 5], wu[(R + 3) % 5], wu[(R + 4) % 5]};
+  const float4 wl_v[5] = {wv[(R + 0) % 5], wv[(R + 1) % 5], wv[(R + 2) % 5], wv[(R + 3) % 5], wv[(R + 4) % 5]};
+  const float4 Gu = wl_u[2], Gv = wl_v[2];
+  float2 Lu_lo, Lu_hi, Lv_lo, Lv_hi;
+  {
+    const float4 y[4] = {lds128(sp), lds128(sp + TX), lds128(sp + 3 * TX), lds128(sp + 4 * TX)};
+    float Lz = __shfl_up_sync(0xffffffffu, Gu.z, 1), Lw = __shfl_up_sync(0xffffffffu, Gu.w, 1);
+    float Rx = __shfl_down_sync(0xffffffffu, Gu.x, 1), Ry = __shfl_down_sync(0xffffffffu, Gu.y, 1);
+    if (c.lane == 0) { Lz = seam_u.x; Lw = seam_u.y; }
+    if (c.lane == 31) { Rx = seam_u.x; Ry = seam_u.y; }
+    lap_quad(TP, wl_u, y, Lz, Lw, Rx, Ry, Lu_lo, Lu_hi);
+  }
+  {
+    const float* spv = sp + ROWS * TX;
+    const float4 y[4] = {lds128(spv), lds128(spv + TX), lds128(spv + 3 * TX), lds128(spv + 4 * TX)};
+    float Lz = __shfl_up_sync(0xffffffffu, Gv.z, 1), Lw = __shfl_up_sync(0xffffffffu, Gv.w, 1);
+    float Rx = __shfl_down_sync(0xffffffffu, Gv.x, 1), Ry = __shfl_down_sync(0xffffffffu, Gv.y, 1);
+    if (c.lane == 0) { Lz = seam_v.x; Lw = seam_v.y; }
+    if (c.lane == 31) { Rx = seam_v.x; Ry = seam_v.y; }
+    lap_quad(TP, wl_v, y, Lz, Lw, Rx, Ry, Lv_lo, Lv_hi);
+  }
+  __syncwarp();
+  if (c.lane == 0) mbar_arrive(&c.empty[s2]);
+  float4 au4 = make_float4(0.f, 0.f, 0.f, 0.f), av4 = au4;
+  if (gadd != nullptr) {
+    au4 = ldg128(gadd + off);
+    av4 = ldg128(gadd + off + field);
+  }
+  const float alpha_u = P[P_ALPHA + 0], alpha_v = P[P_ALPHA + 1], dt = P[P_DT];
+  const float* D = P + P_DPOLY;
+  float4 ou, ov;
+  // ---- g_in for the two register pairs ----
+#define PERCNN_BWD_PAIR(U2, V2, GU2, GV2, LU2, LV2, OU0, OU1, OV0, OV1, AU0, AU1, AV0, AV1)                     \
+  {                                                                                                            \
+    const float2 gdu = mul2(GU2, dt), gdv = mul2(GV2, dt);                                                     \
+    const float2 su = fma2(gdu, quad2(D + 0, U2, V2), __fmul2_rn(gdv, quad2(D + 12, U2, V2)));                 \
+    const float2 sv = fma2(gdu, quad2(D + 6, U2, V2), __fmul2_rn(gdv, quad2(D + 18, U2, V2)));                 \
+    const float2 lu = mul2(LU2, dt), lv = mul2(LV2, dt);                                                       \
+    float2 gu = __fadd2_rn(GU2, fma2(lu, alpha_u, su));                                                        \
+    float2 gv = __fadd2_rn(GV2, fma2(lv, alpha_v, sv));                                                        \
+    gu = __fadd2_rn(gu, make_float2(AU0, AU1));                                                                \
+    gv = __fadd2_rn(gv, make_float2(AV0, AV1));                                                                \
+    OU0 = gu.x; OU1 = gu.y; OV0 = gv.x; OV1 = gv.y;                                                            \
+    if (valid) {                                                                                               \
+      aacc[0] = fmaf(U2.x, lu.x, fmaf(U2.y, lu.y, aacc[0]));                                                   \
+      aacc[1] = fmaf(V2.x, lv.x, fmaf(V2.y, lv.y, aacc[1]));                                                   \
+    }                                                                                                          \
+  }
+  PERCNN_BWD_PAIR(lo(hu), lo(hv), lo(Gu), lo(Gv), Lu_lo, Lv_lo, ou.x, ou.y, ov.x, ov.y, au4.x, au4.y, av4.x, av4.y)
+  PERCNN_BWD_PAIR(hi(hu), hi(hv), hi(Gu), hi(Gv), Lu_hi, Lv_hi, ou.z, ou.w, ov.z, ov.w, au4.z, au4.w, av4.z, av4.w)
+#undef PERCNN_BWD_PAIR
+  *reinterpret_cast<float4*>(dst + off) = ou;
+  *reinterpret_cast<float4*>(dst + off + field) = ov;
+  if (FUSED && mirror != nullptr) {
+    *reinterpret_cast<float4*>(mirror) = ou;
+    *reinterpret_cast<float4*>(mirror + field) = ov;
+  }
+  advance_stage(c);
+}
+
+template <int SLOT, bool FUSED>
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_halo,
+               const __grid_constant__ Params p, const __grid_constant__ BwdExtra x) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  float* ring = reinterpret_cast<float*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  double* wacc = reinterpret_cast<double*>(smem_raw + STAGES * STAGE_BYTES + 2 * STAGES * 8 + 64);   // [TY][22]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], p.ty);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < TY * 2; i += BWD_THREADS) wacc[i] = 0.0;
+  __syncthreads();
+  const int nitems = total_items(p);
+
+  if (warp >= BWD_WARPS) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_main)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_halo)) : "memory");
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const ItemCoord ic = decode_item(p, item);
+        if (FUSED && ic.seg < 2) {
+          wait_flag(p.my_flags + ic.seg, p.epoch_wait, p.scratch + 1);
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+        }
+        int yh[4] = {ic.y0 - 2, ic.y0 - 1, ic.y0 + p.ty, ic.y0 + p.ty + 1};
+#pragma unroll
+        for (int h = 0; h < 4; ++h) yh[h] = yh[h] < 0 ? yh[h] + p.H : (yh[h] >= p.H ? yh[h] - p.H : yh[h]);
+        const uint32_t bytes_main = 2u * uint32_t(p.ty) * TX * 4u, bytes_halo = 2u * 4u * TX * 4u;
+        for (int k = 0; k < ic.nz + 4; ++k, ++it) {
+          const int s = it % STAGES;
+          if (it >= STAGES) mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+          const bool with_halo = (k >= 2) && (k < ic.nz + 2);
+          const int pz = src_plane(p, ic.z0, k);
+          float* st = ring + s * STAGE_FLOATS;
+          mbar_expect_tx(&full[s], with_halo ? bytes_main + bytes_halo : bytes_main);
+#pragma unroll
+          for (int f = 0; f < 2; ++f) {
+            float* sf = st + f * ROWS * TX;
+            tma_load_4d(sf + 2 * TX, &tm_main, &full[s], ic.x0, ic.y0, pz, f);
+            if (with_halo) {
+              tma_load_4d(sf, &tm_halo, &full[s], ic.x0, yh[0], pz, f);
+              tma_load_4d(sf + TX, &tm_halo, &full[s], ic.x0, yh[1], pz, f);
+              tma_load_4d(sf + (p.ty + 2) * TX, &tm_halo, &full[s], ic.x0, yh[2], pz, f);
+              tma_load_4d(sf + (p.ty + 3) * TX, &tm_halo, &full[s], ic.x0, yh[3], pz, f);
+            }
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ===== consumer warps =====
+  if (warp >= p.ty) return;
+  Consumer c;
+  c.P = c_prep[SLOT].f;
+  c.ring = ring;
+  c.full = full;
+  c.empty = empty;
+  c.s = 0;
+  c.parity = 0;
+  c.row = warp;
+  c.lane = lane;
+  c.toff = uint32_t(warp) * uint32_t(p.W) + 4u * uint32_t(lane);
+  c.is_seam = (lane == 0) || (lane == 31);
+  // lap_quad indexes its table as P[P_LAP_C0], P[P_LAP_AX + i]; the mirrored taps sit at P_LAPT in the same order
+  const float* TP = c.P + (P_LAPT - P_LAP_C0);
+  const int64_t plane = int64_t(p.H) * p.W;
+  const int64_t field = p.dst_field;
+  float4 wu[5], wv[5];
+  float2 seam_next[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+  float aacc[2] = {0.f, 0.f};
+  int since_flush = 0;
+  auto flush = [&]() {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      float t = aacc[i];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) t += __shfl_down_sync(0xffffffffu, t, off);
+      if (lane == 0) wacc[warp * 2 + i] += double(t);
+      aacc[i] = 0.f;
+    }
+    since_flush = 0;
+  };
+  bool posted = !FUSED;
+  auto post_boundary_done = [&]() {
+    asm volatile("bar.sync 1, %0;" ::"r"(p.ty * 32) : "memory");
+    if (warp == 0 && lane == 0) {
+      __threadfence_system();
+      const unsigned old = atomicAdd(p.scratch, 1u);
+      if (old == gridDim.x - 1) {
+        atomicExch(p.scratch, 0u);
+        __threadfence_system();
+        st_release_sys(p.post_lo_flag, p.epoch_post);
+        st_release_sys(p.post_hi_flag, p.epoch_post);
+      }
+    }
+  };
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const ItemCoord ic = decode_item(p, item);
+    if (FUSED && !posted && ic.seg == 2) {
+      post_boundary_done();
+      posted = true;
+    }
+    float* mirror = nullptr;
+    if (FUSED && ic.seg < 2) {
+      float* base = ic.seg == 0 ? p.peer_lo_dst : p.peer_hi_dst;
+      const int mz = ic.seg == 0 ? p.D + 2 + ic.z0 : ic.z0 - (p.D - 2);
+      mirror = base + (int64_t(mz) * p.H + ic.y0) * p.W + ic.x0 + c.toff;
+    }
+    // rows below the natural start of this tile are duplicates of the previous tile (last tile shifted back)
+    const bool valid = (ic.y0 + warp) >= ic.ytile * p.ty;
+    const float* src_xy = p.src + int64_t(ic.y0) * p.W + ic.x0;
+    int64_t off = (int64_t(ic.z0 + p.dst_zoff) * p.H + ic.y0) * p.W + ic.x0 + c.toff;   // this lane's quad, first output plane
+    int xs = (lane == 0) ? ic.x0 - 2 : ic.x0 + TX;
+    xs = xs < 0 ? xs + p.W : (xs >= p.W ? xs - p.W : xs);
+    const int seam_off = warp * p.W + xs - ic.x0;
+    int pz = src_plane(p, ic.z0, 2);
+    const float* seam_ptr = src_xy + int64_t(pz) * plane + seam_off;
+    const int64_t wrap_back = int64_t(p.D) * plane;
+
+    warm_plane<0>(c, true, wu, wv);
+    warm_plane<1>(c, true, wu, wv);
+    warm_plane<2>(c, false, wu, wv);
+    warm_plane<3>(c, false, wu, wv);
+    ldg_f2_if(c.is_seam, seam_ptr, seam_next[0]);
+    ldg_f2_if(c.is_seam, seam_ptr + p.src_field, seam_next[1]);
+
+    const int nk = ic.nz + 4;
+#define PERCNN_STEADY_B(RR)                                                                                     \
+  {                                                                                                             \
+    seam_ptr += plane;                                                                                          \
+    if (p.wrap_z && ++pz >= p.D) {                                                                              \
+      pz -= p.D;                                                                                                \
+      seam_ptr -= wrap_back;                                                                                    \
+    }                                                                                                           \
+    steady_plane_bwd<RR, FUSED>(c, TP, k >= ic.nz + 2, k <= ic.nz + 2, seam_ptr, field, plane, off, p.dst, mirror, \
+                                x.h, x.gadd, k + 1 < nk, valid, wu, wv, seam_next, aacc);                 \
+    off += plane;                                                                                               \
+    if (FUSED && mirror != nullptr) mirror += plane;                                                            \
+    if (++since_flush >= BWD_FLUSH) flush();                                                                    \
+    ++k;                                                                                                        \
+  }
+    int k = 4;
+    PERCNN_STEADY_B(4)
+    while (k + 5 <= nk) {
+      PERCNN_STEADY_B(0) PERCNN_STEADY_B(1) PERCNN_STEADY_B(2) PERCNN_STEADY_B(3) PERCNN_STEADY_B(4)
+    }
+    if (k < nk) PERCNN_STEADY_B(0)
+    if (k < nk) PERCNN_STEADY_B(1)
+    if (k < nk) PERCNN_STEADY_B(2)
+    if (k < nk) PERCNN_STEADY_B(3)
+#undef PERCNN_STEADY_B
+  }
+  if (FUSED && !posted) post_boundary_done();
+  flush();
+  // ---- CTA result -> global partials; last CTA folds all CTAs in fixed order ----
+  asm volatile("bar.sync 2, %0;" ::"r"(p.ty * 32) : "memory");
+  __shared__ bool s_last;
+  if (warp == 0) {
+    if (lane < 2) {
+      double s = 0;
+      for (int w = 0; w < p.ty; ++w) s += wacc[w * 2 + lane];
+      x.partials[size_t(blockIdx.x) * 2 + lane] = s;
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) s_last = (atomicAdd(x.counter, 1u) == gridDim.x - 1);
+    __syncwarp();
+    if (s_last) {
+      __threadfence();
+      if (lane < 2) {
+        double s = 0;
+        for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(x.partials + size_t(b) * 2 + lane);
+        x.acc[lane] += s;
+      }
+      if (lane == 0) *x.counter = 0;
+    }
+  }
+}
+
+// The 20 monomial sums  sum_x dt G_f u^a v^b  (-> gradient of the folded cubic) need no stencil: a plain
+// streaming pass over h and G (16 B/cell) with 128-bit loads.  Kept out of the stencil kernel so that the latter
+// fits its register budget (its 5-plane window + 20 running sums spilled).
+__global__ void __launch_bounds__(256) k_monomial_sums(const float* __restrict__ h, const float* __restrict__ g, int64_t field,
+                                                       int64_t base, int64_t n4, float dt, double* __restrict__ partials,
+                                                       unsigned* __restrict__ counter, double* __restrict__ acc) {
+  float2 m[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) m[i] = make_float2(0.f, 0.f);
+  const float4* hu = reinterpret_cast<const float4*>(h + base);
+  const float4* hv = reinterpret_cast<const float4*>(h + base + field);
+  const float4* gu = reinterpret_cast<const float4*>(g + base);
+  const float4* gv = reinterpret_cast<const float4*>(g + base + field);
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x) {
+    const float4 u4 = __ldg(hu + i), v4 = __ldg(hv + i), a4 = __ldg(gu + i), b4 = __ldg(gv + i);
+    const float us[4] = {u4.x, u4.y, u4.z, u4.w}, vs[4] = {v4.x, v4.y, v4.z, v4.w};
+    const float as[4] = {a4.x, a4.y, a4.z, a4.w}, bs[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float u = us[j], v = vs[j];
+      const float2 gg = make_float2(as[j], bs[j]);
+      const float uu = u * u, uv = u * v, vv = v * v;
+      m[0] = __fadd2_rn(m[0], gg);
+      m[1] = fma2(gg, u, m[1]);
+      m[2] = fma2(gg, v, m[2]);
+      m[3] = fma2(gg, uu, m[3]);
+      m[4] = fma2(gg, uv, m[4]);
+      m[5] = fma2(gg, vv, m[5]);
+      m[6] = fma2(gg, uu * u, m[6]);
+      m[7] = fma2(gg, uu * v, m[7]);
+      m[8] = fma2(gg, u * vv, m[8]);
+      m[9] = fma2(gg, vv * v, m[9]);
+    }
+  }
+  __shared__ double sm[8][20];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    double a = double(m[i].x), b = double(m[i].y);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      a += __shfl_down_sync(0xffffffffu, a, off);
+      b += __shfl_down_sync(0xffffffffu, b, off);
+    }
+    if (lane == 0) {
+      sm[warp][i] = a;        // field u sums
+      sm[warp][10 + i] = b;   // field v sums
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 20) {
+    double s = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += sm[w][threadIdx.x];
+    partials[size_t(blockIdx.x) * 20 + threadIdx.x] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    fold_partials(partials, gridDim.x, 20, acc, double(dt), 2);
+    if (threadIdx.x == 0) *counter = 0;
+  }
+}
+
+}  // namespace tma3d
+}  // namespace percnn

@@ -441,9 +441,16 @@ __global__ void __launch_bounds__(BTHREADS) k_pi_k5_bwd(Geom g, int slot, int hc
 __global__ void k5_reduce_partials(const float* __restrict__ partials, int nblocks, int nparams, double* __restrict__ acc) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nparams) return;
-  double s = 0;
-  for (int b = 0; b < nblocks; ++b) s += double(__ldg(partials + size_t(b) * nparams + i));
-  acc[i] += s;
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;   // four independent chains keep the loads in flight; order is fixed
+  int b = 0;
+  for (; b + 4 <= nblocks; b += 4) {
+    s0 += double(__ldg(partials + size_t(b) * nparams + i));
+    s1 += double(__ldg(partials + size_t(b + 1) * nparams + i));
+    s2 += double(__ldg(partials + size_t(b + 2) * nparams + i));
+    s3 += double(__ldg(partials + size_t(b + 3) * nparams + i));
+  }
+  for (; b < nblocks; ++b) s0 += double(__ldg(partials + size_t(b) * nparams + i));
+  acc[i] += (s0 + s1) + (s2 + s3);
 }
 
 // raw-packing accumulators -> gradients (only CA/CB need the sigmoid chain rule; the frozen Laplacian gets 0)

@@ -128,6 +128,11 @@ __global__ void k_prep(const T* __restrict__ raw, PrepDesc d, PrepBlock* __restr
     }
   }
   __syncthreads();
+  if (threadIdx.x < 13) {   // mirrored taps for the adjoint kernels
+    const int i = threadIdx.x;
+    v[P_LAPT + i] = i == 0 ? v[P_LAP_C0] : v[P_LAP_AX + ((i - 1) / 4) * 4 + (3 - (i - 1) % 4)];
+  }
+  __syncthreads();
   for (int i = threadIdx.x; i < P_SIZE; i += blockDim.x) {
     out->d[i] = v[i];
     out->f[i] = float(v[i]);

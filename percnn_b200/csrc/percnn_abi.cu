@@ -9,6 +9,7 @@
 
 #include "kernels_generic.cuh"
 #include "kernels_gs3d_tma.cuh"
+#include "kernels_gs3d_tma_bwd.cuh"
 #include "kernels_pi_k5.cuh"
 #include "kernels_prep.cuh"
 
@@ -123,9 +124,9 @@ double tiling_cost(int nxt, int H, int depth, int nsm, int ty, int nzc, TmaTilin
   return cost;
 }
 TmaTiling choose_tiling(int nxt, int H, int depth, int nsm, int fixed_ty) {
-  TmaTiling best{16, depth, (H + 15) / 16, 1};
+  TmaTiling best{tma3d::BWD_WARPS, depth, (H + tma3d::BWD_WARPS - 1) / tma3d::BWD_WARPS, 1};
   double best_cost = 1e300;
-  for (int ty = (fixed_ty ? fixed_ty : 1); ty <= (fixed_ty ? fixed_ty : tma3d::TY); ++ty) {
+  for (int ty = (fixed_ty ? fixed_ty : 1); ty <= (fixed_ty ? fixed_ty : tma3d::BWD_WARPS); ++ty) {
     if (ty > H) break;
     for (int nzc = 1; nzc <= depth; ++nzc) {
       TmaTiling t;
@@ -184,7 +185,7 @@ struct SlabLink {   // mirrors percnn_slab_link_t
 };
 
 int launch_tma_fwd(percnn_plan* p, const float* src, float* dst, int z_lo, int z_hi, cudaStream_t st,
-                   const SlabLink* link = nullptr) {
+                   const SlabLink* link = nullptr, const tma3d::BwdExtra* bwd = nullptr) {
   const CUtensorMap *mm, *hm;
   int rc = get_maps(p, src, &mm, &hm);
   if (rc) return rc;
@@ -243,7 +244,10 @@ int launch_tma_fwd(percnn_plan* p, const float* src, float* dst, int z_lo, int z
   switch (p->slot) {
 #define PERCNN_TMA_CASE(S) \
   case S:                                                                                                   \
-    if (prm.fused) tma3d::k_gs3d_fwd_tma<S, true><<<grid, tma3d::THREADS, tma3d::SMEM_BYTES, st>>>(*mm, *hm, prm); \
+    if (bwd) {                                                                                              \
+      if (prm.fused) tma3d::k_gs3d_bwd_tma<S, true><<<grid, tma3d::BWD_THREADS, tma3d::SMEM_BYTES_BWD, st>>>(*mm, *hm, prm, *bwd); \
+      else tma3d::k_gs3d_bwd_tma<S, false><<<grid, tma3d::BWD_THREADS, tma3d::SMEM_BYTES_BWD, st>>>(*mm, *hm, prm, *bwd);   \
+    } else if (prm.fused) tma3d::k_gs3d_fwd_tma<S, true><<<grid, tma3d::THREADS, tma3d::SMEM_BYTES, st>>>(*mm, *hm, prm); \
     else tma3d::k_gs3d_fwd_tma<S, false><<<grid, tma3d::THREADS, tma3d::SMEM_BYTES, st>>>(*mm, *hm, prm);   \
     break;
     PERCNN_TMA_CASE(0) PERCNN_TMA_CASE(1) PERCNN_TMA_CASE(2) PERCNN_TMA_CASE(3) PERCNN_TMA_CASE(4) PERCNN_TMA_CASE(5)
@@ -322,7 +326,30 @@ int step_bwd_t(percnn_plan* p, const T* h, const T* gout, const T* gadd, T* gin,
   return PERCNN_OK;
 }
 
-int step_bwd_any(percnn_plan* p, const void* h, const void* gout, const void* gadd, void* gin, void* ws, cudaStream_t st) {
+int step_bwd_any(percnn_plan* p, const void* h, const void* gout, const void* gadd, void* gin, void* ws, cudaStream_t st,
+                 const SlabLink* link = nullptr) {
+  if (p->use_tma) {
+    char* w = static_cast<char*>(ws);
+    tma3d::BwdExtra x;
+    x.h = static_cast<const float*>(h);
+    x.gadd = static_cast<const float*>(gadd);
+    x.partials = reinterpret_cast<double*>(w + kWsPartials);
+    x.counter = reinterpret_cast<unsigned*>(w + kWsCounter);
+    x.acc = reinterpret_cast<double*>(w + kWsAcc);
+    {  // the 20 stencil-free monomial sums: a streaming pass over the interior of h and G
+      const Geom& g = p->g;
+      const int64_t n4 = int64_t(g.D) * g.plane / 4;
+      int64_t blocks = (n4 + 255) / 256;
+      if (blocks > int64_t(p->sm_count) * 8) blocks = int64_t(p->sm_count) * 8;
+      tma3d::k_monomial_sums<<<int(blocks), 256, 0, st>>>(
+          x.h, static_cast<const float*>(gout), g.field, int64_t(g.ghost) * g.plane, n4, float(p->desc.dt),
+          reinterpret_cast<double*>(w + kWsPartials + 8192), reinterpret_cast<unsigned*>(w + kWsCounter + 64), x.acc);
+      PERCNN_CUDA(cudaGetLastError());
+      p->launches++;
+    }
+    return launch_tma_fwd(p, static_cast<const float*>(gout), static_cast<float*>(gin), 0, p->g.D, st, link, &x);
+  }
+  if (link) return fail(PERCNN_ERR_UNSUPPORTED, "fused halo adjoint needs a TMA plan");
   if (is_k5(p)) {
     char* w = static_cast<char*>(ws);
     double* acc = reinterpret_cast<double*>(w);
@@ -456,6 +483,10 @@ int percnn_plan_create(const percnn_desc_t* d, percnn_plan_t** out) {
     ae = cudaFuncSetAttribute(tma3d::k_gs3d_fwd_tma<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma3d::SMEM_BYTES); \
     if (ae == cudaSuccess)                                                                                               \
       ae = cudaFuncSetAttribute(tma3d::k_gs3d_fwd_tma<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma3d::SMEM_BYTES); \
+    if (ae == cudaSuccess)                                                                                               \
+      ae = cudaFuncSetAttribute(tma3d::k_gs3d_bwd_tma<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma3d::SMEM_BYTES_BWD); \
+    if (ae == cudaSuccess)                                                                                               \
+      ae = cudaFuncSetAttribute(tma3d::k_gs3d_bwd_tma<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma3d::SMEM_BYTES_BWD); \
     break;
         PERCNN_TMA_ATTR(0) PERCNN_TMA_ATTR(1) PERCNN_TMA_ATTR(2) PERCNN_TMA_ATTR(3) PERCNN_TMA_ATTR(4) PERCNN_TMA_ATTR(5)
 #undef PERCNN_TMA_ATTR
@@ -463,7 +494,7 @@ int percnn_plan_create(const percnn_desc_t* d, percnn_plan_t** out) {
       if (ae != cudaSuccess) { rc = fail(PERCNN_ERR_CUDA, "cudaFuncSetAttribute(tma) failed"); break; }
       int fixed_ty = 0;
       if (const char* e = getenv("PERCNN_TMA_TY")) fixed_ty = atoi(e);
-      if (fixed_ty < 0 || fixed_ty > tma3d::TY || fixed_ty > g.H) fixed_ty = 0;
+      if (fixed_ty < 0 || fixed_ty > tma3d::BWD_WARPS || fixed_ty > g.H) fixed_ty = 0;
       const TmaTiling til = choose_tiling(g.W / tma3d::TX, g.H, g.D, p->sm_count, fixed_ty);
       p->ty = til.ty;
       p->tz = til.tz;
@@ -557,6 +588,27 @@ int percnn_step_fwd_fused_halo(percnn_plan_t* p, const void* h_in, void* h_out, 
   l.epoch_post = link->epoch + 1;
   return launch_tma_fwd(p, static_cast<const float*>(h_in), static_cast<float*>(h_out), 0, p->g.D,
                         static_cast<cudaStream_t>(stream), &l);
+}
+
+// Adjoint counterpart of percnn_step_fwd_fused_halo: the gradient's boundary planes are mirrored into the
+// neighbours' ghost planes of their g_in buffers.
+int percnn_step_bwd_fused_halo(percnn_plan_t* p, const void* h_in, const void* g_out, const void* g_add, void* g_in,
+                               void* ws, const percnn_slab_link_t* link, void* stream) {
+  if (!p || !h_in || !g_out || !g_in || !ws || !link) return fail(PERCNN_ERR_INVALID, "null argument");
+  if (!p->use_tma || !p->desc.slab_ghost) return fail(PERCNN_ERR_UNSUPPORTED, "fused halo steps need a slab-mode TMA plan");
+  if (p->g.D < 5) return fail(PERCNN_ERR_UNSUPPORTED, "fused halo steps need at least 5 planes per rank");
+  if (!link->peer_lo_out || !link->peer_hi_out || !link->my_flags || !link->peer_lo_flags || !link->peer_hi_flags || !link->scratch)
+    return fail(PERCNN_ERR_INVALID, "incomplete slab link");
+  SlabLink l;
+  l.peer_lo_dst = static_cast<float*>(link->peer_lo_out);
+  l.peer_hi_dst = static_cast<float*>(link->peer_hi_out);
+  l.my_flags = link->my_flags;
+  l.post_lo_flag = link->peer_lo_flags + 1;
+  l.post_hi_flag = link->peer_hi_flags + 0;
+  l.scratch = link->scratch;
+  l.epoch_wait = link->epoch;
+  l.epoch_post = link->epoch + 1;
+  return step_bwd_any(p, h_in, g_out, g_add, g_in, ws, static_cast<cudaStream_t>(stream), &l);
 }
 
 int percnn_param_grads_begin(percnn_plan_t* p, void* ws, void* stream) {

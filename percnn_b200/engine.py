@@ -135,6 +135,14 @@ class Plan:
         check(self._L.percnn_step_fwd_fused_halo(self._h, h_in.data_ptr(), h_out.data_ptr(), ctypes.byref(link),
                                                  _stream_ptr(self.device)))
 
+    def step_bwd_fused_halo(self, h_in, g_out, g_in, link, g_add=None) -> None:
+        check(self._L.percnn_step_bwd_fused_halo(self._h, h_in.data_ptr(), g_out.data_ptr(), _ptr(g_add), g_in.data_ptr(),
+                                                 self.workspace().data_ptr(), ctypes.byref(link), _stream_ptr(self.device)))
+
+    def reduction_sums(self, n: int = 24) -> torch.Tensor:
+        """fp64 view of the running parameter-gradient sums at the head of the workspace (for the all-reduce)."""
+        return self.workspace()[:8 * n].view(torch.float64)
+
     def step_bwd(self, h_in, g_out, g_in, g_add=None) -> None:
         for t, n in ((h_in, "h_in"), (g_out, "g_out"), (g_in, "g_in")):
             self._check_state(t, n)

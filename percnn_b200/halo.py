@@ -226,6 +226,83 @@ class SlabRollout:
         self.epoch += 1
         self.cur = nxt
 
+    # -- training: forward with a tape, fused-halo adjoint ------------------------------------------
+    def _link(self, peer_lo_ptr: int, peer_hi_ptr: int):
+        from ._lib import SlabLink
+        link = SlabLink()
+        link.peer_lo_out, link.peer_hi_out = peer_lo_ptr, peer_hi_ptr
+        link.my_flags = self._words.data_ptr()
+        link.peer_lo_flags = self._peer_lo_words.data_ptr()
+        link.peer_hi_flags = self._peer_hi_words.data_ptr()
+        link.scratch = self._words.data_ptr() + 8
+        link.epoch = self.epoch & 0xFFFFFFFF
+        return link
+
+    def refresh_params(self) -> None:
+        """Re-read the cell's parameters (call after an optimiser step)."""
+        self.flat = engine.pack_params(self.cell._packed_tensors(), torch.float32)
+        self.plan.params_load(self.flat)
+
+    def rollout_tape(self, nsteps: int) -> torch.Tensor:
+        """Forward rollout that keeps every state: returns [nsteps+1, 2, nz+4, H, W] (ghosted slabs, slot 0 = the
+        current state).  The tape lives in peer-mapped memory so that each step's kernel can store its boundary
+        planes straight into the neighbours' tape slot (fused transport only)."""
+        if self.transport != "fused":
+            raise NotImplementedError("rollout_tape needs the fused peer-memory transport")
+        self.refresh_params()
+        import torch.distributed._symmetric_memory as symm_mem
+        shape = (nsteps + 1, *self.plan.buffer_shape)
+        if getattr(self, "_tape_shape", None) != shape:
+            self._tape = symm_mem.empty(shape, dtype=torch.float32, device=self.device)
+            hdl = symm_mem.rendezvous(self._tape, group=self.group if self.group is not None else dist.group.WORLD)
+            lo, hi = (self.rank - 1) % self.world, (self.rank + 1) % self.world
+            self._tape_lo = hdl.get_buffer(lo, shape, torch.float32)
+            self._tape_hi = hdl.get_buffer(hi, shape, torch.float32)
+            self._tape_shape = shape
+        tape = self._tape
+        tape[0].copy_(self.bufs[self.cur])
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)          # every rank's slot 0 (incl. ghosts) is in place before anyone mirrors into the tape
+        for t in range(nsteps):
+            link = self._link(self._tape_lo[t + 1].data_ptr(), self._tape_hi[t + 1].data_ptr())
+            self.plan.step_fwd_fused_halo(tape[t], tape[t + 1], link)
+            self.epoch += 1
+        self.bufs[self.cur].copy_(tape[nsteps])
+        return tape
+
+    def backward(self, tape: torch.Tensor, g_tape: torch.Tensor):
+        """Back-propagate through the taped rollout.  g_tape[t] = dL/d(tape[t]) in the same ghosted layout (what
+        autograd returns for a loss computed on tape[:, :, 2:-2]); ghost entries are ignored.
+        Returns (dL/dh0 interior [2, nz, H, W], flat parameter gradient summed over all ranks)."""
+        if self.transport != "fused":
+            raise NotImplementedError("backward needs the fused peer-memory transport")
+        nsteps = tape.shape[0] - 1
+        nz = self.nz
+        plan = self.plan
+        plan.params_load(self.flat)
+        plan.param_grads_begin()
+        # G_nsteps = dL/dh_nsteps with exchanged ghosts, in the peer-mapped ping-pong buffers
+        b = 0
+        self.bufs[b].zero_()
+        self.bufs[b][:, 2:nz + 2].copy_(g_tape[nsteps][:, 2:nz + 2])
+        self._exchange_blocking(b)
+        self._words[0:2].fill_(self.epoch)
+        self._words[2:4].zero_()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)
+        for t in range(nsteps - 1, -1, -1):
+            nxt = b ^ 1
+            link = self._link(self.peer_lo[nxt].data_ptr(), self.peer_hi[nxt].data_ptr())
+            plan.step_bwd_fused_halo(tape[t], self.bufs[b], self.bufs[nxt], link, g_add=g_tape[t])
+            self.epoch += 1
+            b = nxt
+        g_h0 = self.bufs[b][:, 2:nz + 2].clone()
+        sums = plan.reduction_sums()
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)     # one tiny all-reduce per backward pass
+        grads = plan.param_grads_finish(self.flat)
+        self.cur = 0   # the state buffers were used as gradient scratch: the caller must set_state() again
+        return g_h0, grads
+
     def error_word(self) -> int:
         """Non-zero if a fused step gave up waiting for a neighbour (device-side spin deadline)."""
         return int(self._words[3].item()) if self.transport == "fused" else 0

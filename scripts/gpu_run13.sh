@@ -1,0 +1,3 @@
+timeout 120 python -c "import __graft_entry__ as g; g.build(); g.smoke()" 2>&1 | tail -1
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+timeout 300 python scripts/perf_bwd.py

@@ -55,7 +55,8 @@ def train_case(name, tag, alias, shape, nsteps, lo=0.1, hi=0.9):
             p.grad = None
         h0.grad = None
         out = cell.rollout(h0, nsteps)
-        loss = ((out[0:-1:5, :, ::2, ::2] - target[:, :, ::2, ::2]) ** 2).mean()
+        sl = (slice(None), slice(None)) + (slice(None, None, 2),) * len(shape)
+        loss = ((out[0:-1:5][sl] - target[sl]) ** 2).mean()
         loss.backward()
     try:
         ms = timed(step, reps=3)
@@ -73,7 +74,8 @@ train_case("cfg3i Burgers k5 512^2 fp32", "bur1", "bur1", (512, 512), 40, -0.5, 
 fwd_case("cfg3ii Burgers phys 512^2 fp64", "bur3", None, (512, 512), 40, -0.5, 0.5)
 train_case("cfg3ii Burgers phys 512^2 fp64", "bur3", None, (512, 512), 40, -0.5, 0.5)
 fwd_case("cfg4 GS3D 128^3 fp32", "gs3d", "gs3d", (128, 128, 128), 500)
-train_case("GS3D 128^3 fp32 (generic adjoint)", "gs3d", "gs3d", (128, 128, 128), 20)
+train_case("GS3D 128^3 fp32 (TMA adjoint)", "gs3d", "gs3d", (128, 128, 128), 20)
+train_case("GS3D 256^3 fp32 (TMA adjoint)", "gs3d", "gs3d", (256, 256, 256), 20)
 train_case("GS2D 256^2 fp32", "gs2d", "gs2d", (256, 256), 200)
 fwd_case("ref-size GS3D 48^3", "gs3d", "gs3d", (48, 48, 48), 300)
 fwd_case("ref-size GS2D 100^2", "gs2d", "gs2d", (100, 100), 400)

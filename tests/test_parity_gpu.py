@@ -139,7 +139,8 @@ def test_branch_evaluation_agrees_with_folded_cubic(tag):
     assert rel_l2(a, b) <= roll_tol
 
 
-@pytest.mark.parametrize("tag,shape", [("bur1", (40, 72)), ("lo1", (33, 50)), ("gs2d", (37, 41)), ("gs3d", (9, 12, 20))])
+@pytest.mark.parametrize("tag,shape", [("bur1", (40, 72)), ("lo1", (33, 50)), ("gs2d", (37, 41)), ("gs3d", (9, 12, 20)),
+                                       ("gs3d", (10, 20, 128)), ("gs3d", (7, 33, 256))])
 def test_gradients_match_fp64_oracle_autograd_on_ragged_sizes(tag, shape):
     """Sizes that are not multiples of any tile: CUDA adjoint (fp32) vs torch autograd through the oracle in fp64."""
     alias = tag
@@ -207,6 +208,27 @@ def test_translation_equivariance_at_full_size(tag, shape):
         b = cell.rollout(torch.roll(h0, shifts, dims), 3)[-1]
     assert torch.equal(torch.roll(a, shifts, tuple(d - 1 for d in dims)), b)
     assert torch.isfinite(a).all()
+
+
+@pytest.mark.parametrize("shape", [(24, 37, 256), (64, 64, 128)])
+def test_tma_adjoint_matches_generic_adjoint(shape):
+    """Two independent CUDA adjoints (TMA z-marching vs generic gather) on the same rollout, incl. tile overlap
+    rows (H not a multiple of the tile height) that must not be double counted in the parameter sums."""
+    params = load_weights("gs3d")
+    g = torch.Generator().manual_seed(5)
+    h0 = (torch.rand((1, 2, *shape), generator=g) * 0.8 + 0.1)
+    w = torch.randn((4, 2, *shape), generator=g)
+    res = []
+    for flags in (0, _lib.FLAG_NO_TMA):
+        cell = _cell("gs3d", params)
+        cell._flags = flags
+        assert engine.get_plan(cell._spec(), shape, torch.device(DEV)).uses_tma == (flags == 0)
+        hd = h0.to(DEV).requires_grad_(True)
+        (cell.rollout(hd, 3) * w.to(DEV)).sum().backward()
+        res.append((hd.grad.cpu().numpy(), {k: p.grad.cpu().numpy() for k, p in cell.named_parameters() if p.grad is not None}))
+    assert rel_l2(res[0][0], res[1][0]) <= 2e-6
+    for k in res[0][1]:
+        assert rel_l2(res[0][1][k], res[1][1][k]) <= 1e-5, k
 
 
 def test_full_size_cfg4_tma_vs_generic_and_long_rollout_finite():
