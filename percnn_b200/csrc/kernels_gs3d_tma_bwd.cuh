@@ -5,7 +5,8 @@
 //   22 reductions per step: sum q dt Lap^T(Gq) (-> dL/dalpha_q) and sum dt G_f u^a v^b (-> the folded cubic)
 //
 // G (the incoming gradient) streams through the TMA ring exactly like the state does in the forward kernel
-// (5-plane register window, y-neighbours from shared memory, x-neighbours by shuffle, seam lanes from global);
+// (y-neighbours from shared memory, x-neighbours by shuffle, seam lanes from global; the z-neighbours are read
+// from the ring too instead of a register window);
 // the stored state h_t (centre only, no halo) and the injected loss gradient g_add are read with coalesced
 // 128-bit loads one plane ahead.  Algorithmic traffic: 24 B/cell (+8 with g_add).
 // Reductions: per-lane fp32 partial sums, flushed every 32 planes into per-warp fp64 accumulators in shared
@@ -38,33 +39,24 @@ __device__ __forceinline__ float2 quad2(const float* __restrict__ d, float2 u, f
 }
 __device__ __forceinline__ float4 ldg128(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
-// One steady-state plane of the adjoint.  `valid`: this warp's row is not a duplicate of the previous tile's
-// rows (last tile of a column is shifted back), so it contributes to the reductions.
-template <int R, bool FUSED>
-__device__ __forceinline__ void steady_plane_bwd(Consumer& c, const float* __restrict__ TP, bool drain, bool prefetch_seam,
-                                                 const float* seam_ptr, int64_t field, int64_t plane, int64_t off,
-                                                 float* __restrict__ dst, float* mirror, const float* __restrict__ hbase,
-                                                 const float* __restrict__ gadd, bool prefetch_next, bool valid,
-                                                 float4 (&wu)[5], float4 (&wv)[5], float2 (&seam_next)[2],
-                                                 float (&aacc)[2]) {
+// One output plane of the adjoint.  Unlike the forward kernel there is no register window: the five plane
+// centres (z-2..z+2) are all read from the ring (planes k-4..k stay resident), which frees 32 registers for the
+// state, the injected gradient and the pointwise Jacobian -- the windowed version spilled.
+// `valid`: this warp's row is not a duplicate of the previous tile's rows (last tile of a column is shifted
+// back), so it contributes to the reductions.
+template <bool FUSED>
+__device__ __forceinline__ void adjoint_plane(Consumer& c, const float* __restrict__ TP, bool prefetch_seam,
+                                              const float* seam_ptr, int64_t field, int64_t plane, int64_t off,
+                                              float* __restrict__ dst, float* mirror, const float* __restrict__ hbase,
+                                              const float* __restrict__ gadd, bool prefetch_next, bool valid,
+                                              float2 (&seam_next)[2], float (&aacc)[2]) {
   const float* P = c.P;
-  mbar_wait(&c.full[c.s], c.parity);
-  {
-    const float* st = c.ring + c.s * STAGE_FLOATS + (c.row + 2) * TX + 4 * c.lane;
-    wu[(R + 4) % 5] = lds128(st);
-    wv[(R + 4) % 5] = lds128(st + ROWS * TX);
-  }
-  if (drain) {
-    __syncwarp();
-    if (c.lane == 0) mbar_arrive(&c.empty[c.s]);
-  }
+  mbar_wait(&c.full[c.s], c.parity);   // plane k has landed; planes k-4 .. k-1 are still resident
   const float2 seam_u = seam_next[0], seam_v = seam_next[1];
   if (prefetch_seam) {
     ldg_f2_if(c.is_seam, seam_ptr, seam_next[0]);
     ldg_f2_if(c.is_seam, seam_ptr + field, seam_next[1]);
   }
-  // stored state of this output plane (its lines were pulled into L2 one plane ago); then pull the next
-  // plane's h / g_add lines into L2 (one lane per 128-byte line) so no register is held across the iteration
   const float4 hu = ldg128(hbase + off), hv = ldg128(hbase + off + field);
   if (prefetch_next && (c.lane & 7) == 0) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(hbase + off + plane));
@@ -74,31 +66,34 @@ __device__ __forceinline__ void steady_plane_bwd(Consumer& c, const float* __res
       asm volatile("prefetch.global.L2 [%0];" ::"l"(gadd + off + plane + field));
     }
   }
-  const uint32_t s2 = (c.s + STAGES - 2) & (STAGES - 1);
-  const float* sp = c.ring + s2 * STAGE_FLOATS + c.row * TX + 4 * c.lane;
-  const float4 wl_u[5] = {wu[(R + 0) % 5], wu[(R + 1) % 5], wu[(R + 2) % 5], wu[(R + 3) % 5], wu[(R + 4) % 5]};
-  const float4 wl_v[5] = {wv[(R + 0) % 5], wv[(R + 1) % 5], wv[(R + 2) % 5], wv[(R + 3) % 5], wv[(R + 4) % 5]};
-  const float4 Gu = wl_u[2], Gv = wl_v[2];
+  const uint32_t lane_off = (c.row + 2) * TX + 4 * c.lane;
   float2 Lu_lo, Lu_hi, Lv_lo, Lv_hi;
-  {
+  float4 Gu, Gv;
+#pragma unroll
+  for (int f = 0; f < 2; ++f) {
+    float4 win[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j)   // plane k-4+j sits in stage (s + STAGES - 4 + j) % STAGES
+      win[j] = lds128(c.ring + ((c.s + STAGES - 4 + j) & (STAGES - 1)) * STAGE_FLOATS + f * ROWS * TX + lane_off);
+    const float* sp = c.ring + ((c.s + STAGES - 2) & (STAGES - 1)) * STAGE_FLOATS + f * ROWS * TX + c.row * TX + 4 * c.lane;
     const float4 y[4] = {lds128(sp), lds128(sp + TX), lds128(sp + 3 * TX), lds128(sp + 4 * TX)};
-    float Lz = __shfl_up_sync(0xffffffffu, Gu.z, 1), Lw = __shfl_up_sync(0xffffffffu, Gu.w, 1);
-    float Rx = __shfl_down_sync(0xffffffffu, Gu.x, 1), Ry = __shfl_down_sync(0xffffffffu, Gu.y, 1);
-    if (c.lane == 0) { Lz = seam_u.x; Lw = seam_u.y; }
-    if (c.lane == 31) { Rx = seam_u.x; Ry = seam_u.y; }
-    lap_quad(TP, wl_u, y, Lz, Lw, Rx, Ry, Lu_lo, Lu_hi);
+    const float4 ctr = win[2];
+    float Lz = __shfl_up_sync(0xffffffffu, ctr.z, 1), Lw = __shfl_up_sync(0xffffffffu, ctr.w, 1);
+    float Rx = __shfl_down_sync(0xffffffffu, ctr.x, 1), Ry = __shfl_down_sync(0xffffffffu, ctr.y, 1);
+    const float2 seam = f == 0 ? seam_u : seam_v;
+    if (c.lane == 0) { Lz = seam.x; Lw = seam.y; }
+    if (c.lane == 31) { Rx = seam.x; Ry = seam.y; }
+    if (f == 0) {
+      lap_quad(TP, win, y, Lz, Lw, Rx, Ry, Lu_lo, Lu_hi);
+      Gu = ctr;
+    } else {
+      lap_quad(TP, win, y, Lz, Lw, Rx, Ry, Lv_lo, Lv_hi);
+      Gv = ctr;
+    }
   }
-  {
-    const float* spv = sp + ROWS * TX;
-    const float4 y[4] = {lds128(spv), lds128(spv + TX), lds128(spv + 3 * TX), lds128(spv + 4 * TX)};
-    float Lz = __shfl_up_sync(0xffffffffu, Gv.z, 1), Lw = __shfl_up_sync(0xffffffffu, Gv.w, 1);
-    float Rx = __shfl_down_sync(0xffffffffu, Gv.x, 1), Ry = __shfl_down_sync(0xffffffffu, Gv.y, 1);
-    if (c.lane == 0) { Lz = seam_v.x; Lw = seam_v.y; }
-    if (c.lane == 31) { Rx = seam_v.x; Ry = seam_v.y; }
-    lap_quad(TP, wl_v, y, Lz, Lw, Rx, Ry, Lv_lo, Lv_hi);
-  }
+  // plane k-4 is no longer needed by this warp
   __syncwarp();
-  if (c.lane == 0) mbar_arrive(&c.empty[s2]);
+  if (c.lane == 0) mbar_arrive(&c.empty[(c.s + STAGES - 4) & (STAGES - 1)]);
   float4 au4 = make_float4(0.f, 0.f, 0.f, 0.f), av4 = au4;
   if (gadd != nullptr) {
     au4 = ldg128(gadd + off);
@@ -107,7 +102,6 @@ __device__ __forceinline__ void steady_plane_bwd(Consumer& c, const float* __res
   const float alpha_u = P[P_ALPHA + 0], alpha_v = P[P_ALPHA + 1], dt = P[P_DT];
   const float* D = P + P_DPOLY;
   float4 ou, ov;
-  // ---- g_in for the two register pairs ----
 #define PERCNN_BWD_PAIR(U2, V2, GU2, GV2, LU2, LV2, OU0, OU1, OV0, OV1, AU0, AU1, AV0, AV1)                     \
   {                                                                                                            \
     const float2 gdu = mul2(GU2, dt), gdv = mul2(GV2, dt);                                                     \
@@ -133,7 +127,6 @@ __device__ __forceinline__ void steady_plane_bwd(Consumer& c, const float* __res
     *reinterpret_cast<float4*>(mirror) = ou;
     *reinterpret_cast<float4*>(mirror + field) = ov;
   }
-  advance_stage(c);
 }
 
 template <int SLOT, bool FUSED>
@@ -213,7 +206,6 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
   const float* TP = c.P + (P_LAPT - P_LAP_C0);
   const int64_t plane = int64_t(p.H) * p.W;
   const int64_t field = p.dst_field;
-  float4 wu[5], wv[5];
   float2 seam_next[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
   float aacc[2] = {0.f, 0.f};
   int since_flush = 0;
@@ -265,38 +257,34 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
     const float* seam_ptr = src_xy + int64_t(pz) * plane + seam_off;
     const int64_t wrap_back = int64_t(p.D) * plane;
 
-    warm_plane<0>(c, true, wu, wv);
-    warm_plane<1>(c, true, wu, wv);
-    warm_plane<2>(c, false, wu, wv);
-    warm_plane<3>(c, false, wu, wv);
-    ldg_f2_if(c.is_seam, seam_ptr, seam_next[0]);
-    ldg_f2_if(c.is_seam, seam_ptr + p.src_field, seam_next[1]);
-
-    const int nk = ic.nz + 4;
-#define PERCNN_STEADY_B(RR)                                                                                     \
-  {                                                                                                             \
-    seam_ptr += plane;                                                                                          \
-    if (p.wrap_z && ++pz >= p.D) {                                                                              \
-      pz -= p.D;                                                                                                \
-      seam_ptr -= wrap_back;                                                                                    \
-    }                                                                                                           \
-    steady_plane_bwd<RR, FUSED>(c, TP, k >= ic.nz + 2, k <= ic.nz + 2, seam_ptr, field, plane, off, p.dst, mirror, \
-                                x.h, x.gadd, k + 1 < nk, valid, wu, wv, seam_next, aacc);                 \
-    off += plane;                                                                                               \
-    if (FUSED && mirror != nullptr) mirror += plane;                                                            \
-    if (++since_flush >= BWD_FLUSH) flush();                                                                    \
-    ++k;                                                                                                        \
-  }
-    int k = 4;
-    PERCNN_STEADY_B(4)
-    while (k + 5 <= nk) {
-      PERCNN_STEADY_B(0) PERCNN_STEADY_B(1) PERCNN_STEADY_B(2) PERCNN_STEADY_B(3) PERCNN_STEADY_B(4)
+    const int nk = ic.nz + 4;   // local planes 0 .. nz+3 arrive in order; output plane k-2 is produced when plane k lands
+    for (int k = 0; k < nk; ++k) {
+      if (k < 4) {
+        mbar_wait(&c.full[c.s], c.parity);
+        if (k == 3) {
+          ldg_f2_if(c.is_seam, seam_ptr, seam_next[0]);
+          ldg_f2_if(c.is_seam, seam_ptr + p.src_field, seam_next[1]);
+        }
+      } else {
+        seam_ptr += plane;
+        if (p.wrap_z && ++pz >= p.D) {
+          pz -= p.D;
+          seam_ptr -= wrap_back;
+        }
+        adjoint_plane<FUSED>(c, TP, k <= ic.nz + 2, seam_ptr, field, plane, off, p.dst, mirror, x.h, x.gadd, k + 1 < nk,
+                             valid, seam_next, aacc);
+        off += plane;
+        if (FUSED && mirror != nullptr) mirror += plane;
+        if (++since_flush >= BWD_FLUSH) flush();
+      }
+      advance_stage(c);
     }
-    if (k < nk) PERCNN_STEADY_B(0)
-    if (k < nk) PERCNN_STEADY_B(1)
-    if (k < nk) PERCNN_STEADY_B(2)
-    if (k < nk) PERCNN_STEADY_B(3)
-#undef PERCNN_STEADY_B
+    // the last four planes of the item are still held: hand their stages back
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 1; j <= 4; ++j) mbar_arrive(&c.empty[(c.s + STAGES - j) & (STAGES - 1)]);
+    }
   }
   if (FUSED && !posted) post_boundary_done();
   flush();

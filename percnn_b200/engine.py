@@ -199,8 +199,18 @@ class Plan:
         if flat_host.is_cuda or h0_host.is_cuda:
             raise ValueError("rollout_fwd_host takes host tensors")
         nemit = 0 if emit is None else sum(1 for e in emit if e)
-        traj = torch.empty((nemit, *self.buffer_shape), dtype=self.spec.dtype).pin_memory() if nemit else None
-        fin = torch.empty(self.buffer_shape, dtype=self.spec.dtype).pin_memory() if want_final else None
+        # page-locking a GiB-sized buffer costs ~100 ms, so the pinned result buffers are kept across calls
+        # (the caller must consume/copy a result before the next call overwrites it)
+        cache = self.__dict__.setdefault("_host_out", {})
+        traj = fin = None
+        if nemit:
+            traj = cache.get(("traj", nemit))
+            if traj is None:
+                traj = cache[("traj", nemit)] = torch.empty((nemit, *self.buffer_shape), dtype=self.spec.dtype).pin_memory()
+        if want_final:
+            fin = cache.get("fin")
+            if fin is None:
+                fin = cache["fin"] = torch.empty(self.buffer_shape, dtype=self.spec.dtype).pin_memory()
         emit_arr = None if emit is None else (ctypes.c_uint8 * nsteps)(*[1 if e else 0 for e in emit])
         check(self._L.percnn_rollout_fwd_host(self._h, flat_host.data_ptr(), h0_host.data_ptr(), _ptr(traj), emit_arr,
                                               int(nsteps), _ptr(fin)))
