@@ -339,6 +339,11 @@ k_gs3d_fwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  // Programmatic dependent launch: the next step's grid may be scheduled while this one drains (its CTAs take
+  // the SMs our CTAs leave and run their prologue), and this grid touches global memory only after the previous
+  // one has completed (it wrote our input and reads the buffer we overwrite).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int nitems = total_items(p);
 
   if (warp >= TY) {

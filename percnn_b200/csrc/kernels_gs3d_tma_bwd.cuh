@@ -148,6 +148,8 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
   }
   for (int i = threadIdx.x; i < TY * 2; i += BWD_THREADS) wacc[i] = 0.0;
   __syncthreads();
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // see the forward kernel
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int nitems = total_items(p);
 
   if (warp >= BWD_WARPS) {

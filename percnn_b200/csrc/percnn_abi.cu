@@ -62,6 +62,7 @@ struct percnn_plan {
   int64_t launches = 0;
   bool use_tma = false;
   int ty = 16, tz = 0;
+  bool pdl = true;   // programmatic dependent launch between consecutive step kernels (PERCNN_NO_PDL=1 disables)
   int tz_override = 0, grid_override = 0;   // experiment knobs (PERCNN_TMA_TY / _TZ / _GRID environment variables)
   PrepBlock* d_prep = nullptr;
   float* d_k5w = nullptr;
@@ -174,6 +175,23 @@ int get_maps(percnn_plan* p, const void* src, const CUtensorMap** main_map, cons
   return PERCNN_OK;
 }
 
+// Launch with programmatic stream serialization allowed (the kernels call griddepcontrol.wait themselves).
+template <typename... KArgs>
+cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, bool pdl, KArgs... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 struct SlabLink {   // mirrors percnn_slab_link_t
   float* peer_lo_dst = nullptr;
   float* peer_hi_dst = nullptr;
@@ -241,19 +259,21 @@ int launch_tma_fwd(percnn_plan* p, const float* src, float* dst, int z_lo, int z
   for (int s = 0; s < prm.nseg; ++s) nitems += prm.nxt * prm.nyt * prm.seg_nzc[s];
   int grid = nitems < p->sm_count ? nitems : p->sm_count;
   if (p->grid_override > 0 && p->grid_override < grid) grid = p->grid_override;
+  cudaError_t le = cudaSuccess;
   switch (p->slot) {
 #define PERCNN_TMA_CASE(S) \
   case S:                                                                                                   \
     if (bwd) {                                                                                              \
-      if (prm.fused) tma3d::k_gs3d_bwd_tma<S, true><<<grid, tma3d::BWD_THREADS, tma3d::SMEM_BYTES_BWD, st>>>(*mm, *hm, prm, *bwd); \
-      else tma3d::k_gs3d_bwd_tma<S, false><<<grid, tma3d::BWD_THREADS, tma3d::SMEM_BYTES_BWD, st>>>(*mm, *hm, prm, *bwd);   \
-    } else if (prm.fused) tma3d::k_gs3d_fwd_tma<S, true><<<grid, tma3d::THREADS, tma3d::SMEM_BYTES, st>>>(*mm, *hm, prm); \
-    else tma3d::k_gs3d_fwd_tma<S, false><<<grid, tma3d::THREADS, tma3d::SMEM_BYTES, st>>>(*mm, *hm, prm);   \
+      if (prm.fused) le = launch_pdl(tma3d::k_gs3d_bwd_tma<S, true>, grid, tma3d::BWD_THREADS, tma3d::SMEM_BYTES_BWD, st, p->pdl, *mm, *hm, prm, *bwd); \
+      else le = launch_pdl(tma3d::k_gs3d_bwd_tma<S, false>, grid, tma3d::BWD_THREADS, tma3d::SMEM_BYTES_BWD, st, p->pdl, *mm, *hm, prm, *bwd); \
+    } else if (prm.fused) le = launch_pdl(tma3d::k_gs3d_fwd_tma<S, true>, grid, tma3d::THREADS, tma3d::SMEM_BYTES, st, p->pdl, *mm, *hm, prm); \
+    else le = launch_pdl(tma3d::k_gs3d_fwd_tma<S, false>, grid, tma3d::THREADS, tma3d::SMEM_BYTES, st, p->pdl, *mm, *hm, prm); \
     break;
     PERCNN_TMA_CASE(0) PERCNN_TMA_CASE(1) PERCNN_TMA_CASE(2) PERCNN_TMA_CASE(3) PERCNN_TMA_CASE(4) PERCNN_TMA_CASE(5)
 #undef PERCNN_TMA_CASE
     default: return fail(PERCNN_ERR_INVALID, "bad parameter slot");
   }
+  if (le != cudaSuccess) return fail(PERCNN_ERR_CUDA, std::string("TMA kernel launch: ") + cudaGetErrorString(le));
   PERCNN_CUDA(cudaGetLastError());
   p->launches++;
   return PERCNN_OK;
@@ -498,6 +518,7 @@ int percnn_plan_create(const percnn_desc_t* d, percnn_plan_t** out) {
       const TmaTiling til = choose_tiling(g.W / tma3d::TX, g.H, g.D, p->sm_count, fixed_ty);
       p->ty = til.ty;
       p->tz = til.tz;
+      if (const char* e = getenv("PERCNN_NO_PDL")) p->pdl = atoi(e) == 0;
       if (const char* e = getenv("PERCNN_TMA_TZ")) p->tz_override = atoi(e);
       if (const char* e = getenv("PERCNN_TMA_GRID")) p->grid_override = atoi(e);
     }
