@@ -66,6 +66,7 @@ struct Params {
   uint32_t* post_hi_flag;    // upper neighbour's flags[0]
   uint32_t* scratch;         // [0] CTA arrival counter, [1] error word (spin deadline exceeded)
   uint32_t epoch_wait, epoch_post;
+  int debug;                 // bisecting aid: 1 = no mirror stores, 2 = no flag wait, 4 = no flag post
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -78,6 +79,16 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Release a ring stage only after the shared-memory loads of it have COMPLETED.  `last_loaded` must come from the
+// last LDS issued on that stage: the arrive's address is made data-dependent on it (x * 0 cannot be folded for
+// IEEE floats), and a warp issues in order, so the arrive cannot be issued while the load is still queued.
+// Without this a load stuck behind peer (NVLink) stores in the LSU was overtaken by the arrive, the producer
+// refilled the stage and the load returned the NEXT plane (found by the multi-GPU bitwise test).
+__device__ __forceinline__ void mbar_arrive_after(uint64_t* bar, float last_loaded) {
+  uint32_t z;
+  asm volatile("{\n\t.reg .f32 t;\n\tmul.rn.f32 t, %1, 0f00000000;\n\tcvt.rzi.u32.f32 %0, t;\n\t}" : "=r"(z) : "f"(last_loaded));
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar) + z) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -250,7 +261,7 @@ __device__ __forceinline__ void warm_plane(Consumer& c, bool release_now, float4
   wv[(R + 4) % 5] = lds128(st + ROWS * TX);
   if (release_now) {
     __syncwarp();
-    if (c.lane == 0) mbar_arrive(&c.empty[c.s]);
+    if (c.lane == 0) mbar_arrive_after(&c.empty[c.s], wv[(R + 4) % 5].w);
   }
   advance_stage(c);
 }
@@ -271,7 +282,7 @@ __device__ __forceinline__ void steady_plane(Consumer& c, bool drain, bool prefe
   }
   if (drain) {  // planes past the chunk end are z-neighbours only
     __syncwarp();
-    if (c.lane == 0) mbar_arrive(&c.empty[c.s]);
+    if (c.lane == 0) mbar_arrive_after(&c.empty[c.s], wv[(R + 4) % 5].w);
   }
   const float2 seam_u = seam_next[0], seam_v = seam_next[1];
   if (prefetch_seam) {
@@ -301,9 +312,9 @@ __device__ __forceinline__ void steady_plane(Consumer& c, bool drain, bool prefe
     if (c.lane == 31) { Rx = seam_v.x; Ry = seam_v.y; }
     lap_quad(P, wl_v, y, Lz, Lw, Rx, Ry, Lv_lo, Lv_hi);
   }
-  // the y-neighbour rows of plane k-2 are no longer needed
+  // the y-neighbour rows of plane k-2 are no longer needed (both Laplacians depend on every row load)
   __syncwarp();
-  if (c.lane == 0) mbar_arrive(&c.empty[s2]);
+  if (c.lane == 0) mbar_arrive_after(&c.empty[s2], Lu_lo.x + Lv_lo.x);
   const float au = P[P_ALPHA + 0], av = P[P_ALPHA + 1], dt = P[P_DT];
   const float2 ou_lo = fma2(fma2(Lu_lo, au, cubic2(P + P_POLY, lo(cu), lo(cv))), dt, lo(cu));
   const float2 ou_hi = fma2(fma2(Lu_hi, au, cubic2(P + P_POLY, hi(cu), hi(cv))), dt, hi(cu));
@@ -355,7 +366,7 @@ k_gs3d_fwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
       uint32_t it = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const ItemCoord ic = decode_item(p, item);
-        if (FUSED && ic.seg < 2) {
+        if (FUSED && ic.seg < 2 && !(p.debug & 2)) {
           // the ghost planes this item reads are written by a neighbour GPU: wait for its flag, then order
           // the TMA (async proxy) reads after the acquire
           wait_flag(p.my_flags + ic.seg, p.epoch_wait, p.scratch + 1);
@@ -410,6 +421,10 @@ k_gs3d_fwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
   // Tell the neighbours that every boundary plane of this step has landed in their ghost planes: the consumer
   // warps of this CTA meet, one thread publishes (release, system scope); the last CTA raises the flags.
   auto post_boundary_done = [&]() {
+    // Every storing warp fences at system scope itself: its peer (NVLink) stores must be performed before the
+    // flag can be observed.  Relying on one thread's fence after the CTA barrier to cover the other warps'
+    // in-flight peer stores produced stale ghost planes on a neighbour (caught by the 2-GPU bitwise test).
+    __threadfence_system();
     asm volatile("bar.sync 1, %0;" ::"r"(p.ty * 32) : "memory");
     if (warp == 0 && lane == 0) {
       __threadfence_system();
@@ -425,11 +440,11 @@ k_gs3d_fwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
     const ItemCoord ic = decode_item(p, item);
     if (FUSED && !posted && ic.seg == 2) {
-      post_boundary_done();
+      if (!(p.debug & 4)) post_boundary_done();
       posted = true;
     }
     float* mirror = nullptr;
-    if (FUSED && ic.seg < 2) {
+    if (FUSED && ic.seg < 2 && !(p.debug & 1)) {
       float* base = ic.seg == 0 ? p.peer_lo_dst : p.peer_hi_dst;
       const int mz = ic.seg == 0 ? p.D + 2 + ic.z0 : ic.z0 - (p.D - 2);
       mirror = base + (int64_t(mz) * p.H + ic.y0) * p.W + ic.x0 + c.toff;
@@ -476,7 +491,7 @@ k_gs3d_fwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
     if (k < nk) PERCNN_STEADY(3)
 #undef PERCNN_STEADY
   }
-  if (FUSED && !posted) post_boundary_done();
+  if (FUSED && !posted && !(p.debug & 4)) post_boundary_done();
 }
 
 }  // namespace tma3d

@@ -91,9 +91,9 @@ __device__ __forceinline__ void adjoint_plane(Consumer& c, const float* __restri
       Gv = ctr;
     }
   }
-  // plane k-4 is no longer needed by this warp
+  // plane k-4 is no longer needed by this warp (release only once the loads have completed, see mbar_arrive_after)
   __syncwarp();
-  if (c.lane == 0) mbar_arrive(&c.empty[(c.s + STAGES - 4) & (STAGES - 1)]);
+  if (c.lane == 0) mbar_arrive_after(&c.empty[(c.s + STAGES - 4) & (STAGES - 1)], Lu_lo.x + Lv_lo.x);
   float4 au4 = make_float4(0.f, 0.f, 0.f, 0.f), av4 = au4;
   if (gadd != nullptr) {
     au4 = ldg128(gadd + off);
@@ -224,6 +224,10 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
   };
   bool posted = !FUSED;
   auto post_boundary_done = [&]() {
+    // Every storing warp fences at system scope itself: its peer (NVLink) stores must be performed before the
+    // flag can be observed.  Relying on one thread's fence after the CTA barrier to cover the other warps'
+    // in-flight peer stores produced stale ghost planes on a neighbour (caught by the 2-GPU bitwise test).
+    __threadfence_system();
     asm volatile("bar.sync 1, %0;" ::"r"(p.ty * 32) : "memory");
     if (warp == 0 && lane == 0) {
       __threadfence_system();
@@ -281,7 +285,8 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
       }
       advance_stage(c);
     }
-    // the last four planes of the item are still held: hand their stages back
+    // the last four planes of the item are still held: hand their stages back (their loads fed the outputs that
+    // were already stored, so they have completed)
     __syncwarp();
     if (lane == 0) {
 #pragma unroll

@@ -62,6 +62,7 @@ struct percnn_plan {
   int64_t launches = 0;
   bool use_tma = false;
   int ty = 16, tz = 0;
+  bool debug_split = false;   // PERCNN_TMA_SPLIT=1
   bool pdl = true;   // programmatic dependent launch between consecutive step kernels (PERCNN_NO_PDL=1 disables)
   int tz_override = 0, grid_override = 0;   // experiment knobs (PERCNN_TMA_TY / _TZ / _GRID environment variables)
   PrepBlock* d_prep = nullptr;
@@ -251,6 +252,11 @@ int launch_tma_fwd(percnn_plan* p, const float* src, float* dst, int z_lo, int z
     prm.scratch = link->scratch;
     prm.epoch_wait = link->epoch_wait;
     prm.epoch_post = link->epoch_post;
+    if (const char* e = getenv("PERCNN_FUSED_DEBUG")) prm.debug = atoi(e);
+  } else if (p->debug_split && z_lo == 0 && z_hi == g.D && g.D >= 5) {
+    add_segment(0, 2);            // debugging aid: the fused step's three-segment schedule without any flags
+    add_segment(g.D - 2, g.D);
+    add_segment(2, g.D - 2);
   } else {
     add_segment(z_lo, z_hi);
   }
@@ -519,6 +525,7 @@ int percnn_plan_create(const percnn_desc_t* d, percnn_plan_t** out) {
       p->ty = til.ty;
       p->tz = til.tz;
       if (const char* e = getenv("PERCNN_NO_PDL")) p->pdl = atoi(e) == 0;
+      if (const char* e = getenv("PERCNN_TMA_SPLIT")) p->debug_split = atoi(e) != 0;
       if (const char* e = getenv("PERCNN_TMA_TZ")) p->tz_override = atoi(e);
       if (const char* e = getenv("PERCNN_TMA_GRID")) p->grid_override = atoi(e);
     }

@@ -21,6 +21,7 @@ ap.add_argument("--shape", type=int, nargs=3, default=[64, 64, 128])
 ap.add_argument("--steps", type=int, default=7)
 ap.add_argument("--transport", default="nccl")
 ap.add_argument("--time-steps", type=int, default=0)
+ap.add_argument("--repeat", type=int, default=1)
 a = ap.parse_args()
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 dev = torch.device("cuda", lr)
@@ -32,18 +33,28 @@ cell.load_state_dict(load_gs3d_weights())
 cell = cell.to(dev)
 slab = halo.SlabRollout(cell, shape, dev, rank, world, transport=a.transport)
 full = synthetic_state(shape, 0, shape[0], dev, torch.float32, seed=3)       # every rank builds the same global field
-slab.set_state(full[:, slab.z0:slab.z0 + slab.nz])
-slab.run(a.steps)
-torch.cuda.synchronize()
 with torch.no_grad():
     ref = cell.rollout(full[None], a.steps)[-1]
-mine = slab.interior()
-ok = torch.equal(mine, ref[:, slab.z0:slab.z0 + slab.nz])
-err = float((mine - ref[:, slab.z0:slab.z0 + slab.nz]).abs().max())
+ok, err = True, 0.0
+for rep in range(a.repeat):
+    slab.set_state(full[:, slab.z0:slab.z0 + slab.nz])
+    slab.run(a.steps)
+    torch.cuda.synchronize()
+    mine = slab.interior()
+    ok = ok and torch.equal(mine, ref[:, slab.z0:slab.z0 + slab.nz]) and slab.error_word() == 0
+    err = max(err, float((mine - ref[:, slab.z0:slab.z0 + slab.nz]).abs().max()))
+    bad = (mine != ref[:, slab.z0:slab.z0 + slab.nz])
+    if bool(bad.any()):
+        zs = bad.any(dim=0).flatten(1).any(dim=1).nonzero().flatten().tolist()
+        ys = bad.any(dim=0).any(dim=0).any(dim=1).nonzero().flatten().tolist()
+        xs = bad.any(dim=0).any(dim=0).any(dim=0).nonzero().flatten().tolist()
+        fs = bad.flatten(1).any(dim=1).nonzero().flatten().tolist()
+        print(f"MISMATCH rank={rank} rep={rep} cells={int(bad.sum())} fields={fs} local_planes={zs[:12]}{'...' if len(zs) > 12 else ''} "
+              f"rows={ys[:10]}..{ys[-2:]} cols={xs[:6]}..{xs[-3:]} ncols={len(xs)} err_word={slab.error_word()}", flush=True)
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print(f"SLAB_CHECK transport={a.transport} world={world} shape={shape} steps={a.steps} bitwise_equal={bool(flag.item())} max_abs_err_rank0={err:.3e}", flush=True)
+    print(f"SLAB_CHECK transport={a.transport} world={world} shape={shape} steps={a.steps} repeats={a.repeat} bitwise_equal={bool(flag.item())} max_abs_err_rank0={err:.3e}", flush=True)
 if a.time_steps:
     slab.run(20)
     torch.cuda.synchronize(); dist.barrier()

@@ -31,6 +31,15 @@ def test_slab_forward_is_bitwise_equal_to_single_gpu(transport):
 
 
 @needs2
+def test_fused_halo_stress_full_width_planes():
+    """Regression for the stage-release race: with 512^2 planes (all 148 CTAs busy, peer stores back-pressuring
+    the LSU) an mbarrier arrive used to overtake a queued shared-memory load; ~1 rollout in 40 was off by 1e-5."""
+    rc, out = _torchrun("check_slab.py", ["--shape", "128", "512", "512", "--steps", "2", "--repeat", "60",
+                                          "--transport", "fused"], 29613, timeout=600)
+    assert "bitwise_equal=True" in out, out[-2000:]
+
+
+@needs2
 def test_slab_training_step_matches_single_gpu_autograd():
     rc, out = _torchrun("check_slab_bwd.py", ["--shape", "64", "48", "128", "--steps", "6"], 29612)
     assert "ok=True" in out, out[-2000:]
