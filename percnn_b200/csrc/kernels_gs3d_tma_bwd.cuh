@@ -22,12 +22,12 @@ constexpr int BWD_FLUSH = 32;
 // warp = 512 threads = 128 registers per thread (a 17th warp would round the allocation down to 96).
 constexpr int BWD_WARPS = 15;
 constexpr int BWD_THREADS = (BWD_WARPS + 1) * 32;
-constexpr int SMEM_BYTES_BWD = SMEM_BYTES + 16 * 2 * 8 + 64;
+constexpr int SMEM_BYTES_BWD = SMEM_BYTES + 16 * kRedPiK1 * 8 + 64 + 10 * BWD_THREADS * 8;
 
 struct BwdExtra {
   const float* h;        // stored state of this step, same layout as the G buffers
   const float* gadd;     // injected gradient for this step (nullable)
-  double* partials;      // [gridDim.x][2]
+  double* partials;      // [gridDim.x][2 or 22]
   unsigned* counter;
   double* acc;           // [22] running sums over steps ([0..1] from this kernel, [2..21] from k_monomial_sums)
 };
@@ -44,12 +44,12 @@ __device__ __forceinline__ float4 ldg128(const float* p) { return __ldg(reinterp
 // state, the injected gradient and the pointwise Jacobian -- the windowed version spilled.
 // `valid`: this warp's row is not a duplicate of the previous tile's rows (last tile of a column is shifted
 // back), so it contributes to the reductions.
-template <bool FUSED>
+template <bool FUSED, bool MONO>
 __device__ __forceinline__ void adjoint_plane(Consumer& c, const float* __restrict__ TP, bool prefetch_seam,
                                               const float* seam_ptr, int64_t field, int64_t plane, int64_t off,
                                               float* __restrict__ dst, float* mirror, const float* __restrict__ hbase,
                                               const float* __restrict__ gadd, bool prefetch_next, bool valid,
-                                              float2 (&seam_next)[2], float (&aacc)[2]) {
+                                              float2 (&seam_next)[2], float (&aacc)[2], float2* __restrict__ macc) {
   const float* P = c.P;
   mbar_wait(&c.full[c.s], c.parity);   // plane k has landed; planes k-4 .. k-1 are still resident
   const float2 seam_u = seam_next[0], seam_v = seam_next[1];
@@ -121,6 +121,40 @@ __device__ __forceinline__ void adjoint_plane(Consumer& c, const float* __restri
   PERCNN_BWD_PAIR(lo(hu), lo(hv), lo(Gu), lo(Gv), Lu_lo, Lv_lo, ou.x, ou.y, ov.x, ov.y, au4.x, au4.y, av4.x, av4.y)
   PERCNN_BWD_PAIR(hi(hu), hi(hv), hi(Gu), hi(Gv), Lu_hi, Lv_hi, ou.z, ou.w, ov.z, ov.w, au4.z, au4.w, av4.z, av4.w)
 #undef PERCNN_BWD_PAIR
+  if (MONO && valid) {
+    // 20 monomial sums  sum G_f u^a v^b  for this lane's 4 cells, added to per-lane accumulators in shared memory
+    // (keeping them in registers next to the stencil state spilled); (G_u, G_v) is the packed FFMA2 operand.
+    const float us[4] = {hu.x, hu.y, hu.z, hu.w}, vs[4] = {hv.x, hv.y, hv.z, hv.w};
+    const float2 g[4] = {make_float2(Gu.x, Gv.x), make_float2(Gu.y, Gv.y), make_float2(Gu.z, Gv.z), make_float2(Gu.w, Gv.w)};
+    float uu[4], uv[4], vv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uu[j] = us[j] * us[j];
+      uv[j] = us[j] * vs[j];
+      vv[j] = vs[j] * vs[j];
+    }
+#define PERCNN_MONO(M, E0, E1, E2, E3)                                                              \
+  {                                                                                                 \
+    float2 t = macc[M * BWD_THREADS];                                                               \
+    t = fma2(g[0], E0, t); t = fma2(g[1], E1, t); t = fma2(g[2], E2, t); t = fma2(g[3], E3, t);     \
+    macc[M * BWD_THREADS] = t;                                                                      \
+  }
+    {
+      float2 t = macc[0];
+      t = __fadd2_rn(t, __fadd2_rn(__fadd2_rn(g[0], g[1]), __fadd2_rn(g[2], g[3])));
+      macc[0] = t;
+    }
+    PERCNN_MONO(1, us[0], us[1], us[2], us[3])
+    PERCNN_MONO(2, vs[0], vs[1], vs[2], vs[3])
+    PERCNN_MONO(3, uu[0], uu[1], uu[2], uu[3])
+    PERCNN_MONO(4, uv[0], uv[1], uv[2], uv[3])
+    PERCNN_MONO(5, vv[0], vv[1], vv[2], vv[3])
+    PERCNN_MONO(6, uu[0] * us[0], uu[1] * us[1], uu[2] * us[2], uu[3] * us[3])
+    PERCNN_MONO(7, uu[0] * vs[0], uu[1] * vs[1], uu[2] * vs[2], uu[3] * vs[3])
+    PERCNN_MONO(8, us[0] * vv[0], us[1] * vv[1], us[2] * vv[2], us[3] * vv[3])
+    PERCNN_MONO(9, vv[0] * vs[0], vv[1] * vs[1], vv[2] * vs[2], vv[3] * vs[3])
+#undef PERCNN_MONO
+  }
   *reinterpret_cast<float4*>(dst + off) = ou;
   *reinterpret_cast<float4*>(dst + off + field) = ov;
   if (FUSED && mirror != nullptr) {
@@ -129,7 +163,7 @@ __device__ __forceinline__ void adjoint_plane(Consumer& c, const float* __restri
   }
 }
 
-template <int SLOT, bool FUSED>
+template <int SLOT, bool FUSED, bool MONO>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_halo,
                const __grid_constant__ Params p, const __grid_constant__ BwdExtra x) {
@@ -146,7 +180,10 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < TY * 2; i += BWD_THREADS) wacc[i] = 0.0;
+  float2* macc_all = reinterpret_cast<float2*>(wacc + 16 * kRedPiK1);   // [10][BWD_THREADS] per-lane monomial sums
+  for (int i = threadIdx.x; i < TY * kRedPiK1; i += BWD_THREADS) wacc[i] = 0.0;
+  if (MONO)
+    for (int m = 0; m < 10; ++m) macc_all[m * BWD_THREADS + threadIdx.x] = make_float2(0.f, 0.f);
   __syncthreads();
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // see the forward kernel
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -211,14 +248,31 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
   float2 seam_next[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
   float aacc[2] = {0.f, 0.f};
   int since_flush = 0;
-  auto flush = [&]() {
+  float2* macc = macc_all + threadIdx.x;
+  auto flush = [&]() {   // per-lane fp32 partial sums -> per-warp fp64 accumulators (every BWD_FLUSH planes)
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       float t = aacc[i];
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) t += __shfl_down_sync(0xffffffffu, t, off);
-      if (lane == 0) wacc[warp * 2 + i] += double(t);
+      if (lane == 0) wacc[warp * kRedPiK1 + i] += double(t);
       aacc[i] = 0.f;
+    }
+    if (MONO) {
+      const float dt = c.P[P_DT];
+      for (int m = 0; m < 10; ++m) {
+        float2 t = macc[m * BWD_THREADS];
+        macc[m * BWD_THREADS] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          t.x += __shfl_down_sync(0xffffffffu, t.x, off);
+          t.y += __shfl_down_sync(0xffffffffu, t.y, off);
+        }
+        if (lane == 0) {
+          wacc[warp * kRedPiK1 + 2 + m] += double(dt) * double(t.x);
+          wacc[warp * kRedPiK1 + 12 + m] += double(dt) * double(t.y);
+        }
+      }
     }
     since_flush = 0;
   };
@@ -277,8 +331,8 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
           pz -= p.D;
           seam_ptr -= wrap_back;
         }
-        adjoint_plane<FUSED>(c, TP, k <= ic.nz + 2, seam_ptr, field, plane, off, p.dst, mirror, x.h, x.gadd, k + 1 < nk,
-                             valid, seam_next, aacc);
+        adjoint_plane<FUSED, MONO>(c, TP, k <= ic.nz + 2, seam_ptr, field, plane, off, p.dst, mirror, x.h, x.gadd,
+                                   k + 1 < nk, valid, seam_next, aacc, macc);
         off += plane;
         if (FUSED && mirror != nullptr) mirror += plane;
         if (++since_flush >= BWD_FLUSH) flush();
@@ -298,11 +352,12 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
   // ---- CTA result -> global partials; last CTA folds all CTAs in fixed order ----
   asm volatile("bar.sync 2, %0;" ::"r"(p.ty * 32) : "memory");
   __shared__ bool s_last;
+  constexpr int NR = MONO ? kRedPiK1 : 2;
   if (warp == 0) {
-    if (lane < 2) {
+    if (lane < NR) {
       double s = 0;
-      for (int w = 0; w < p.ty; ++w) s += wacc[w * 2 + lane];
-      x.partials[size_t(blockIdx.x) * 2 + lane] = s;
+      for (int w = 0; w < p.ty; ++w) s += wacc[w * kRedPiK1 + lane];
+      x.partials[size_t(blockIdx.x) * NR + lane] = s;
     }
     __threadfence();
     __syncwarp();
@@ -310,10 +365,15 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
     __syncwarp();
     if (s_last) {
       __threadfence();
-      if (lane < 2) {
-        double s = 0;
-        for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(x.partials + size_t(b) * 2 + lane);
-        x.acc[lane] += s;
+      if (lane < NR) {
+        double s0 = 0, s1 = 0;   // two chains keep the loads in flight; fixed order
+        unsigned b = 0;
+        for (; b + 2 <= gridDim.x; b += 2) {
+          s0 += __ldcg(x.partials + size_t(b) * NR + lane);
+          s1 += __ldcg(x.partials + size_t(b + 1) * NR + lane);
+        }
+        if (b < gridDim.x) s0 += __ldcg(x.partials + size_t(b) * NR + lane);
+        x.acc[lane] += s0 + s1;
       }
       if (lane == 0) *x.counter = 0;
     }

@@ -63,6 +63,7 @@ struct percnn_plan {
   bool use_tma = false;
   int ty = 16, tz = 0;
   bool debug_split = false;   // PERCNN_TMA_SPLIT=1
+  bool bwd_split_mono = false;   // PERCNN_BWD_SPLIT_MONO=1: monomial sums in their own streaming kernel
   bool pdl = true;   // programmatic dependent launch between consecutive step kernels (PERCNN_NO_PDL=1 disables)
   int tz_override = 0, grid_override = 0;   // experiment knobs (PERCNN_TMA_TY / _TZ / _GRID environment variables)
   PrepBlock* d_prep = nullptr;
@@ -270,8 +271,13 @@ int launch_tma_fwd(percnn_plan* p, const float* src, float* dst, int z_lo, int z
 #define PERCNN_TMA_CASE(S) \
   case S:                                                                                                   \
     if (bwd) {                                                                                              \
-      if (prm.fused) le = launch_pdl(tma3d::k_gs3d_bwd_tma<S, true>, grid, tma3d::BWD_THREADS, tma3d::SMEM_BYTES_BWD, st, p->pdl, *mm, *hm, prm, *bwd); \
-      else le = launch_pdl(tma3d::k_gs3d_bwd_tma<S, false>, grid, tma3d::BWD_THREADS, tma3d::SMEM_BYTES_BWD, st, p->pdl, *mm, *hm, prm, *bwd); \
+      if (p->bwd_split_mono) {                                                                              \
+        if (prm.fused) le = launch_pdl(tma3d::k_gs3d_bwd_tma<S, true, false>, grid, tma3d::BWD_THREADS, tma3d::SMEM_BYTES_BWD, st, p->pdl, *mm, *hm, prm, *bwd); \
+        else le = launch_pdl(tma3d::k_gs3d_bwd_tma<S, false, false>, grid, tma3d::BWD_THREADS, tma3d::SMEM_BYTES_BWD, st, p->pdl, *mm, *hm, prm, *bwd); \
+      } else {                                                                                              \
+        if (prm.fused) le = launch_pdl(tma3d::k_gs3d_bwd_tma<S, true, true>, grid, tma3d::BWD_THREADS, tma3d::SMEM_BYTES_BWD, st, p->pdl, *mm, *hm, prm, *bwd); \
+        else le = launch_pdl(tma3d::k_gs3d_bwd_tma<S, false, true>, grid, tma3d::BWD_THREADS, tma3d::SMEM_BYTES_BWD, st, p->pdl, *mm, *hm, prm, *bwd); \
+      }                                                                                                     \
     } else if (prm.fused) le = launch_pdl(tma3d::k_gs3d_fwd_tma<S, true>, grid, tma3d::THREADS, tma3d::SMEM_BYTES, st, p->pdl, *mm, *hm, prm); \
     else le = launch_pdl(tma3d::k_gs3d_fwd_tma<S, false>, grid, tma3d::THREADS, tma3d::SMEM_BYTES, st, p->pdl, *mm, *hm, prm); \
     break;
@@ -362,7 +368,7 @@ int step_bwd_any(percnn_plan* p, const void* h, const void* gout, const void* ga
     x.partials = reinterpret_cast<double*>(w + kWsPartials);
     x.counter = reinterpret_cast<unsigned*>(w + kWsCounter);
     x.acc = reinterpret_cast<double*>(w + kWsAcc);
-    {  // the 20 stencil-free monomial sums: a streaming pass over the interior of h and G
+    if (p->bwd_split_mono) {  // the 20 stencil-free monomial sums as a separate streaming pass over h and G
       const Geom& g = p->g;
       const int64_t n4 = int64_t(g.D) * g.plane / 4;
       int64_t blocks = (n4 + 255) / 256;
@@ -510,9 +516,13 @@ int percnn_plan_create(const percnn_desc_t* d, percnn_plan_t** out) {
     if (ae == cudaSuccess)                                                                                               \
       ae = cudaFuncSetAttribute(tma3d::k_gs3d_fwd_tma<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma3d::SMEM_BYTES); \
     if (ae == cudaSuccess)                                                                                               \
-      ae = cudaFuncSetAttribute(tma3d::k_gs3d_bwd_tma<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma3d::SMEM_BYTES_BWD); \
+      ae = cudaFuncSetAttribute(tma3d::k_gs3d_bwd_tma<S, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma3d::SMEM_BYTES_BWD); \
     if (ae == cudaSuccess)                                                                                               \
-      ae = cudaFuncSetAttribute(tma3d::k_gs3d_bwd_tma<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma3d::SMEM_BYTES_BWD); \
+      ae = cudaFuncSetAttribute(tma3d::k_gs3d_bwd_tma<S, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma3d::SMEM_BYTES_BWD); \
+    if (ae == cudaSuccess)                                                                                               \
+      ae = cudaFuncSetAttribute(tma3d::k_gs3d_bwd_tma<S, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma3d::SMEM_BYTES_BWD); \
+    if (ae == cudaSuccess)                                                                                               \
+      ae = cudaFuncSetAttribute(tma3d::k_gs3d_bwd_tma<S, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma3d::SMEM_BYTES_BWD); \
     break;
         PERCNN_TMA_ATTR(0) PERCNN_TMA_ATTR(1) PERCNN_TMA_ATTR(2) PERCNN_TMA_ATTR(3) PERCNN_TMA_ATTR(4) PERCNN_TMA_ATTR(5)
 #undef PERCNN_TMA_ATTR
@@ -526,6 +536,7 @@ int percnn_plan_create(const percnn_desc_t* d, percnn_plan_t** out) {
       p->tz = til.tz;
       if (const char* e = getenv("PERCNN_NO_PDL")) p->pdl = atoi(e) == 0;
       if (const char* e = getenv("PERCNN_TMA_SPLIT")) p->debug_split = atoi(e) != 0;
+      if (const char* e = getenv("PERCNN_BWD_SPLIT_MONO")) p->bwd_split_mono = atoi(e) != 0;
       if (const char* e = getenv("PERCNN_TMA_TZ")) p->tz_override = atoi(e);
       if (const char* e = getenv("PERCNN_TMA_GRID")) p->grid_override = atoi(e);
     }
