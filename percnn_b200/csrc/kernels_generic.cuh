@@ -238,3 +238,87 @@ __global__ void __launch_bounds__(kGenericThreads) k_lo_bwd(Geom g, int slot, co
 }
 
 }  // namespace percnn
+
+// =====================================================================================================
+// Persistent multi-step kernel for small grids.  The 2-D configs (<= 512^2) and the reference's own sizes
+// (100^2, 48^3) hold their whole state in L2 and a per-step kernel takes ~2 us, so a rollout of per-step
+// launches is bound by launch latency (~4.3 us/step measured).  Here ONE cooperative launch runs all
+// steps; blocks meet at a grid barrier (monotonic counter, release/acquire) between steps.  State loads
+// bypass L1 (ld.global.cg): the buffers are rewritten by other SMs during the kernel.
+// =====================================================================================================
+namespace percnn {
+
+template <typename T>
+struct MultiStepArgs {
+  const T* h0;      // initial state
+  T* tape;          // if non-null: step s reads tape + s*stride, writes tape + (s+1)*stride (tape[0] must hold h0)
+  T* ping;          // otherwise: ping-pong scratch ...
+  T* pong;
+  T* final_state;   // ... with the last step written here
+  int nsteps;
+  int64_t stride;   // elements between tape slots
+};
+
+template <typename T, int NDIM>
+__device__ __forceinline__ Cross<T, NDIM> gather_cg(const T* __restrict__ f, const CellOffsets<NDIM>& o) {
+  Cross<T, NDIM> q;
+  q.c = __ldcg(f + o.c);
+#pragma unroll
+  for (int a = 0; a < NDIM; ++a)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) q.n[a][k] = __ldcg(f + o.n[a][k]);
+  return q;
+}
+
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while (v < target);
+  }
+  __syncthreads();
+}
+
+// CELL: 0 = Pi-block k=1 (folded cubic), 1 = Burgers physics, 2 = lambda-omega physics
+// 512-thread blocks, at most one per SM: the barrier costs one serialized L2 atomic per block, so fewer, fatter
+// blocks are faster than the 256-thread grids of the per-step kernels (measured 2.7 -> see profiles).
+constexpr int kMultiThreads = 512;
+template <typename T, int NDIM, int CELL>
+__global__ void __launch_bounds__(kMultiThreads) k_multi_step(Geom g, int slot, MultiStepArgs<T> m, unsigned* counter) {
+  const T* P = PrepView<T>::get(c_prep[slot]);
+  const int64_t ncell = int64_t(g.D) * g.H * g.W;
+  for (int s = 0; s < m.nsteps; ++s) {
+    const T* src;
+    T* dst;
+    if (m.tape != nullptr) {
+      src = m.tape + int64_t(s) * m.stride;
+      dst = m.tape + int64_t(s + 1) * m.stride;
+    } else {
+      src = s == 0 ? m.h0 : ((s & 1) ? m.ping : m.pong);
+      dst = s == m.nsteps - 1 ? m.final_state : ((s & 1) ? m.pong : m.ping);
+    }
+    for (int64_t cell = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; cell < ncell;
+         cell += int64_t(gridDim.x) * blockDim.x) {
+      const CellOffsets<NDIM> o = cell_offsets<NDIM>(g, cell);
+      const Cross<T, NDIM> U = gather_cg<T, NDIM>(src, o);
+      const Cross<T, NDIM> V = gather_cg<T, NDIM>(src + g.field, o);
+      T ou, ov;
+      if (CELL == 0) {
+        pi_k1_fwd_poly<T>(U.c, V.c, lap_apply<T, NDIM>(U, P), lap_apply<T, NDIM>(V, P), P, ou, ov);
+      } else if (CELL == 1) {
+        if constexpr (NDIM == 2) burgers_fwd<T>(U, V, P, ou, ov);
+      } else {
+        lo_fwd<T>(U.c, V.c, lap_apply<T, NDIM>(U, P), lap_apply<T, NDIM>(V, P), P, ou, ov);
+      }
+      dst[o.c] = ou;
+      dst[g.field + o.c] = ov;
+    }
+    if (s + 1 < m.nsteps) grid_barrier(counter, unsigned(s + 1) * gridDim.x);
+  }
+}
+
+}  // namespace percnn

@@ -62,6 +62,8 @@ struct percnn_plan {
   int64_t launches = 0;
   bool use_tma = false;
   int ty = 16, tz = 0;
+  unsigned* d_sync = nullptr;   // grid-barrier counter of the persistent multi-step kernel
+  int multi_grid = 0;           // co-resident grid size of that kernel (0 = not available)
   bool debug_split = false;   // PERCNN_TMA_SPLIT=1
   bool bwd_split_mono = false;   // PERCNN_BWD_SPLIT_MONO=1: monomial sums in their own streaming kernel
   bool pdl = true;   // programmatic dependent launch between consecutive step kernels (PERCNN_NO_PDL=1 disables)
@@ -320,6 +322,43 @@ int step_fwd_t(percnn_plan* p, const T* src, T* dst, cudaStream_t st) {
   return PERCNN_OK;
 }
 
+template <typename T>
+const void* multi_step_kernel(const percnn_plan* p) {
+  const int cell = p->desc.cell;
+  if (cell == PERCNN_CELL_PI)
+    return p->g.ndim == 3 ? (const void*)k_multi_step<T, 3, 0> : (const void*)k_multi_step<T, 2, 0>;
+  if (cell == PERCNN_CELL_BURGERS) return (const void*)k_multi_step<T, 2, 1>;
+  return (const void*)k_multi_step<T, 2, 2>;
+}
+bool multi_step_eligible(const percnn_plan* p) {
+  if (p->use_tma || is_k5(p) || p->desc.slab_ghost) return false;
+  if (p->desc.cell == PERCNN_CELL_PI && (p->desc.flags & PERCNN_FLAG_EVAL_BRANCH)) return false;
+  return p->multi_grid > 0 && p->d_sync != nullptr;
+}
+template <typename T>
+int launch_multi_step(percnn_plan* p, const void* h0, void* tape, void* ping, void* pong, void* final_state, int nsteps,
+                      cudaStream_t st) {
+  MultiStepArgs<T> m;
+  m.h0 = static_cast<const T*>(h0);
+  m.tape = static_cast<T*>(tape);
+  m.ping = static_cast<T*>(ping);
+  m.pong = static_cast<T*>(pong);
+  m.final_state = static_cast<T*>(final_state);
+  m.nsteps = nsteps;
+  m.stride = p->state_elems;
+  PERCNN_CUDA(cudaMemsetAsync(p->d_sync, 0, sizeof(unsigned), st));
+  Geom g = p->g;
+  int slot = p->slot;
+  unsigned* counter = p->d_sync;
+  void* args[] = {&g, &slot, &m, &counter};
+  const int64_t ncell = int64_t(g.D) * g.H * g.W;
+  int grid = int((ncell + kMultiThreads - 1) / kMultiThreads);
+  if (grid > p->multi_grid) grid = p->multi_grid;
+  PERCNN_CUDA(cudaLaunchCooperativeKernel(multi_step_kernel<T>(p), dim3(grid), dim3(kMultiThreads), args, 0, st));
+  p->launches++;
+  return PERCNN_OK;
+}
+
 int step_fwd_any(percnn_plan* p, const void* src, void* dst, cudaStream_t st) {
   if (p->use_tma) return launch_tma_fwd(p, static_cast<const float*>(src), static_cast<float*>(dst), 0, p->g.D, st);
   if (p->desc.cell == PERCNN_CELL_PI && p->desc.ksize == 5) {
@@ -497,6 +536,14 @@ int percnn_plan_create(const percnn_desc_t* d, percnn_plan_t** out) {
       if (cudaFuncSetAttribute(k5::k_pi_k5_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                int(k5::bwd_smem_floats(d->hidden, int(p->nparams)) * sizeof(float))) != cudaSuccess) { rc = fail(PERCNN_ERR_CUDA, "cudaFuncSetAttribute(k5 bwd) failed"); break; }
     }
+    if (!(d->cell == PERCNN_CELL_PI && d->ksize == 5) && !d->slab_ghost && !getenv("PERCNN_NO_MULTISTEP")) {
+      int coop = 0, per_sm = 0;
+      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, d->device);
+      const void* fn = p->elt == 4 ? multi_step_kernel<float>(p) : multi_step_kernel<double>(p);
+      if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kMultiThreads, 0) == cudaSuccess && per_sm > 0) {
+        if (cudaMalloc(&p->d_sync, 256) == cudaSuccess) p->multi_grid = p->sm_count;   // one block per SM
+      }
+    }
     p->use_tma = d->cell == PERCNN_CELL_PI && d->ksize == 1 && d->ndim == 3 && d->dtype == PERCNN_F32 &&
                  !(d->flags & (PERCNN_FLAG_NO_TMA | PERCNN_FLAG_EVAL_BRANCH)) && g.W % tma3d::TX == 0 &&
                  g.H >= 4 && g.D >= 4;
@@ -555,6 +602,7 @@ int percnn_plan_destroy(percnn_plan_t* p) {
   if (!p) return PERCNN_OK;
   if (p->d_prep) cudaFree(p->d_prep);
   if (p->d_k5w) cudaFree(p->d_k5w);
+  if (p->d_sync) cudaFree(p->d_sync);
   if (p->h_params_dev) cudaFree(p->h_params_dev);
   if (p->h_states) cudaFree(p->h_states);
   if (p->h_stream) cudaStreamDestroy(p->h_stream);
@@ -702,6 +750,11 @@ int percnn_rollout_fwd(percnn_plan_t* p, const void* h0, void* traj, const uint8
     pp[1] = pp[0] + (sb + 255) / 256 * 256;
   }
   if (tp && tp != h0) PERCNN_CUDA(cudaMemcpyAsync(tp, h0, sb, cudaMemcpyDeviceToDevice, st));
+  // small grids: one persistent cooperative launch for the whole rollout (tape mode, or final-state-only mode)
+  if (nsteps >= 2 && multi_step_eligible(p) && !traj && (tp || (h_final && pp[0]))) {
+    return p->elt == 4 ? launch_multi_step<float>(p, h0, tp, pp[0], pp[1], h_final, nsteps, st)
+                       : launch_multi_step<double>(p, h0, tp, pp[0], pp[1], h_final, nsteps, st);
+  }
   const char* cur = tp ? tp : static_cast<const char*>(h0);
   int slot = 0, flip = 0;
   for (int s = 0; s < nsteps; ++s) {
