@@ -158,6 +158,41 @@ int percnn_rollout_fwd(percnn_plan_t* plan, const void* h0, void* traj, const ui
 int percnn_rollout_bwd(percnn_plan_t* plan, const void* params, const void* tape, const void* g_tape,
                        const uint8_t* gmask, int nsteps, void* g_h0, void* param_grads, void* ws, void* stream);
 
+/* ---- fused data loss ---------------------------------------------------- */
+/* The training scripts' data loss is a strided-subsample MSE over selected states of the rollout:
+ *     mse_loss(output[:-1:15, :, ::2, ::2, ::2], truth[::15, :, ::2, ::2, ::2])          (GS3D:403)
+ *     mse_loss(output[0:-1:20, :, ::4, ::4], truth[::20, :, ::4, ::4])                   (GS2D:397-401)
+ *     mse_loss(output[0:-1:s_t, :, ::s, ::s], truth...)                                  (BUR1:610-614)
+ * Stock autograd materialises a dense [T+1, 2, ...] gradient for it.  Here the loss is one small reduction over
+ * the sampled points of the tape, and its gradient 2/N (h_s - target) is INJECTED by the adjoint kernel of step s
+ * itself (it already holds h_s in registers): no dense gradient tape, 8/s^ndim extra bytes per cell on the
+ * selected steps only. */
+typedef struct percnn_data_loss {
+  const void* target;    /* device, plan dtype: the selected states' low-res frames, packed in increasing step
+                            order, each [2][ceil(D/s)][ceil(H/s)][ceil(W/s)] (2-D: [2][ceil(H/s)][ceil(W/s)]) */
+  const uint8_t* sel;    /* host, [nsteps + 1]: sel[s] != 0 <=> state h_s enters the loss */
+  int32_t stride;        /* spatial subsampling stride s >= 1 (`::s` on every spatial axis) */
+  int32_t reserved;      /* must be 0 */
+  int64_t n_total;       /* number of elements the mean runs over; 0 = this plan's own count
+                            (nsel * 2 * prod ceil(extent/s)).  Slab ranks pass the global count. */
+  const void* gscale;    /* device scalar (plan dtype) dL/dloss for the backward pass; NULL = 1 */
+} percnn_data_loss_t;
+/* loss = sum over selected states and sampled points of (h - target)^2 / n_total, written to *loss_out (device,
+ * one plan-dtype scalar).  `tape` as written by percnn_rollout_fwd.  Uses the head of `ws`; deterministic
+ * (fixed-order fp64 partial sums). */
+int percnn_data_loss_fwd(percnn_plan_t* plan, const void* tape, int nsteps, const percnn_data_loss_t* loss,
+                         void* loss_out, void* ws, void* stream);
+/* percnn_step_bwd with the loss gradient of ONE selected state injected: g_in += gscale * 2/n_total * (h_in -
+ * target_frame) at the sampled points.  `target_frame` is that state's low-res frame (NULL = no injection);
+ * `link` (NULL = single GPU) selects the fused-halo slab step. */
+int percnn_step_bwd_loss(percnn_plan_t* plan, const void* h_in, const void* g_out, const void* g_add,
+                         const void* target_frame, int stride, int64_t n_total, const void* gscale, void* g_in,
+                         void* ws, const percnn_slab_link_t* link, void* stream);
+/* percnn_rollout_bwd with the fused data loss as an additional gradient source (`g_tape`/`gmask` may be NULL). */
+int percnn_rollout_bwd_loss(percnn_plan_t* plan, const void* params, const void* tape, const void* g_tape,
+                            const uint8_t* gmask, const percnn_data_loss_t* loss, int nsteps, void* g_h0,
+                            void* param_grads, void* ws, void* stream);
+
 /* ---- host-buffer convenience (end-to-end path) ------------------------------------------------ */
 /* Same as params_load + rollout_fwd but with HOST pointers: copies params and h0 to the device, runs the
  * rollout, copies the emitted frames (and h_final if non-NULL) back, blocks until done.  Scratch is

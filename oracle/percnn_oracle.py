@@ -465,6 +465,48 @@ def cell_step_vjp_np(h, g_out, p, variant: str):
 
 
 # --------------------------------------------------------------------------------------
+# Data loss of the training scripts and its gradient, restated in numpy
+# --------------------------------------------------------------------------------------
+
+
+def data_loss_frames(step: int, effective_step: Sequence[int], time_stride: int,
+                     first_frames: Optional[int] = None) -> List[int]:
+    """State indices that `torch.cat(outputs)[0:-1:time_stride]` picks (GS3D:394-403, GS2D:394-397).
+
+    `outputs` = [h_0] + [h_{s+1} for s in range(step) if s in effective_step] (GS3D:191-212); the slice
+    drops the last list entry (the dummy step) and keeps every time_stride-th one.  `first_frames`
+    mirrors `pred[:idx]` of GS2D:398-401 / BUR1:611-614 (training part of the selected frames)."""
+    eff = set(int(e) for e in effective_step)
+    frame_state = [0] + [s + 1 for s in range(step) if s in eff]
+    picked = [frame_state[i] for i in range(0, len(frame_state) - 1, time_stride)]
+    return picked if first_frames is None else picked[:first_frames]
+
+
+def data_loss_np(states, target, frames: Sequence[int], stride: int) -> float:
+    """nn.MSELoss()(output[frames][:, :, ::s, ::s(, ::s)], target)  (GS3D:401-403), fp64.
+
+    states: [nsteps+1, 2, ...]; target: [len(frames), 2, ceil(./s) ...]."""
+    st = np.asarray(states, dtype=np.float64)
+    nd = st.ndim - 2
+    sub = st[list(frames)][(slice(None), slice(None)) + (slice(None, None, stride),) * nd]
+    d = sub - np.asarray(target, dtype=np.float64)
+    return float(np.mean(d * d))
+
+
+def data_loss_grad_np(states, target, frames: Sequence[int], stride: int, gscale: float = 1.0) -> np.ndarray:
+    """d(gscale * data_loss)/d(states): 2/N (h - target) on the sampling lattice of the picked states, 0 elsewhere."""
+    st = np.asarray(states, dtype=np.float64)
+    nd = st.ndim - 2
+    sl = (slice(None), slice(None)) + (slice(None, None, stride),) * nd
+    sub = st[list(frames)][sl]
+    d = sub - np.asarray(target, dtype=np.float64)
+    g = np.zeros_like(st)
+    for i, f in enumerate(frames):
+        g[f][sl[1:]] = (2.0 * gscale / d.size) * d[i]
+    return g
+
+
+# --------------------------------------------------------------------------------------
 # Synthetic initial states of SURVEY 8d (seeded, periodic-safe) -- shared by tests and bench.
 # --------------------------------------------------------------------------------------
 

@@ -26,7 +26,7 @@ EXPORTS = (
     "percnn_plan_launch_count", "percnn_params_load", "percnn_step_fwd", "percnn_step_fwd_range",
     "percnn_step_fwd_fused_halo", "percnn_step_bwd_fused_halo", "percnn_step_bwd",
     "percnn_param_grads_begin", "percnn_param_grads_finish", "percnn_rollout_fwd", "percnn_rollout_bwd",
-    "percnn_rollout_fwd_host",
+    "percnn_rollout_fwd_host", "percnn_data_loss_fwd", "percnn_step_bwd_loss", "percnn_rollout_bwd_loss",
 )
 
 
@@ -44,6 +44,14 @@ class SlabLink(ctypes.Structure):
     _fields_ = [
         ("peer_lo_out", c_void_p), ("peer_hi_out", c_void_p), ("my_flags", c_void_p), ("peer_lo_flags", c_void_p),
         ("peer_hi_flags", c_void_p), ("scratch", c_void_p), ("epoch", ctypes.c_uint32),
+    ]
+
+
+class DataLoss(ctypes.Structure):
+    """percnn_data_loss_t"""
+    _fields_ = [
+        ("target", c_void_p), ("sel", POINTER(c_uint8)), ("stride", c_int32), ("reserved", c_int32),
+        ("n_total", c_int64), ("gscale", c_void_p),
     ]
 
 
@@ -89,6 +97,9 @@ def lib() -> ctypes.CDLL:
     L.percnn_rollout_fwd.argtypes = [vp, vp, vp, POINTER(c_uint8), c_int, vp, vp, vp, vp]
     L.percnn_rollout_bwd.argtypes = [vp, vp, vp, vp, POINTER(c_uint8), c_int, vp, vp, vp, vp]
     L.percnn_rollout_fwd_host.argtypes = [vp, vp, vp, vp, POINTER(c_uint8), c_int, vp]
+    L.percnn_data_loss_fwd.argtypes = [vp, vp, c_int, POINTER(DataLoss), vp, vp, vp]
+    L.percnn_step_bwd_loss.argtypes = [vp, vp, vp, vp, vp, c_int, c_int64, vp, vp, vp, POINTER(SlabLink), vp]
+    L.percnn_rollout_bwd_loss.argtypes = [vp, vp, vp, vp, POINTER(c_uint8), POINTER(DataLoss), c_int, vp, vp, vp, vp]
     if L.percnn_abi_version() != ABI_VERSION:
         raise ImportError(f"{LIB_PATH}: ABI version {L.percnn_abi_version()} != {ABI_VERSION}; rebuild the library")
     _lib = L

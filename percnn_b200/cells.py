@@ -80,6 +80,15 @@ class _FusedCell(nn.Module):
         plan = self._plan(h0)
         return engine.rollout_states(plan, int(nsteps), h0[0], self._packed_tensors())
 
+    def rollout_data_loss(self, h0: torch.Tensor, nsteps: int, target: torch.Tensor, sel: Sequence[bool], stride: int):
+        """(states, loss): the rollout plus the fused strided-subsample MSE over the states with sel[s] set,
+        `mse_loss(states[sel][:, :, ::stride, ::stride(, ::stride)], target)` -- the data loss of the training
+        scripts (GS3D:403, GS2D:397-401, BUR1:610-614).  Its gradient is injected inside the adjoint kernels, so
+        backward needs no dense gradient of `states`."""
+        plan = self._plan(h0)
+        spec = engine.DataLossSpec(sel=tuple(bool(e) for e in sel), stride=int(stride))
+        return engine.rollout_states_with_data_loss(plan, int(nsteps), h0[0], self._packed_tensors(), spec, target)
+
     def rollout_emit(self, h0: torch.Tensor, nsteps: int, emit: Sequence[bool], want_final: bool = False):
         plan = self._plan(h0)
         return engine.rollout_emit(plan, int(nsteps), h0[0], self._packed_tensors(), emit, want_final)
@@ -230,3 +239,26 @@ class FusedRCNN(nn.Module):
                         second_last_state = traj[slot:slot + 1].clone()
                     slot += 1
         return outputs, second_last_state
+
+    def forward_data_loss(self, truth_sub: torch.Tensor, time_stride: int, space_stride: int):
+        """`forward()` plus the scripts' data loss in one pass: returns (outputs, second_last_state, loss_data) with
+
+            loss_data == mse_loss(torch.cat(outputs)[0:-1:time_stride, :, ::space_stride, ...], truth_sub)
+
+        (GS3D:394-403, GS2D:394-401, BUR1:606-614).  The selection of frames follows the reference exactly
+        (list index -> state index through `effective_step`); the loss and its gradient are computed by the fused
+        kernels (`percnn_data_loss_fwd`, injection inside the adjoint), not by slicing a dense trajectory."""
+        self.init_state = self._initial_state()
+        cell: _FusedCell = getattr(self, self.cell_attr)
+        eff = set(int(s) for s in self.effective_step)
+        frame_state = [0] + [s + 1 for s in range(self.step) if s in eff]     # outputs[i] is state frame_state[i]
+        picked = [frame_state[i] for i in range(0, len(frame_state) - 1, int(time_stride))]
+        if not picked:
+            raise ValueError("data loss selects no frame")
+        sel = [False] * (self.step + 1)
+        for st in picked:
+            sel[st] = True
+        states, loss = cell.rollout_data_loss(self.init_state, self.step, truth_sub, sel, int(space_stride))
+        outputs = [self.init_state] + [states[st:st + 1] for st in frame_state[1:]]
+        second_last_state = states[self.step - 1:self.step].clone() if self.step >= 2 else []
+        return outputs, second_last_state, loss

@@ -93,4 +93,39 @@ __device__ __forceinline__ void fold_partials(const double* __restrict__ partial
 __device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
 __device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
 
+// ---------------------------------------------------------------------------------------------
+// Fused data loss (percnn_data_loss_t): the gradient of  sum (h[::s] - target)^2 / N  with respect to the state
+// a step's adjoint produces is  coef * (h(x) - target[x / s])  at the cells whose every coordinate is a multiple
+// of s, coef = dL/dloss * 2 / N.  The adjoint kernels hold h(x) already, so they add it on the fly.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct Inject {
+  const T* target;     // low-res frame [2][ld][lh][lw] of the state this step differentiates; nullptr = none
+  const T* gscale;     // device scalar dL/dloss, nullptr = 1
+  double two_over_n;   // 2 / N
+  int s;               // spatial stride
+  int lh, lw;          // low-res extents of the two fastest axes
+  int64_t lfield;      // low-res elements per field
+};
+template <typename T>
+__device__ __forceinline__ T inject_coef(const Inject<T>& j) {
+  if (j.target == nullptr) return T(0);
+  return T(j.two_over_n * (j.gscale != nullptr ? double(__ldg(j.gscale)) : 1.0));
+}
+// One field of one cell: the gradient contribution itself (0 off the sampling lattice).
+template <typename T>
+__device__ __forceinline__ T inject_field(const Inject<T>& j, T coef, int f, int z, int y, int x, T hval) {
+  if ((x % j.s) | (y % j.s) | (z % j.s)) return T(0);
+  const int64_t i = (int64_t(z / j.s) * j.lh + y / j.s) * j.lw + x / j.s;
+  return coef * (hval - __ldg(j.target + f * j.lfield + i));
+}
+// One cell (z, y, x) of the interior grid; u, v = h at that cell.
+template <typename T>
+__device__ __forceinline__ void inject_cell(const Inject<T>& j, T coef, int z, int y, int x, T u, T v, T& gu, T& gv) {
+  if ((x % j.s) | (y % j.s) | (z % j.s)) return;
+  const int64_t i = (int64_t(z / j.s) * j.lh + y / j.s) * j.lw + x / j.s;
+  gu = fma_t(coef, u - __ldg(j.target + i), gu);
+  gv = fma_t(coef, v - __ldg(j.target + j.lfield + i), gv);
+}
+
 }  // namespace percnn

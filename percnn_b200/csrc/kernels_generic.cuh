@@ -121,9 +121,11 @@ template <typename T, int NDIM>
 __global__ void __launch_bounds__(kGenericThreads) k_pi_k1_bwd(Geom g, int slot, const T* __restrict__ h,
                                                                const T* __restrict__ gout, const T* __restrict__ gadd,
                                                                T* __restrict__ gin, double* __restrict__ partials,
-                                                               unsigned* __restrict__ counter, double* __restrict__ acc) {
+                                                               unsigned* __restrict__ counter, double* __restrict__ acc,
+                                                               Inject<T> inj) {
   const T* P = PrepView<T>::get(c_prep[slot]);
   const int64_t ncell = int64_t(g.D) * g.H * g.W;
+  const T icoef = inject_coef(inj);
   T red[kRedPiK1];
 #pragma unroll
   for (int i = 0; i < kRedPiK1; ++i) red[i] = T(0);
@@ -139,10 +141,66 @@ __global__ void __launch_bounds__(kGenericThreads) k_pi_k1_bwd(Geom g, int slot,
       gu += __ldg(gadd + o.c);
       gv += __ldg(gadd + g.field + o.c);
     }
+    if (inj.target != nullptr) {
+      const int64_t r = cell / g.W;
+      inject_cell<T>(inj, icoef, NDIM == 3 ? int(r / g.H) : 0, NDIM == 3 ? int(r % g.H) : int(r), int(cell % g.W), u, v, gu, gv);
+    }
     gin[o.c] = gu;
     gin[g.field + o.c] = gv;
   }
   reduce_into_acc<T, kRedPiK1>(red, partials, counter, acc);
+}
+
+// ---- fused data loss, forward value (percnn_data_loss_fwd) -------------------------------------------
+// Sum over the sampling lattice of ONE state of (h - target)^2, both fields, added to acc[0] (fp64, fixed order).
+// Reads only the sampled points: 1/s^ndim of the state.
+template <typename T>
+__global__ void __launch_bounds__(kGenericThreads) k_data_loss(Geom g, const T* __restrict__ h, Inject<T> inj,
+                                                               double* __restrict__ partials, unsigned* __restrict__ counter,
+                                                               double* __restrict__ acc) {
+  double red[1] = {0.0};
+  const int64_t npts = 2 * inj.lfield;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < npts; i += int64_t(gridDim.x) * blockDim.x) {
+    const int f = int(i / inj.lfield);
+    const int64_t r = i - f * inj.lfield;
+    const int lx = int(r % inj.lw);
+    const int64_t t = r / inj.lw;
+    const int ly = int(t % inj.lh), lz = int(t / inj.lh);
+    int64_t off;
+    if (g.ndim == 3)
+      off = int64_t(lz * inj.s + g.ghost) * g.plane + int64_t(ly * inj.s) * g.W + lx * inj.s;
+    else
+      off = int64_t(ly * inj.s + g.ghost) * g.W + lx * inj.s;
+    const T d = __ldg(h + f * g.field + off) - __ldg(inj.target + i);
+    red[0] += double(d) * double(d);
+  }
+  reduce_into_acc<double, 1>(red, partials, counter, acc);
+}
+// The loss gradient of the LAST state of a rollout (no adjoint step differentiates it): g += coef (h - target) on
+// the sampling lattice.  One thread per low-res point.
+template <typename T>
+__global__ void __launch_bounds__(kGenericThreads) k_inject_only(Geom g, const T* __restrict__ h, T* __restrict__ gbuf,
+                                                                 Inject<T> inj) {
+  const T coef = inject_coef(inj);
+  const int64_t npts = 2 * inj.lfield;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < npts; i += int64_t(gridDim.x) * blockDim.x) {
+    const int f = int(i / inj.lfield);
+    const int64_t r = i - f * inj.lfield;
+    const int lx = int(r % inj.lw);
+    const int64_t t = r / inj.lw;
+    const int ly = int(t % inj.lh), lz = int(t / inj.lh);
+    int64_t off;
+    if (g.ndim == 3)
+      off = int64_t(lz * inj.s + g.ghost) * g.plane + int64_t(ly * inj.s) * g.W + lx * inj.s;
+    else
+      off = int64_t(ly * inj.s + g.ghost) * g.W + lx * inj.s;
+    off += f * g.field;
+    gbuf[off] = fma_t(coef, __ldg(h + off) - __ldg(inj.target + i), gbuf[off]);
+  }
+}
+template <typename T>
+__global__ void k_data_loss_finish(const double* __restrict__ acc, double inv_n, T* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = T(acc[0] * inv_n);
 }
 
 // ---- Stage-3 physics cells (2-D) --------------------------------------------------------------
@@ -167,9 +225,11 @@ template <typename T>
 __global__ void __launch_bounds__(kGenericThreads) k_burgers_bwd(Geom g, int slot, const T* __restrict__ h,
                                                                  const T* __restrict__ gout, const T* __restrict__ gadd,
                                                                  T* __restrict__ gin, double* __restrict__ partials,
-                                                                 unsigned* __restrict__ counter, double* __restrict__ acc) {
+                                                                 unsigned* __restrict__ counter, double* __restrict__ acc,
+                                                                 Inject<T> inj) {
   const T* P = PrepView<T>::get(c_prep[slot]);
   const int64_t ncell = int64_t(g.H) * g.W;
+  const T icoef = inject_coef(inj);
   T red[kRedBurgers];
 #pragma unroll
   for (int i = 0; i < kRedBurgers; ++i) red[i] = T(0);
@@ -186,6 +246,7 @@ __global__ void __launch_bounds__(kGenericThreads) k_burgers_bwd(Geom g, int slo
       gu += __ldg(gadd + o.c);
       gv += __ldg(gadd + g.field + o.c);
     }
+    if (inj.target != nullptr) inject_cell<T>(inj, icoef, 0, int(cell / g.W), int(cell % g.W), U.c, V.c, gu, gv);
     gin[o.c] = gu;
     gin[g.field + o.c] = gv;
   }
@@ -213,9 +274,11 @@ template <typename T>
 __global__ void __launch_bounds__(kGenericThreads) k_lo_bwd(Geom g, int slot, const T* __restrict__ h,
                                                             const T* __restrict__ gout, const T* __restrict__ gadd,
                                                             T* __restrict__ gin, double* __restrict__ partials,
-                                                            unsigned* __restrict__ counter, double* __restrict__ acc) {
+                                                            unsigned* __restrict__ counter, double* __restrict__ acc,
+                                                            Inject<T> inj) {
   const T* P = PrepView<T>::get(c_prep[slot]);
   const int64_t ncell = int64_t(g.H) * g.W;
+  const T icoef = inject_coef(inj);
   T red[kRedLO];
 #pragma unroll
   for (int i = 0; i < kRedLO; ++i) red[i] = T(0);
@@ -231,6 +294,7 @@ __global__ void __launch_bounds__(kGenericThreads) k_lo_bwd(Geom g, int slot, co
       gu += __ldg(gadd + o.c);
       gv += __ldg(gadd + g.field + o.c);
     }
+    if (inj.target != nullptr) inject_cell<T>(inj, icoef, 0, int(cell / g.W), int(cell % g.W), u, v, gu, gv);
     gin[o.c] = gu;
     gin[g.field + o.c] = gv;
   }

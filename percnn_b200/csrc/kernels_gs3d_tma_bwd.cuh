@@ -30,6 +30,7 @@ struct BwdExtra {
   double* partials;      // [gridDim.x][2 or 22]
   unsigned* counter;
   double* acc;           // [22] running sums over steps ([0..1] from this kernel, [2..21] from k_monomial_sums)
+  Inject<float> inj;     // fused data-loss gradient of this step's state (target == nullptr: none)
 };
 
 __device__ __forceinline__ float2 quad2(const float* __restrict__ d, float2 u, float2 v) {
@@ -49,7 +50,8 @@ __device__ __forceinline__ void adjoint_plane(Consumer& c, const float* __restri
                                               const float* seam_ptr, int64_t field, int64_t plane, int64_t off,
                                               float* __restrict__ dst, float* mirror, const float* __restrict__ hbase,
                                               const float* __restrict__ gadd, bool prefetch_next, bool valid,
-                                              float2 (&seam_next)[2], float (&aacc)[2], float2* __restrict__ macc) {
+                                              float2 (&seam_next)[2], float (&aacc)[2], float2* __restrict__ macc,
+                                              const Inject<float>& inj, int64_t inj_row, int xq) {
   const float* P = c.P;
   mbar_wait(&c.full[c.s], c.parity);   // plane k has landed; planes k-4 .. k-1 are still resident
   const float2 seam_u = seam_next[0], seam_v = seam_next[1];
@@ -154,6 +156,24 @@ __device__ __forceinline__ void adjoint_plane(Consumer& c, const float* __restri
     PERCNN_MONO(8, us[0] * vv[0], us[1] * vv[1], us[2] * vv[2], us[3] * vv[3])
     PERCNN_MONO(9, vv[0] * vs[0], vv[1] * vs[1], vv[2] * vs[2], vv[3] * vs[3])
 #undef PERCNN_MONO
+  }
+  if (inj_row >= 0) {
+    // This (plane, row) lies on the sampling lattice of the fused data loss (warp-uniform branch, taken on the
+    // selected steps only): add coef * (h - target) at the lane's cells whose x is a multiple of the stride.
+    const float icoef = inject_coef(inj);
+    const float hus[4] = {hu.x, hu.y, hu.z, hu.w}, hvs[4] = {hv.x, hv.y, hv.z, hv.w};
+    float iu[4] = {ou.x, ou.y, ou.z, ou.w}, iv[4] = {ov.x, ov.y, ov.z, ov.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int xg = xq + j;
+      if (xg % inj.s == 0) {
+        const int64_t i = inj_row + xg / inj.s;
+        iu[j] = fmaf(icoef, hus[j] - __ldg(inj.target + i), iu[j]);
+        iv[j] = fmaf(icoef, hvs[j] - __ldg(inj.target + inj.lfield + i), iv[j]);
+      }
+    }
+    ou = make_float4(iu[0], iu[1], iu[2], iu[3]);
+    ov = make_float4(iv[0], iv[1], iv[2], iv[3]);
   }
   *reinterpret_cast<float4*>(dst + off) = ou;
   *reinterpret_cast<float4*>(dst + off + field) = ov;
@@ -308,6 +328,8 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
     }
     // rows below the natural start of this tile are duplicates of the previous tile (last tile shifted back)
     const bool valid = (ic.y0 + warp) >= ic.ytile * p.ty;
+    // fused data loss: is this warp's row on the sampling lattice, and where does it start in the low-res frame
+    const int inj_ly = (x.inj.target != nullptr && (ic.y0 + warp) % x.inj.s == 0) ? (ic.y0 + warp) / x.inj.s : -1;
     const float* src_xy = p.src + int64_t(ic.y0) * p.W + ic.x0;
     int64_t off = (int64_t(ic.z0 + p.dst_zoff) * p.H + ic.y0) * p.W + ic.x0 + c.toff;   // this lane's quad, first output plane
     int xs = (lane == 0) ? ic.x0 - 2 : ic.x0 + TX;
@@ -331,8 +353,13 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
           pz -= p.D;
           seam_ptr -= wrap_back;
         }
+        int64_t inj_row = -1;
+        if (inj_ly >= 0) {
+          const int zg = ic.z0 + k - 4;   // interior index of the output plane
+          if (zg % x.inj.s == 0) inj_row = (int64_t(zg / x.inj.s) * x.inj.lh + inj_ly) * x.inj.lw;
+        }
         adjoint_plane<FUSED, MONO>(c, TP, k <= ic.nz + 2, seam_ptr, field, plane, off, p.dst, mirror, x.h, x.gadd,
-                                   k + 1 < nk, valid, seam_next, aacc, macc);
+                                   k + 1 < nk, valid, seam_next, aacc, macc, x.inj, inj_row, ic.x0 + 4 * lane);
         off += plane;
         if (FUSED && mirror != nullptr) mirror += plane;
         if (++since_flush >= BWD_FLUSH) flush();

@@ -373,22 +373,52 @@ int step_fwd_any(percnn_plan* p, const void* src, void* dst, cudaStream_t st) {
                      : step_fwd_t<double>(p, static_cast<const double*>(src), static_cast<double*>(dst), st);
 }
 
+// Type-erased description of the fused data-loss gradient of one state (see percnn_data_loss_t).
+struct InjectHost {
+  const void* target = nullptr;   // that state's low-res frame
+  const void* gscale = nullptr;
+  int stride = 1;
+  int64_t n_total = 0;
+};
+int lowres(int n, int s) { return (n + s - 1) / s; }
+int64_t lowres_field_elems(const percnn_plan* p, int s) {
+  const Geom& g = p->g;
+  return int64_t(g.ndim == 3 ? lowres(g.D, s) : 1) * lowres(g.H, s) * lowres(g.W, s);
+}
 template <typename T>
-int step_bwd_t(percnn_plan* p, const T* h, const T* gout, const T* gadd, T* gin, char* ws, cudaStream_t st) {
+Inject<T> make_inject(const percnn_plan* p, const InjectHost* ih) {
+  Inject<T> j;
+  memset(&j, 0, sizeof(j));
+  j.s = 1;
+  if (!ih || !ih->target) return j;
+  j.target = static_cast<const T*>(ih->target);
+  j.gscale = static_cast<const T*>(ih->gscale);
+  j.two_over_n = 2.0 / double(ih->n_total);
+  j.s = ih->stride;
+  j.lh = lowres(p->g.H, ih->stride);
+  j.lw = lowres(p->g.W, ih->stride);
+  j.lfield = lowres_field_elems(p, ih->stride);
+  return j;
+}
+
+template <typename T>
+int step_bwd_t(percnn_plan* p, const T* h, const T* gout, const T* gadd, T* gin, char* ws, cudaStream_t st,
+               const InjectHost* ih) {
   const Geom& g = p->g;
   const int grid = generic_grid(p, 2);
+  const Inject<T> inj = make_inject<T>(p, ih);
   double* acc = reinterpret_cast<double*>(ws + kWsAcc);
   unsigned* counter = reinterpret_cast<unsigned*>(ws + kWsCounter);
   double* partials = reinterpret_cast<double*>(ws + kWsPartials);
   if (p->desc.cell == PERCNN_CELL_PI && p->desc.ksize == 1) {
     if (g.ndim == 3)
-      k_pi_k1_bwd<T, 3><<<grid, kGenericThreads, 0, st>>>(g, p->slot, h, gout, gadd, gin, partials, counter, acc);
+      k_pi_k1_bwd<T, 3><<<grid, kGenericThreads, 0, st>>>(g, p->slot, h, gout, gadd, gin, partials, counter, acc, inj);
     else
-      k_pi_k1_bwd<T, 2><<<grid, kGenericThreads, 0, st>>>(g, p->slot, h, gout, gadd, gin, partials, counter, acc);
+      k_pi_k1_bwd<T, 2><<<grid, kGenericThreads, 0, st>>>(g, p->slot, h, gout, gadd, gin, partials, counter, acc, inj);
   } else if (p->desc.cell == PERCNN_CELL_BURGERS) {
-    k_burgers_bwd<T><<<grid, kGenericThreads, 0, st>>>(g, p->slot, h, gout, gadd, gin, partials, counter, acc);
+    k_burgers_bwd<T><<<grid, kGenericThreads, 0, st>>>(g, p->slot, h, gout, gadd, gin, partials, counter, acc, inj);
   } else if (p->desc.cell == PERCNN_CELL_LO) {
-    k_lo_bwd<T><<<grid, kGenericThreads, 0, st>>>(g, p->slot, h, gout, gadd, gin, partials, counter, acc);
+    k_lo_bwd<T><<<grid, kGenericThreads, 0, st>>>(g, p->slot, h, gout, gadd, gin, partials, counter, acc, inj);
   } else {
     return fail(PERCNN_ERR_UNSUPPORTED, "adjoint of the 5x5 Pi-block cell is not implemented yet");
   }
@@ -398,7 +428,7 @@ int step_bwd_t(percnn_plan* p, const T* h, const T* gout, const T* gadd, T* gin,
 }
 
 int step_bwd_any(percnn_plan* p, const void* h, const void* gout, const void* gadd, void* gin, void* ws, cudaStream_t st,
-                 const SlabLink* link = nullptr) {
+                 const SlabLink* link = nullptr, const InjectHost* ih = nullptr) {
   if (p->use_tma) {
     char* w = static_cast<char*>(ws);
     tma3d::BwdExtra x;
@@ -407,6 +437,7 @@ int step_bwd_any(percnn_plan* p, const void* h, const void* gout, const void* ga
     x.partials = reinterpret_cast<double*>(w + kWsPartials);
     x.counter = reinterpret_cast<unsigned*>(w + kWsCounter);
     x.acc = reinterpret_cast<double*>(w + kWsAcc);
+    x.inj = make_inject<float>(p, ih);
     if (p->bwd_split_mono) {  // the 20 stencil-free monomial sums as a separate streaming pass over h and G
       const Geom& g = p->g;
       const int64_t n4 = int64_t(g.D) * g.plane / 4;
@@ -431,6 +462,13 @@ int step_bwd_any(percnn_plan* p, const void* h, const void* gout, const void* ga
         p->g, p->slot, p->desc.hidden, np, static_cast<const float*>(h), static_cast<const float*>(gout),
         static_cast<const float*>(gadd), static_cast<float*>(gin), p->d_k5w, partials);
     PERCNN_CUDA(cudaGetLastError());
+    if (ih && ih->target) {
+      // the 5x5 adjoint sits at its register limit; the (rare, 1/s^2-sized) loss injection runs as its own pass
+      k_inject_only<float><<<generic_grid(p), kGenericThreads, 0, st>>>(p->g, static_cast<const float*>(h),
+                                                                         static_cast<float*>(gin), make_inject<float>(p, ih));
+      PERCNN_CUDA(cudaGetLastError());
+      p->launches++;
+    }
     k5::k5_reduce_partials<<<(np + 255) / 256, 256, 0, st>>>(partials, int(grid.x * grid.y), np, acc);
     PERCNN_CUDA(cudaGetLastError());
     p->launches += 2;
@@ -438,10 +476,10 @@ int step_bwd_any(percnn_plan* p, const void* h, const void* gout, const void* ga
   }
   return p->elt == 4 ? step_bwd_t<float>(p, static_cast<const float*>(h), static_cast<const float*>(gout),
                                          static_cast<const float*>(gadd), static_cast<float*>(gin),
-                                         static_cast<char*>(ws), st)
+                                         static_cast<char*>(ws), st, ih)
                      : step_bwd_t<double>(p, static_cast<const double*>(h), static_cast<const double*>(gout),
                                           static_cast<const double*>(gadd), static_cast<double*>(gin),
-                                          static_cast<char*>(ws), st);
+                                          static_cast<char*>(ws), st, ih);
 }
 
 }  // namespace
@@ -681,7 +719,26 @@ int percnn_step_fwd_fused_halo(percnn_plan_t* p, const void* h_in, void* h_out, 
 // neighbours' ghost planes of their g_in buffers.
 int percnn_step_bwd_fused_halo(percnn_plan_t* p, const void* h_in, const void* g_out, const void* g_add, void* g_in,
                                void* ws, const percnn_slab_link_t* link, void* stream) {
-  if (!p || !h_in || !g_out || !g_in || !ws || !link) return fail(PERCNN_ERR_INVALID, "null argument");
+  if (!link) return fail(PERCNN_ERR_INVALID, "null argument");
+  return percnn_step_bwd_loss(p, h_in, g_out, g_add, nullptr, 1, 0, nullptr, g_in, ws, link, stream);
+}
+
+// Adjoint step with the fused data-loss gradient of state h_in injected (and, with `link`, the fused halo exchange).
+int percnn_step_bwd_loss(percnn_plan_t* p, const void* h_in, const void* g_out, const void* g_add,
+                         const void* target_frame, int stride, int64_t n_total, const void* gscale, void* g_in,
+                         void* ws, const percnn_slab_link_t* link, void* stream) {
+  if (!p || !h_in || !g_out || !g_in || !ws) return fail(PERCNN_ERR_INVALID, "null argument");
+  if (g_out == g_in) return fail(PERCNN_ERR_INVALID, "step_bwd cannot run in place");
+  InjectHost ih;
+  if (target_frame) {
+    if (stride < 1) return fail(PERCNN_ERR_INVALID, "data-loss stride must be >= 1");
+    if (n_total < 1) return fail(PERCNN_ERR_INVALID, "data-loss n_total must be >= 1 for a single step");
+    ih.target = target_frame;
+    ih.gscale = gscale;
+    ih.stride = stride;
+    ih.n_total = n_total;
+  }
+  if (!link) return step_bwd_any(p, h_in, g_out, g_add, g_in, ws, static_cast<cudaStream_t>(stream), nullptr, &ih);
   if (!p->use_tma || !p->desc.slab_ghost) return fail(PERCNN_ERR_UNSUPPORTED, "fused halo steps need a slab-mode TMA plan");
   if (p->g.D < 5) return fail(PERCNN_ERR_UNSUPPORTED, "fused halo steps need at least 5 planes per rank");
   if (!link->peer_lo_out || !link->peer_hi_out || !link->my_flags || !link->peer_lo_flags || !link->peer_hi_flags || !link->scratch)
@@ -695,7 +752,68 @@ int percnn_step_bwd_fused_halo(percnn_plan_t* p, const void* h_in, const void* g
   l.scratch = link->scratch;
   l.epoch_wait = link->epoch;
   l.epoch_post = link->epoch + 1;
-  return step_bwd_any(p, h_in, g_out, g_add, g_in, ws, static_cast<cudaStream_t>(stream), &l);
+  return step_bwd_any(p, h_in, g_out, g_add, g_in, ws, static_cast<cudaStream_t>(stream), &l, &ih);
+}
+
+namespace {
+int check_data_loss(const percnn_plan* p, const percnn_data_loss_t* dl, int nsteps, int* nsel_out, int64_t* n_out) {
+  if (!dl->target || !dl->sel) return fail(PERCNN_ERR_INVALID, "data loss needs a target and a selection mask");
+  if (dl->stride < 1) return fail(PERCNN_ERR_INVALID, "data-loss stride must be >= 1");
+  if (dl->reserved != 0) return fail(PERCNN_ERR_INVALID, "percnn_data_loss_t.reserved must be 0");
+  if (dl->n_total < 0) return fail(PERCNN_ERR_INVALID, "data-loss n_total must be >= 0");
+  int nsel = 0;
+  for (int s = 0; s <= nsteps; ++s) nsel += dl->sel[s] ? 1 : 0;
+  if (nsel == 0) return fail(PERCNN_ERR_INVALID, "data loss selects no state");
+  *nsel_out = nsel;
+  *n_out = dl->n_total > 0 ? dl->n_total : int64_t(nsel) * 2 * lowres_field_elems(p, dl->stride);
+  return PERCNN_OK;
+}
+}  // namespace
+
+// Forward value of the fused data loss: one small launch per selected state (reads the sampled points only).
+int percnn_data_loss_fwd(percnn_plan_t* p, const void* tape, int nsteps, const percnn_data_loss_t* dl, void* loss_out,
+                         void* ws, void* stream) {
+  if (!p || !tape || !dl || !loss_out || !ws) return fail(PERCNN_ERR_INVALID, "null argument");
+  if (nsteps < 0) return fail(PERCNN_ERR_INVALID, "nsteps must be >= 0");
+  int nsel = 0;
+  int64_t n = 0;
+  int rc = check_data_loss(p, dl, nsteps, &nsel, &n);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* w = static_cast<char*>(ws);
+  double* acc = reinterpret_cast<double*>(w + kWsAcc);
+  unsigned* counter = reinterpret_cast<unsigned*>(w + kWsCounter);
+  double* partials = reinterpret_cast<double*>(w + kWsPartials);
+  PERCNN_CUDA(cudaMemsetAsync(w, 0, kWsPartials, st));
+  const int64_t lf = lowres_field_elems(p, dl->stride);
+  int64_t blocks = (2 * lf + kGenericThreads - 1) / kGenericThreads;
+  if (blocks > 256) blocks = 256;   // partials must fit the smallest workspace header (5x5 plans, hidden = 2)
+  const size_t sb = state_bytes(p);
+  int slot = 0;
+  for (int s = 0; s <= nsteps; ++s) {
+    if (!dl->sel[s]) continue;
+    InjectHost ih;
+    ih.target = static_cast<const char*>(dl->target) + size_t(slot) * size_t(2 * lf) * p->elt;
+    ih.stride = dl->stride;
+    ih.n_total = n;
+    const char* h = static_cast<const char*>(tape) + size_t(s) * sb;
+    if (p->elt == 4)
+      k_data_loss<float><<<int(blocks), kGenericThreads, 0, st>>>(p->g, reinterpret_cast<const float*>(h),
+                                                                  make_inject<float>(p, &ih), partials, counter, acc);
+    else
+      k_data_loss<double><<<int(blocks), kGenericThreads, 0, st>>>(p->g, reinterpret_cast<const double*>(h),
+                                                                   make_inject<double>(p, &ih), partials, counter, acc);
+    PERCNN_CUDA(cudaGetLastError());
+    p->launches++;
+    ++slot;
+  }
+  if (p->elt == 4)
+    k_data_loss_finish<float><<<1, 32, 0, st>>>(acc, 1.0 / double(n), static_cast<float*>(loss_out));
+  else
+    k_data_loss_finish<double><<<1, 32, 0, st>>>(acc, 1.0 / double(n), static_cast<double*>(loss_out));
+  PERCNN_CUDA(cudaGetLastError());
+  p->launches++;
+  return PERCNN_OK;
 }
 
 int percnn_param_grads_begin(percnn_plan_t* p, void* ws, void* stream) {
@@ -784,9 +902,33 @@ int percnn_rollout_fwd(percnn_plan_t* p, const void* h0, void* traj, const uint8
 
 int percnn_rollout_bwd(percnn_plan_t* p, const void* params, const void* tape, const void* g_tape, const uint8_t* gmask,
                        int nsteps, void* g_h0, void* param_grads, void* ws, void* stream) {
+  return percnn_rollout_bwd_loss(p, params, tape, g_tape, gmask, nullptr, nsteps, g_h0, param_grads, ws, stream);
+}
+
+int percnn_rollout_bwd_loss(percnn_plan_t* p, const void* params, const void* tape, const void* g_tape,
+                            const uint8_t* gmask, const percnn_data_loss_t* dl, int nsteps, void* g_h0, void* param_grads,
+                            void* ws, void* stream) {
   if (!p || !params || !tape || !g_h0 || !param_grads || !ws) return fail(PERCNN_ERR_INVALID, "null argument");
   if (nsteps < 1) return fail(PERCNN_ERR_INVALID, "nsteps must be >= 1");
   if (g_tape && !gmask) return fail(PERCNN_ERR_INVALID, "g_tape given without a mask");
+  int dl_nsel = 0;
+  int64_t dl_n = 0;
+  if (dl) {
+    int rcl = check_data_loss(p, dl, nsteps, &dl_nsel, &dl_n);
+    if (rcl) return rcl;
+  }
+  const size_t dl_frame_bytes = dl ? size_t(2 * lowres_field_elems(p, dl->stride)) * p->elt : 0;
+  int dl_slot = dl_nsel;   // walks the packed target frames backwards, like `slot` does for g_tape
+  auto inject_for = [&](int s, InjectHost* ih) {
+    *ih = InjectHost();
+    if (dl && dl->sel[s]) {
+      --dl_slot;
+      ih->target = static_cast<const char*>(dl->target) + size_t(dl_slot) * dl_frame_bytes;
+      ih->gscale = dl->gscale;
+      ih->stride = dl->stride;
+      ih->n_total = dl_n;
+    }
+  };
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t sb = state_bytes(p);
   char* w = static_cast<char*>(ws);
@@ -808,6 +950,25 @@ int percnn_rollout_bwd(percnn_plan_t* p, const void* params, const void* tape, c
     PERCNN_CUDA(cudaMemsetAsync(pp[0], 0, sb, st));
     G = pp[0];
   }
+  InjectHost ih;
+  inject_for(nsteps, &ih);
+  if (ih.target) {
+    // the last state has no adjoint step of its own: scatter its loss gradient into G_nsteps
+    if (G != pp[0]) {
+      PERCNN_CUDA(cudaMemcpyAsync(pp[0], G, sb, cudaMemcpyDeviceToDevice, st));
+      G = pp[0];
+    }
+    const int grid = generic_grid(p);
+    const char* hT = static_cast<const char*>(tape) + size_t(nsteps) * sb;
+    if (p->elt == 4)
+      k_inject_only<float><<<grid, kGenericThreads, 0, st>>>(p->g, reinterpret_cast<const float*>(hT),
+                                                             reinterpret_cast<float*>(pp[0]), make_inject<float>(p, &ih));
+    else
+      k_inject_only<double><<<grid, kGenericThreads, 0, st>>>(p->g, reinterpret_cast<const double*>(hT),
+                                                              reinterpret_cast<double*>(pp[0]), make_inject<double>(p, &ih));
+    PERCNN_CUDA(cudaGetLastError());
+    p->launches++;
+  }
   int flip = (G == pp[0]) ? 1 : 0;
   for (int s = nsteps - 1; s >= 0; --s) {
     const char* add = nullptr;
@@ -815,9 +976,10 @@ int percnn_rollout_bwd(percnn_plan_t* p, const void* params, const void* tape, c
       --slot;
       add = gt + size_t(slot) * sb;
     }
+    inject_for(s, &ih);
     char* gin = (s == 0) ? static_cast<char*>(g_h0) : pp[flip];
     if (s != 0) flip ^= 1;
-    rc = step_bwd_any(p, static_cast<const char*>(tape) + size_t(s) * sb, G, add, gin, ws, st);
+    rc = step_bwd_any(p, static_cast<const char*>(tape) + size_t(s) * sb, G, add, gin, ws, st, nullptr, &ih);
     if (rc) return rc;
     G = gin;
   }

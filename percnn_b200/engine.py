@@ -31,6 +31,22 @@ class CellSpec:
     flags: int = 0
 
 
+@dataclasses.dataclass(frozen=True)
+class DataLossSpec:
+    """Which states and which points enter the fused data loss (percnn_data_loss_t).
+
+    `mse_loss(output[0:-1:15, :, ::2, ::2, ::2], truth_sub)` (GS3D:403) over a rollout whose `output` holds every
+    state is `DataLossSpec(sel=[s % 15 == 0 and s < nsteps for s in range(nsteps + 1)], stride=2)`.
+    """
+    sel: Tuple[bool, ...]      # nsteps + 1 entries; sel[s]: state h_s takes part
+    stride: int = 1            # `::stride` on every spatial axis
+    n_total: int = 0           # elements in the mean; 0 = this plan's own count (slab ranks pass the global one)
+
+    @property
+    def nsel(self) -> int:
+        return sum(1 for e in self.sel if e)
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -193,6 +209,67 @@ class Plan:
                                          _stream_ptr(self.device)))
         return g_h0, g_flat
 
+    # -- fused data loss ------------------------------------------------------------------------
+    def lowres_shape(self, stride: int) -> Tuple[int, ...]:
+        """Shape of one state's low-res target frame: (2, ceil(D/s), ceil(H/s), ceil(W/s)) (no D in 2-D)."""
+        return (2, *[(n + stride - 1) // stride for n in self.spatial])
+
+    def _data_loss_struct(self, spec: DataLossSpec, nsteps: int, target: torch.Tensor, gscale: Optional[torch.Tensor]):
+        if len(spec.sel) != nsteps + 1:
+            raise ValueError(f"data loss: selection mask needs nsteps + 1 = {nsteps + 1} entries, got {len(spec.sel)}")
+        if spec.stride < 1:
+            raise ValueError("data loss: stride must be >= 1")
+        _require_cuda(target, "data-loss target")
+        want = (spec.nsel, *self.lowres_shape(spec.stride))
+        if target.dtype != self.spec.dtype or not target.is_contiguous() or tuple(target.shape) != want:
+            raise ValueError(f"data-loss target: need a contiguous {self.spec.dtype} tensor of shape {want}, "
+                             f"got {target.dtype} {tuple(target.shape)}")
+        dl = _lib.DataLoss()
+        sel_arr = (ctypes.c_uint8 * (nsteps + 1))(*[1 if e else 0 for e in spec.sel])
+        dl.target, dl.sel, dl.stride, dl.reserved, dl.n_total = target.data_ptr(), sel_arr, int(spec.stride), 0, int(spec.n_total)
+        if gscale is not None:
+            _require_cuda(gscale, "data-loss gradient scale")
+            if gscale.numel() != 1 or gscale.dtype != self.spec.dtype:
+                raise ValueError("data-loss gradient scale must be one scalar of the plan dtype")
+            dl.gscale = gscale.data_ptr()
+        return dl, sel_arr          # sel_arr must outlive the call
+
+    def data_loss_fwd(self, tape: torch.Tensor, nsteps: int, spec: DataLossSpec, target: torch.Tensor) -> torch.Tensor:
+        """0-dim tensor: sum over selected states / sampled points of (h - target)^2, divided by n_total."""
+        self._check_state(tape, "tape", nsteps + 1)
+        dl, _keep = self._data_loss_struct(spec, nsteps, target, None)
+        out = torch.empty((), dtype=self.spec.dtype, device=self.device)
+        check(self._L.percnn_data_loss_fwd(self._h, tape.data_ptr(), int(nsteps), ctypes.byref(dl), out.data_ptr(),
+                                           self.workspace().data_ptr(), _stream_ptr(self.device)))
+        return out
+
+    def rollout_bwd_loss(self, flat: torch.Tensor, tape: torch.Tensor, nsteps: int, spec: DataLossSpec,
+                         target: torch.Tensor, gscale: Optional[torch.Tensor] = None,
+                         g_tape: Optional[torch.Tensor] = None, gmask: Optional[Sequence[bool]] = None):
+        """rollout_bwd with the loss gradient injected by the adjoint kernels (no dense gradient tape)."""
+        self._check_state(tape, "tape", nsteps + 1)
+        dl, _keep = self._data_loss_struct(spec, nsteps, target, gscale)
+        mask_arr = None
+        if g_tape is not None:
+            if gmask is None or len(gmask) != nsteps + 1:
+                raise ValueError("g_tape needs a mask with nsteps+1 entries")
+            self._check_state(g_tape, "g_tape", sum(1 for e in gmask if e))
+            mask_arr = (ctypes.c_uint8 * (nsteps + 1))(*[1 if e else 0 for e in gmask])
+        g_h0 = torch.empty(self.buffer_shape, dtype=self.spec.dtype, device=self.device)
+        g_flat = torch.empty_like(flat)
+        check(self._L.percnn_rollout_bwd_loss(self._h, flat.data_ptr(), tape.data_ptr(), _ptr(g_tape), mask_arr,
+                                              ctypes.byref(dl), int(nsteps), g_h0.data_ptr(), g_flat.data_ptr(),
+                                              self.workspace().data_ptr(), _stream_ptr(self.device)))
+        return g_h0, g_flat
+
+    def step_bwd_loss(self, h_in, g_out, g_in, *, target_frame=None, stride=1, n_total=0, gscale=None, g_add=None,
+                      link=None) -> None:
+        """One adjoint step with the loss gradient of state h_in injected (link: fused-halo slab step)."""
+        check(self._L.percnn_step_bwd_loss(self._h, h_in.data_ptr(), g_out.data_ptr(), _ptr(g_add), _ptr(target_frame),
+                                           int(stride), int(n_total), _ptr(gscale), g_in.data_ptr(),
+                                           self.workspace().data_ptr(), None if link is None else ctypes.byref(link),
+                                           _stream_ptr(self.device)))
+
     def rollout_fwd_host(self, flat_host: torch.Tensor, h0_host: torch.Tensor, nsteps: int,
                          emit: Optional[Sequence[bool]] = None, want_final: bool = True):
         """End-to-end call with HOST buffers (pinned or pageable): H2D, rollout, D2H, sync."""
@@ -287,6 +364,67 @@ class _Rollout(torch.autograd.Function):
                 grads.append(None)
             off += n
         return (None, None, g_h0 if ctx.needs_input_grad[2] else None, *grads)
+
+
+def _split_param_grads(ctx, g_flat: torch.Tensor, first: int) -> List[Optional[torch.Tensor]]:
+    grads: List[Optional[torch.Tensor]] = []
+    off = 0
+    for i, (shape, dt) in enumerate(zip(ctx.shapes, ctx.dtypes)):
+        n = 1
+        for s in shape:
+            n *= s
+        grads.append(g_flat[off:off + n].view(shape).to(dt) if ctx.needs_input_grad[first + i] else None)
+        off += n
+    return grads
+
+
+class _RolloutLoss(torch.autograd.Function):
+    """(states, loss) = rollout + fused strided-subsample MSE.
+
+    The loss value is one small reduction over the sampled points of the tape; in backward its gradient is
+    injected by the adjoint kernels themselves, so no dense [nsteps+1, 2, ...] gradient is ever materialised
+    unless the caller ALSO differentiates through `states` (then both sources are combined).
+    """
+
+    @staticmethod
+    def forward(ctx, plan: Plan, nsteps: int, spec: DataLossSpec, target: torch.Tensor, h0: torch.Tensor,
+                *params: torch.Tensor):
+        _require_cuda(h0, "state")
+        flat = pack_params(params, plan.spec.dtype)
+        plan.params_load(flat)
+        states = torch.empty((nsteps + 1, *plan.buffer_shape), dtype=plan.spec.dtype, device=h0.device)
+        plan.rollout_fwd(h0.detach().contiguous().view(plan.buffer_shape), nsteps, tape=states)
+        target = target.detach().contiguous()
+        loss = plan.data_loss_fwd(states, nsteps, spec, target)
+        ctx.plan, ctx.nsteps, ctx.spec = plan, nsteps, spec
+        ctx.shapes = [tuple(p.shape) for p in params]
+        ctx.dtypes = [p.dtype for p in params]
+        ctx.save_for_backward(states, flat, target)
+        ctx.set_materialize_grads(False)
+        return states, loss
+
+    @staticmethod
+    def backward(ctx, g_states: Optional[torch.Tensor], g_loss: Optional[torch.Tensor]):
+        states, flat, target = ctx.saved_tensors
+        plan, nsteps = ctx.plan, ctx.nsteps
+        none = (None,) * (5 + len(ctx.shapes))
+        if g_states is None and g_loss is None:
+            return none
+        plan.params_load(flat)
+        dense = None if g_states is None else g_states.contiguous()
+        mask = None if dense is None else [True] * (nsteps + 1)
+        if g_loss is None:
+            g_h0, g_flat = plan.rollout_bwd(flat, states, dense, mask, nsteps)
+        else:
+            gscale = g_loss.detach().to(plan.spec.dtype).reshape(1).contiguous()
+            g_h0, g_flat = plan.rollout_bwd_loss(flat, states, nsteps, ctx.spec, target, gscale, dense, mask)
+        return (None, None, None, None, g_h0 if ctx.needs_input_grad[4] else None, *_split_param_grads(ctx, g_flat, 5))
+
+
+def rollout_states_with_data_loss(plan: Plan, nsteps: int, h0: torch.Tensor, params: Sequence[torch.Tensor],
+                                  spec: DataLossSpec, target: torch.Tensor):
+    """(states [nsteps+1, 2, ...], loss 0-dim); both differentiable w.r.t. h0 and the parameters."""
+    return _RolloutLoss.apply(plan, nsteps, spec, target, h0, *params)
 
 
 def rollout_states(plan: Plan, nsteps: int, h0: torch.Tensor, params: Sequence[torch.Tensor]) -> torch.Tensor:

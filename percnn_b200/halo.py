@@ -270,30 +270,79 @@ class SlabRollout:
         self.bufs[self.cur].copy_(tape[nsteps])
         return tape
 
-    def backward(self, tape: torch.Tensor, g_tape: torch.Tensor):
+    def _loss_spec(self, nsteps: int, sel, stride: int) -> "engine.DataLossSpec":
+        """Slab-local view of the global fused data loss: the sampling lattice `::stride` of the global grid must
+        coincide with the local one (slab origin and depth multiples of the stride), and the mean runs over the
+        GLOBAL number of sampled points."""
+        if self.z0 % stride or self.nz % stride:
+            raise ValueError(f"slab [{self.z0}, {self.z0 + self.nz}) does not respect the loss stride {stride}")
+        sel = tuple(bool(e) for e in sel)
+        if len(sel) != nsteps + 1:
+            raise ValueError("selection mask needs nsteps + 1 entries")
+        if sel[nsteps]:
+            raise NotImplementedError("the last state has no adjoint step; the scripts' `[0:-1:...]` never selects it")
+        D, (H, W) = self.nz * self.world, self.plan.spatial[1:]
+        n_total = sum(sel) * 2 * ((D + stride - 1) // stride) * ((H + stride - 1) // stride) * ((W + stride - 1) // stride)
+        return engine.DataLossSpec(sel=sel, stride=int(stride), n_total=n_total)
+
+    def data_loss(self, tape: torch.Tensor, target_sub: torch.Tensor, sel, stride: int) -> torch.Tensor:
+        """Fused data loss over the whole (global) grid: `mse_loss(states[sel][:, :, ::s, ::s, ::s], truth_sub)` with
+        `target_sub` this rank's slab of the low-res truth, [nsel, 2, nz/s, ceil(H/s), ceil(W/s)].  Each rank reduces
+        its sampled points (percnn_data_loss_fwd), one scalar all-reduce adds them up."""
+        nsteps = tape.shape[0] - 1
+        spec = self._loss_spec(nsteps, sel, stride)
+        part = self.plan.data_loss_fwd(tape, nsteps, spec, target_sub)
+        if self.world > 1:
+            dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group)
+        return part
+
+    def backward(self, tape: torch.Tensor, g_tape: Optional[torch.Tensor] = None, *, loss=None):
         """Back-propagate through the taped rollout.  g_tape[t] = dL/d(tape[t]) in the same ghosted layout (what
-        autograd returns for a loss computed on tape[:, :, 2:-2]); ghost entries are ignored.
+        autograd returns for a loss computed on tape[:, :, 2:-2]); ghost entries are ignored.  `loss` =
+        (target_sub, sel, stride, gscale) adds the fused data loss of `data_loss()` as a gradient source: its
+        gradient is injected inside the adjoint kernel of each selected step, so cfg5-sized training needs no dense
+        gradient tape at all (g_tape=None).
         Returns (dL/dh0 interior [2, nz, H, W], flat parameter gradient summed over all ranks)."""
         if self.transport != "fused":
             raise NotImplementedError("backward needs the fused peer-memory transport")
         nsteps = tape.shape[0] - 1
         nz = self.nz
         plan = self.plan
+        spec = target_sub = gscale = None
+        if loss is not None:
+            target_sub, sel, stride, gscale = loss
+            spec = self._loss_spec(nsteps, sel, stride)
+            if gscale is not None:
+                gscale = torch.as_tensor(gscale, dtype=torch.float32, device=self.device).reshape(1)
+            want = (spec.nsel, *plan.lowres_shape(spec.stride))
+            if tuple(target_sub.shape) != want or target_sub.dtype != torch.float32 or not target_sub.is_contiguous():
+                raise ValueError(f"loss target: need contiguous float32 {want}, got {tuple(target_sub.shape)}")
+        elif g_tape is None:
+            raise ValueError("backward needs g_tape and/or loss")
         plan.params_load(self.flat)
         plan.param_grads_begin()
         # G_nsteps = dL/dh_nsteps with exchanged ghosts, in the peer-mapped ping-pong buffers
         b = 0
         self.bufs[b].zero_()
-        self.bufs[b][:, 2:nz + 2].copy_(g_tape[nsteps][:, 2:nz + 2])
+        if g_tape is not None:
+            self.bufs[b][:, 2:nz + 2].copy_(g_tape[nsteps][:, 2:nz + 2])
         self._exchange_blocking(b)
         self._words[0:2].fill_(self.epoch)
         self._words[2:4].zero_()
         torch.cuda.synchronize(self.device)
         dist.barrier(self.group)
+        slot = spec.nsel if spec is not None else 0
         for t in range(nsteps - 1, -1, -1):
             nxt = b ^ 1
             link = self._link(self.peer_lo[nxt].data_ptr(), self.peer_hi[nxt].data_ptr())
-            plan.step_bwd_fused_halo(tape[t], self.bufs[b], self.bufs[nxt], link, g_add=g_tape[t])
+            frame = None
+            if spec is not None and spec.sel[t]:
+                slot -= 1
+                frame = target_sub[slot]
+            plan.step_bwd_loss(tape[t], self.bufs[b], self.bufs[nxt], target_frame=frame,
+                               stride=spec.stride if frame is not None else 1,
+                               n_total=spec.n_total if frame is not None else 0, gscale=gscale,
+                               g_add=None if g_tape is None else g_tape[t], link=link)
             self.epoch += 1
             b = nxt
         g_h0 = self.bufs[b][:, 2:nz + 2].clone()

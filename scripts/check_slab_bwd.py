@@ -55,11 +55,29 @@ def rel(a_, b_):
 e_h0 = rel(g_h0, h0.grad[0, :, z0:z0 + nz])
 e_p = rel(grads, ref_flat)
 e_loss = abs(float(loss) - float(ref_loss)) / abs(float(ref_loss))
-worst = torch.tensor([e_h0, e_p, e_loss, float(slab.error_word())], device=dev, dtype=torch.float64)
+# ---- the same training step with the FUSED data loss (no dense gradient tape): frames 0, 2, 4, ... < steps, stride 2
+sel = [(t % 2 == 0) and t < a.steps for t in range(a.steps + 1)]
+frames = [t for t in range(a.steps + 1) if sel[t]]
+truth_sub = target[frames][:, :, ::2, ::2, ::2].contiguous()                    # global low-res truth
+slab.set_state(full[:, z0:z0 + nz])
+tape = slab.rollout_tape(a.steps)
+local_truth = truth_sub[:, :, z0 // 2:(z0 + nz) // 2].contiguous()
+f_loss = slab.data_loss(tape, local_truth, sel, 2)
+f_g_h0, f_grads = slab.backward(tape, None, loss=(local_truth, sel, 2, torch.tensor(3.0, device=dev)))
+for p_ in cell.parameters():
+    p_.grad = None
+h0f = full[None].clone().requires_grad_(True)
+_, ref_f_loss = cell.rollout_data_loss(h0f, a.steps, truth_sub, sel, 2)
+(3.0 * ref_f_loss).backward()
+ref_f_flat = engine.pack_params([p.grad if p.grad is not None else torch.zeros_like(p) for p in cell._packed_tensors()], torch.float32)
+e_fused = max(rel(f_g_h0, h0f.grad[0, :, z0:z0 + nz]), rel(f_grads, ref_f_flat),
+              abs(float(f_loss) - float(ref_f_loss)) / abs(float(ref_f_loss)))
+
+worst = torch.tensor([e_h0, e_p, max(e_loss, e_fused), float(slab.error_word())], device=dev, dtype=torch.float64)
 dist.all_reduce(worst, op=dist.ReduceOp.MAX)
 if rank == 0:
     ok = worst[0] < 1e-5 and worst[1] < 1e-5 and worst[2] < 1e-5 and worst[3] == 0
-    print(f"SLAB_BWD_CHECK world={world} shape={shape} steps={a.steps}: loss rel {worst[2]:.2e}  dL/dh0 rel {worst[0]:.2e}  "
+    print(f"SLAB_BWD_CHECK world={world} shape={shape} steps={a.steps}: loss/fused-loss rel {worst[2]:.2e}  dL/dh0 rel {worst[0]:.2e}  "
           f"param-grad rel {worst[1]:.2e}  device_error_word={int(worst[3])}  ok={bool(ok)}", flush=True)
 dist.barrier()
 dist.destroy_process_group()

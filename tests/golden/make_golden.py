@@ -163,6 +163,55 @@ def make_case(alias, shape, nstep, seed, tag=None, amp=(0.1, 0.9)):
           f"{os.path.getsize(os.path.join(OUT, name)) / 1024:.0f} KiB")
 
 
+def make_data_loss_case(alias, shape, nstep, seed, t_stride, s_stride, first_frames=None, tag=None, amp=(0.1, 0.9)):
+    """The scripts' data loss through the reference's own cell, loop and nn.MSELoss (GS3D:394-403, GS2D:394-401,
+    BUR1:606-614): loss = mse_loss(cat(outputs)[0:-1:t, :, ::s, ::s(, ::s)][:first_frames], truth_sub), and its
+    autograd gradients w.r.t. the initial state and every trainable parameter."""
+    mod = load_reference_module(alias)
+    cell = build_cell(alias, mod)
+    dtype = mod._default_dtype
+    if alias in ("bur3", "lo3", "lo3n"):
+        g = torch.Generator().manual_seed(seed + 100)
+        with torch.no_grad():
+            for n, prm in cell.named_parameters():
+                if prm.requires_grad:
+                    prm.add_(0.05 * (torch.rand((), generator=g, dtype=torch.float64) - 0.5))
+    h0 = smooth_state(shape, seed, dtype, *amp).requires_grad_(True)
+    outputs, _ = reference_rollout(cell, h0, nstep, list(range(nstep)))
+    output = torch.cat(tuple(outputs), dim=0)
+    sub = (slice(None), slice(None)) + (slice(None, None, s_stride),) * len(shape)
+    pred = output[0:-1:t_stride][sub]
+    if first_frames is not None:
+        pred = pred[:first_frames]
+    g = torch.Generator().manual_seed(seed + 9)
+    truth_sub = (pred.detach().double() + 0.05 * torch.randn(pred.shape, generator=g, dtype=torch.float64)).to(dtype)
+    loss = torch.nn.MSELoss()(pred, truth_sub)
+    (3.0 * loss).backward()           # a non-unit upstream gradient, like `10*loss_data` in GS3D:407
+    frames = list(range(0, nstep, t_stride))[:first_frames]
+    rec = {"h0": h0.detach().numpy(), "traj": output.detach().numpy(), "truth_sub": truth_sub.numpy(),
+           "loss": np.array(loss.item()), "gscale": np.array(3.0), "g_h0": h0.grad.numpy(), "nstep": np.array(nstep),
+           "t_stride": np.array(t_stride), "s_stride": np.array(s_stride), "frames": np.array(frames),
+           "first_frames": np.array(-1 if first_frames is None else first_frames), "dtype": np.array(str(dtype))}
+    for k, v in cell_state(cell).items():
+        rec["param/" + k] = v.numpy()
+    for n, prm in cell.named_parameters():
+        if prm.requires_grad:
+            rec["grad/" + n] = prm.grad.numpy()
+    name = f"dloss_{tag or alias}.npz"
+    np.savez_compressed(os.path.join(OUT, name), **rec)
+    print(f"{name}: shape={tuple(h0.shape)} steps={nstep} frames={frames} stride={s_stride} loss={loss.item():.6g} "
+          f"{os.path.getsize(os.path.join(OUT, name)) / 1024:.0f} KiB")
+
+
+def make_data_loss_cases():
+    make_data_loss_case("gs2d", (22, 26), 9, 21, 4, 4, first_frames=2)
+    make_data_loss_case("gs3d", (6, 8, 12), 7, 22, 3, 2)
+    make_data_loss_case("gs3d", (8, 16, 128), 4, 23, 2, 2, tag="gs3d_tma")
+    make_data_loss_case("bur1", (16, 20), 6, 24, 5, 2, amp=(-0.5, 0.5))
+    make_data_loss_case("bur3", (20, 24), 6, 25, 5, 2, amp=(-0.5, 0.5))
+    make_data_loss_case("lo3", (20, 24), 6, 26, 5, 2, amp=(-0.8, 0.8))
+
+
 def make_weights():
     """Cell weights of the shipped checkpoints at full size (bench + full-size property tests)."""
     for alias in CHECKPOINTS:
@@ -195,6 +244,9 @@ def make_rcnn_case():
 
 if __name__ == "__main__":
     torch.set_num_threads(1)  # oneDNN summation order depends on the thread count
+    if "--data-loss-only" in sys.argv:
+        make_data_loss_cases()
+        sys.exit(0)
     make_case("fwd", (20, 24), 6, 11, amp=(-0.8, 0.8))
     make_case("gs2d", (20, 24), 6, 12)
     make_case("gs3d", (6, 8, 12), 5, 13)
@@ -206,3 +258,4 @@ if __name__ == "__main__":
     make_case("lo3n", (20, 24), 6, 19, amp=(-0.8, 0.8))
     make_weights()
     make_rcnn_case()
+    make_data_loss_cases()

@@ -20,6 +20,17 @@ def load_golden(tag):
     return z, params, grads
 
 
+#: data-loss golden tag -> oracle variant name (tests/golden/dloss_*.npz, make_golden.make_data_loss_case)
+DLOSS_CASES = {"gs2d": "gs2d", "gs3d": "gs3d", "gs3d_tma": "gs3d", "bur1": "bur1", "bur3": "bur3", "lo3": "lo3"}
+
+
+def load_dloss(tag):
+    z = np.load(os.path.join(GOLDEN, f"dloss_{tag}.npz"))
+    params = {k[len("param/"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("param/")}
+    grads = {k[len("grad/"):]: z[k] for k in z.files if k.startswith("grad/")}
+    return z, params, grads
+
+
 def load_weights(alias):
     z = np.load(os.path.join(GOLDEN, f"weights_{alias}.npz"))
     return {k: torch.from_numpy(z[k]) for k in z.files}

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import percnn_oracle as po
-from tests.helpers import GOLDEN_CASES, load_golden, rel_l2, rel_linf
+from tests.helpers import DLOSS_CASES, GOLDEN_CASES, load_dloss, load_golden, rel_l2, rel_linf
 
 
 @pytest.mark.parametrize("tag", list(GOLDEN_CASES))
@@ -73,6 +73,44 @@ def test_torch_autograd_of_oracle_matches_reference_grads():
     assert rel_l2(h0.grad.numpy(), z["g_h0"]) <= 1e-5
     for k, ref in grads.items():
         assert rel_l2(p[k].grad.numpy(), ref) <= 2e-4, k
+
+
+@pytest.mark.parametrize("tag", list(DLOSS_CASES))
+def test_data_loss_restatement_matches_reference(tag):
+    """Frame selection, loss value and gradient of the scripts' data loss (GS3D:394-403 and siblings) against the
+    reference's own loop + nn.MSELoss + autograd; the gradient goes through the hand-derived adjoint with the loss
+    gradient injected at the selected states -- the scheme the fused kernels implement."""
+    z, params, grads = load_dloss(tag)
+    variant = DLOSS_CASES[tag]
+    nstep, ts, ss, ff = int(z["nstep"]), int(z["t_stride"]), int(z["s_stride"]), int(z["first_frames"])
+    frames = po.data_loss_frames(nstep, range(nstep), ts, None if ff < 0 else ff)
+    assert frames == [int(f) for f in z["frames"]]
+    traj = z["traj"].astype(np.float64)
+    fp64 = z["h0"].dtype == np.float64
+    loss = po.data_loss_np(traj, z["truth_sub"], frames, ss)
+    assert abs(loss - float(z["loss"])) <= (1e-12 if fp64 else 2e-6) * abs(float(z["loss"]))
+    gl = po.data_loss_grad_np(traj, z["truth_sub"], frames, ss, float(z["gscale"]))
+    assert np.count_nonzero(gl[nstep]) == 0          # `[0:-1:...]` never selects the last (dummy) state
+    G = gl[nstep:nstep + 1].copy()
+    acc = {}
+    for t in range(nstep - 1, -1, -1):
+        G, pg = po.cell_step_vjp_np(traj[t:t + 1], G, params, variant)
+        G = G + gl[t:t + 1]
+        for k, v in pg.items():
+            acc[k] = acc.get(k, 0) + v
+    tol = 1e-10 if fp64 else 3e-4
+    assert rel_l2(G, z["g_h0"]) <= tol
+    for k, ref in grads.items():
+        assert rel_l2(np.asarray(acc[k]).reshape(ref.shape), ref) <= tol, k
+
+
+def test_data_loss_frames_follow_effective_step():
+    """`outputs` only holds the effective steps, so list index != state index in general (GS3D:191-212)."""
+    assert po.data_loss_frames(7, [0, 2, 3, 6], 2) == [0, 3]          # outputs = h0 h1 h3 h4 h7 -> [0:-1:2] = h0 h3
+    assert po.data_loss_frames(6, range(6), 5) == [0, 5]
+    assert po.data_loss_frames(30, range(30), 15) == [0, 15]
+    assert po.data_loss_frames(31, range(31), 15) == [0, 15, 30]
+    assert po.data_loss_frames(9, range(9), 4, first_frames=2) == [0, 4]
 
 
 def test_stencil_tables_match_reference_weights():
