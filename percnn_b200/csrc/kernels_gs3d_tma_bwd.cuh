@@ -125,36 +125,35 @@ __device__ __forceinline__ void adjoint_plane(Consumer& c, const float* __restri
 #undef PERCNN_BWD_PAIR
   if (MONO && valid) {
     // 20 monomial sums  sum G_f u^a v^b  for this lane's 4 cells, added to per-lane accumulators in shared memory
-    // (keeping them in registers next to the stencil state spilled); (G_u, G_v) is the packed FFMA2 operand.
-    const float us[4] = {hu.x, hu.y, hu.z, hu.w}, vs[4] = {hv.x, hv.y, hv.z, hv.w};
-    const float2 g[4] = {make_float2(Gu.x, Gv.x), make_float2(Gu.y, Gv.y), make_float2(Gu.z, Gv.z), make_float2(Gu.w, Gv.w)};
-    float uu[4], uv[4], vv[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uu[j] = us[j] * us[j];
-      uv[j] = us[j] * vs[j];
-      vv[j] = vs[j] * vs[j];
-    }
-#define PERCNN_MONO(M, E0, E1, E2, E3)                                                              \
+    // (keeping them in registers next to the stencil state spilled).  Everything stays in the NATURAL register pairs
+    // of the 128-bit loads -- (cell0, cell1) and (cell2, cell3) -- so that no operand has to be re-packed: monomials
+    // by FMUL2, products by FMUL2/FFMA2, then one FADD per field folds the pair and (sum_u, sum_v) is the float2
+    // that is accumulated.  (Packing (G_u, G_v) per cell instead cost ~80 MOVs per plane: ncu r01b_ncu_bwd_512.)
+    const float2 ul = lo(hu), uh = hi(hu), vl = lo(hv), vh = hi(hv);
+    const float2 gul = lo(Gu), guh = hi(Gu), gvl = lo(Gv), gvh = hi(Gv);
+    const float2 uul = __fmul2_rn(ul, ul), uuh = __fmul2_rn(uh, uh);
+    const float2 uvl = __fmul2_rn(ul, vl), uvh = __fmul2_rn(uh, vh);
+    const float2 vvl = __fmul2_rn(vl, vl), vvh = __fmul2_rn(vh, vh);
+#define PERCNN_MONO(M, EL, EH)                                                                      \
   {                                                                                                 \
-    float2 t = macc[M * BWD_THREADS];                                                               \
-    t = fma2(g[0], E0, t); t = fma2(g[1], E1, t); t = fma2(g[2], E2, t); t = fma2(g[3], E3, t);     \
-    macc[M * BWD_THREADS] = t;                                                                      \
+    const float2 el = EL, eh = EH;                                                                  \
+    const float2 tu = fma2(guh, eh, __fmul2_rn(gul, el));                                           \
+    const float2 tv = fma2(gvh, eh, __fmul2_rn(gvl, el));                                           \
+    macc[M * BWD_THREADS] = __fadd2_rn(macc[M * BWD_THREADS], make_float2(tu.x + tu.y, tv.x + tv.y)); \
   }
     {
-      float2 t = macc[0];
-      t = __fadd2_rn(t, __fadd2_rn(__fadd2_rn(g[0], g[1]), __fadd2_rn(g[2], g[3])));
-      macc[0] = t;
+      const float2 tu = __fadd2_rn(gul, guh), tv = __fadd2_rn(gvl, gvh);
+      macc[0] = __fadd2_rn(macc[0], make_float2(tu.x + tu.y, tv.x + tv.y));
     }
-    PERCNN_MONO(1, us[0], us[1], us[2], us[3])
-    PERCNN_MONO(2, vs[0], vs[1], vs[2], vs[3])
-    PERCNN_MONO(3, uu[0], uu[1], uu[2], uu[3])
-    PERCNN_MONO(4, uv[0], uv[1], uv[2], uv[3])
-    PERCNN_MONO(5, vv[0], vv[1], vv[2], vv[3])
-    PERCNN_MONO(6, uu[0] * us[0], uu[1] * us[1], uu[2] * us[2], uu[3] * us[3])
-    PERCNN_MONO(7, uu[0] * vs[0], uu[1] * vs[1], uu[2] * vs[2], uu[3] * vs[3])
-    PERCNN_MONO(8, us[0] * vv[0], us[1] * vv[1], us[2] * vv[2], us[3] * vv[3])
-    PERCNN_MONO(9, vv[0] * vs[0], vv[1] * vs[1], vv[2] * vs[2], vv[3] * vs[3])
+    PERCNN_MONO(1, ul, uh)
+    PERCNN_MONO(2, vl, vh)
+    PERCNN_MONO(3, uul, uuh)
+    PERCNN_MONO(4, uvl, uvh)
+    PERCNN_MONO(5, vvl, vvh)
+    PERCNN_MONO(6, __fmul2_rn(uul, ul), __fmul2_rn(uuh, uh))
+    PERCNN_MONO(7, __fmul2_rn(uul, vl), __fmul2_rn(uuh, vh))
+    PERCNN_MONO(8, __fmul2_rn(ul, vvl), __fmul2_rn(uh, vvh))
+    PERCNN_MONO(9, __fmul2_rn(vvl, vl), __fmul2_rn(vvh, vh))
 #undef PERCNN_MONO
   }
   if (inj_row >= 0) {
@@ -335,9 +334,8 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
     int xs = (lane == 0) ? ic.x0 - 2 : ic.x0 + TX;
     xs = xs < 0 ? xs + p.W : (xs >= p.W ? xs - p.W : xs);
     const int seam_off = warp * p.W + xs - ic.x0;
-    int pz = src_plane(p, ic.z0, 2);
-    const float* seam_ptr = src_xy + int64_t(pz) * plane + seam_off;
-    const int64_t wrap_back = int64_t(p.D) * plane;
+    // seam cells come from planes [z0, z0 + nz) of the item itself: no periodic wrap needed (see the forward kernel)
+    const float* seam_ptr = src_xy + int64_t(src_plane(p, ic.z0, 2)) * plane + seam_off;
 
     const int nk = ic.nz + 4;   // local planes 0 .. nz+3 arrive in order; output plane k-2 is produced when plane k lands
     for (int k = 0; k < nk; ++k) {
@@ -349,10 +347,6 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
         }
       } else {
         seam_ptr += plane;
-        if (p.wrap_z && ++pz >= p.D) {
-          pz -= p.D;
-          seam_ptr -= wrap_back;
-        }
         int64_t inj_row = -1;
         if (inj_ly >= 0) {
           const int zg = ic.z0 + k - 4;   // interior index of the output plane

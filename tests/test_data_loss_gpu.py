@@ -197,7 +197,8 @@ def test_rcnn_forward_data_loss_drop_in():
         res.append((loss.item(), torch.cat(tuple(outputs), 0).detach().cpu().numpy(), second_last.detach().cpu().numpy(),
                     {k: p.grad.cpu().numpy() for k, p in model.named_parameters() if p.grad is not None}))
     assert abs(res[0][0] - res[1][0]) <= 2e-6 * abs(res[1][0])
-    assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
+    # (two model instances: the stock cuDNN transposed convs of the upscaler are not bit-reproducible across calls)
+    assert rel_l2(res[0][1], res[1][1]) <= 1e-6 and rel_l2(res[0][2], res[1][2]) <= 1e-6
     assert set(res[0][3]) == set(res[1][3]) and any(k.startswith("UpconvBlock") for k in res[0][3])
     for k in res[1][3]:
         assert rel_l2(res[0][3][k], res[1][3][k]) <= 2e-5, k
