@@ -193,6 +193,36 @@ int percnn_rollout_bwd_loss(percnn_plan_t* plan, const void* params, const void*
                             const uint8_t* gmask, const percnn_data_loss_t* loss, int nsteps, void* g_h0,
                             void* param_grads, void* ws, void* stream);
 
+/* ---- fused physics-residual loss ------------------------------------------ */
+/* `loss_gen(output, loss_generator(dt, dx))` of the scripts (FWD:288-357, the TRAINING loss of the forward-simulation
+ * script FWD:371-373; GS2D:270-353 and GS3D:286-345, where it is a validation metric):
+ *     f_q = D_q * Lap(q_t) + R_q(u_t, v_t) - (q_{t+1} - q_t) / dt,   loss = mse(f_u, 0) + mse(f_v, 0)
+ * over frames t = 0 .. nframes-3, with the 4th-order Laplacian / dx^2 on the periodic grid.  The reference pads 2
+ * cells before and 3 after every axis, so each axis contributes extent + 1 residual points, the last being the
+ * periodic image of the first; that double counting is reproduced exactly (weights, N = (nframes-2) prod(extent+1)).
+ * R_q is a bivariate cubic (lambda-omega: FWD:338-339, Gray-Scott: GS2D:322-328, GS3D:319-326).
+ * Stand-alone (no plan): works on any [nframes][2][(D,)H,W] contiguous device tensor. */
+typedef struct percnn_phys_loss {
+  int32_t ndim;          /* 2 | 3 */
+  int32_t dtype;         /* percnn_dtype_t */
+  int64_t extent[3];     /* D, H, W (2-D: extent[0] = 1) */
+  int32_t nframes;       /* frames in `frames` (>= 3); consecutive frames are one time step dt apart */
+  int32_t device;
+  double diff[2];        /* D_u, D_v */
+  double poly[2][10];    /* R_u, R_v as cubics in (u, v): c00 c10 c01 c20 c11 c02 c30 c21 c12 c03 */
+  double dt;             /* FWD:283-286 */
+  double dx;             /* FWD:276-280: Laplacian table / dx^2 */
+} percnn_phys_loss_t;
+size_t percnn_phys_loss_workspace_bytes(void);
+/* loss -> *loss_out (device scalar of `dtype`).  `resid` (nullable): [nframes-2] frames receiving dloss/df, needed
+ * by percnn_phys_loss_bwd.  `ws`: percnn_phys_loss_workspace_bytes() of device scratch. */
+int percnn_phys_loss_fwd(const percnn_phys_loss_t* pl, const void* frames, void* resid, void* loss_out, void* ws,
+                         void* stream);
+/* g_frames[t] = gscale * dloss/dframes[t] for every frame (dense; the last frame's gradient is zero).
+ * `gscale`: device scalar of `dtype` (NULL = 1). */
+int percnn_phys_loss_bwd(const percnn_phys_loss_t* pl, const void* frames, const void* resid, const void* gscale,
+                         void* g_frames, void* stream);
+
 /* ---- host-buffer convenience (end-to-end path) ------------------------------------------------ */
 /* Same as params_load + rollout_fwd but with HOST pointers: copies params and h0 to the device, runs the
  * rollout, copies the emitted frames (and h_final if non-NULL) back, blocks until done.  Scratch is

@@ -507,6 +507,94 @@ def data_loss_grad_np(states, target, frames: Sequence[int], stride: int, gscale
 
 
 # --------------------------------------------------------------------------------------
+# Physics-residual loss of the training scripts, restated
+# --------------------------------------------------------------------------------------
+
+#: PDE constants hard-coded in each script's get_phy_Loss and loss_generator defaults
+PHYS_CONSTS = {
+    "fwd": dict(kind="lo", D=(0.1, 0.1), dt=0.0125, dx=0.2),                                  # FWD:268, 337-340
+    "gs2d": dict(kind="gs", D=(2e-5, 2e-5 / 4), f=1 / 25, k=3 / 50, dt=1.0 / 2, dx=1.0 / 100),  # GS2D:244, 321-328
+    "gs3d": dict(kind="gs", D=(0.2, 0.1), f=0.025, k=0.055, dt=0.5, dx=100 / 48),             # GS3D:267, 319-326
+}
+
+
+def _phys_reaction(kind, c, u, v):
+    if kind == "lo":
+        a = u * u + v * v
+        return (1 - a) * u + a * v, -a * u + (1 - a) * v
+    return -u * v * v + c["f"] * (1 - u), u * v * v - (c["f"] + c["k"]) * v
+
+
+def phys_loss_torch(output: torch.Tensor, variant: str) -> torch.Tensor:
+    """`loss_gen(output, loss_generator())` (FWD:288-357 and siblings) as the same sequence of steps on the
+    un-padded trajectory [T, 2, ...]: periodic pad (2 before, 3 after), valid Laplacian of frames 0..T-3 on
+    extent+1 points, forward time difference, PDE residual, mse(f_u, 0) + mse(f_v, 0).  Differentiable."""
+    c = PHYS_CONSTS[variant]
+    nd = output.dim() - 2
+    pad = output
+    for ax in range(2 + nd - 1, 1, -1):     # FWD:349-350: last axis first
+        n = pad.shape[ax]
+        pad = torch.cat((pad.narrow(ax, n - 2, 2), pad, pad.narrow(ax, 0, 3)), dim=ax)
+    w = torch.tensor(laplace_stencil(nd), dtype=output.dtype) / c["dx"] ** 2
+    conv = torch.nn.functional.conv2d if nd == 2 else torch.nn.functional.conv3d
+    inner = (slice(None), slice(None)) + (slice(2, -2),) * nd
+    lap_u = conv(pad[0:-2, 0:1], w)
+    lap_v = conv(pad[0:-2, 1:2], w)
+    q = pad[inner]
+    q_t = (q[1:-1] - q[:-2]) / c["dt"]          # Conv1d([-1, 1, 0]) / dt over time (FWD:283-286, 324-327)
+    u, v = q[0:-2, 0:1], q[0:-2, 1:2]
+    ru, rv = _phys_reaction(c["kind"], c, u, v)
+    f_u = c["D"][0] * lap_u + ru - q_t[:, 0:1]
+    f_v = c["D"][1] * lap_v + rv - q_t[:, 1:2]
+    return (f_u ** 2).mean() + (f_v ** 2).mean()
+
+
+def phys_loss_np(output, variant: str):
+    """Independent numpy/fp64 version written from the maths on the PERIODIC grid: residual by np.roll, the
+    (2, 3) padding's double counting as the weight w(x) = prod_axes (1 + [x_axis == 0]).  Returns
+    (loss, dloss/doutput)."""
+    c = PHYS_CONSTS[variant]
+    o = np.asarray(output, dtype=np.float64)
+    T, nd = o.shape[0], o.ndim - 2
+    taps = np.array([-1 / 12, 4 / 3, -5 / 2, 4 / 3, -1 / 12]) / c["dx"] ** 2
+
+    def lap(a):      # a: [t, ...spatial]
+        r = np.zeros_like(a)
+        for ax in range(1, 1 + nd):
+            for off, wgt in zip(range(-2, 3), taps):
+                r += wgt * np.roll(a, -off, axis=ax)
+        return r
+
+    u, v = o[:-2, 0], o[:-2, 1]
+    ru, rv = _phys_reaction(c["kind"], c, u, v)
+    fu = c["D"][0] * lap(u) + ru - (o[1:-1, 0] - u) / c["dt"]
+    fv = c["D"][1] * lap(v) + rv - (o[1:-1, 1] - v) / c["dt"]
+    w = np.ones(o.shape[2:])
+    n = T - 2
+    for ax, ext in enumerate(o.shape[2:]):
+        n *= ext + 1
+        idx = [slice(None)] * nd
+        idx[ax] = 0
+        w[tuple(idx)] *= 2
+    loss = float((w * (fu ** 2 + fv ** 2)).sum() / n)
+    # gradient: R = 2 w f / N; d/dq_t = D Lap(R_q[t]) + J^T R[t] + R_q[t]/dt - R_q[t-1]/dt
+    Ru, Rv = 2 * w * fu / n, 2 * w * fv / n
+    if c["kind"] == "lo":
+        a = u * u + v * v
+        ruu, ruv = (1 - a) - 2 * u * u + 2 * u * v, -2 * u * v + a + 2 * v * v
+        rvu, rvv = -a - 2 * u * u - 2 * u * v, -2 * u * v + (1 - a) - 2 * v * v
+    else:
+        ruu, ruv = -v * v - c["f"], -2 * u * v
+        rvu, rvv = v * v, 2 * u * v - (c["f"] + c["k"])
+    g = np.zeros_like(o)
+    g[:-2, 0] += c["D"][0] * lap(Ru) + ruu * Ru + rvu * Rv + Ru / c["dt"]
+    g[:-2, 1] += c["D"][1] * lap(Rv) + ruv * Ru + rvv * Rv + Rv / c["dt"]
+    g[1:-1, 0] -= Ru / c["dt"]
+    g[1:-1, 1] -= Rv / c["dt"]
+    return loss, g
+
+
+# --------------------------------------------------------------------------------------
 # Synthetic initial states of SURVEY 8d (seeded, periodic-safe) -- shared by tests and bench.
 # --------------------------------------------------------------------------------------
 

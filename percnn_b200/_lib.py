@@ -27,6 +27,7 @@ EXPORTS = (
     "percnn_step_fwd_fused_halo", "percnn_step_bwd_fused_halo", "percnn_step_bwd",
     "percnn_param_grads_begin", "percnn_param_grads_finish", "percnn_rollout_fwd", "percnn_rollout_bwd",
     "percnn_rollout_fwd_host", "percnn_data_loss_fwd", "percnn_step_bwd_loss", "percnn_rollout_bwd_loss",
+    "percnn_phys_loss_workspace_bytes", "percnn_phys_loss_fwd", "percnn_phys_loss_bwd",
 )
 
 
@@ -52,6 +53,14 @@ class DataLoss(ctypes.Structure):
     _fields_ = [
         ("target", c_void_p), ("sel", POINTER(c_uint8)), ("stride", c_int32), ("reserved", c_int32),
         ("n_total", c_int64), ("gscale", c_void_p),
+    ]
+
+
+class PhysLoss(ctypes.Structure):
+    """percnn_phys_loss_t"""
+    _fields_ = [
+        ("ndim", c_int32), ("dtype", c_int32), ("extent", c_int64 * 3), ("nframes", c_int32), ("device", c_int32),
+        ("diff", c_double * 2), ("poly", (c_double * 10) * 2), ("dt", c_double), ("dx", c_double),
     ]
 
 
@@ -100,6 +109,9 @@ def lib() -> ctypes.CDLL:
     L.percnn_data_loss_fwd.argtypes = [vp, vp, c_int, POINTER(DataLoss), vp, vp, vp]
     L.percnn_step_bwd_loss.argtypes = [vp, vp, vp, vp, vp, c_int, c_int64, vp, vp, vp, POINTER(SlabLink), vp]
     L.percnn_rollout_bwd_loss.argtypes = [vp, vp, vp, vp, POINTER(c_uint8), POINTER(DataLoss), c_int, vp, vp, vp, vp]
+    L.percnn_phys_loss_workspace_bytes.restype = c_size_t
+    L.percnn_phys_loss_fwd.argtypes = [POINTER(PhysLoss), vp, vp, vp, vp, vp]
+    L.percnn_phys_loss_bwd.argtypes = [POINTER(PhysLoss), vp, vp, vp, vp, vp]
     if L.percnn_abi_version() != ABI_VERSION:
         raise ImportError(f"{LIB_PATH}: ABI version {L.percnn_abi_version()} != {ABI_VERSION}; rebuild the library")
     _lib = L

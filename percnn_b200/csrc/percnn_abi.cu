@@ -10,6 +10,7 @@
 #include "kernels_generic.cuh"
 #include "kernels_gs3d_tma.cuh"
 #include "kernels_gs3d_tma_bwd.cuh"
+#include "kernels_phys_loss.cuh"
 #include "kernels_pi_k5.cuh"
 #include "kernels_prep.cuh"
 
@@ -984,6 +985,122 @@ int percnn_rollout_bwd_loss(percnn_plan_t* p, const void* params, const void* ta
     G = gin;
   }
   return percnn_param_grads_finish(p, params, param_grads, ws, stream);
+}
+
+// ---- fused physics-residual loss (kernels_phys_loss.cuh) ------------------------------------------------
+extern "C++" {
+namespace {
+int phys_check(const percnn_phys_loss_t* pl, Geom* g) {
+  if (!pl) return fail(PERCNN_ERR_INVALID, "null physics-loss descriptor");
+  if (pl->ndim != 2 && pl->ndim != 3) return fail(PERCNN_ERR_INVALID, "ndim must be 2 or 3");
+  if (pl->dtype != PERCNN_F32 && pl->dtype != PERCNN_F64) return fail(PERCNN_ERR_INVALID, "dtype must be f32 or f64");
+  if (pl->extent[0] < 1 || pl->extent[1] < 1 || pl->extent[2] < 1 || pl->extent[0] > (1 << 20) ||
+      pl->extent[1] > (1 << 20) || pl->extent[2] > (1 << 20))
+    return fail(PERCNN_ERR_INVALID, "bad extents");
+  if (pl->ndim == 2 && pl->extent[0] != 1) return fail(PERCNN_ERR_INVALID, "2-D needs extent[0] == 1");
+  if (pl->nframes < 3) return fail(PERCNN_ERR_INVALID, "the physics loss needs at least 3 frames (FWD:318-319: output[0:-2])");
+  if (!(pl->dt > 0) || !(pl->dx > 0)) return fail(PERCNN_ERR_INVALID, "dt and dx must be positive");
+  if (!percnn_device_ok(pl->device)) return fail(PERCNN_ERR_NO_DEVICE, "no sm_100 CUDA device with this ordinal");
+  g->ndim = pl->ndim;
+  g->D = int(pl->extent[0]);
+  g->H = int(pl->extent[1]);
+  g->W = int(pl->extent[2]);
+  g->ghost = 0;
+  g->plane = pl->ndim == 3 ? int64_t(g->H) * g->W : g->W;
+  g->field = int64_t(g->D) * g->H * g->W;
+  return PERCNN_OK;
+}
+template <typename T>
+PhysLossDev<T> phys_dev(const percnn_phys_loss_t* pl, const Geom& g) {
+  PhysLossDev<T> d;
+  for (int q = 0; q < 2; ++q) {
+    d.diff[q] = T(pl->diff[q]);
+    for (int i = 0; i < 10; ++i) d.poly[q][i] = T(pl->poly[q][i]);
+    const double* c = pl->poly[q];   // c00 c10 c01 c20 c11 c02 c30 c21 c12 c03
+    const double du[6] = {c[1], 2 * c[3], c[4], 3 * c[6], 2 * c[7], c[8]};   // over 1 u v u^2 uv v^2
+    const double dv[6] = {c[2], c[4], 2 * c[5], c[7], 2 * c[8], 3 * c[9]};
+    for (int i = 0; i < 6; ++i) {
+      d.dpoly[2 * q + 0][i] = T(du[i]);
+      d.dpoly[2 * q + 1][i] = T(dv[i]);
+    }
+  }
+  d.inv_dt = T(1.0 / pl->dt);
+  const double t1[5] = {-1.0 / 12.0, 4.0 / 3.0, -5.0 / 2.0, 4.0 / 3.0, -1.0 / 12.0};   // FWD:18-22 along one axis
+  for (int i = 0; i < 5; ++i) d.tap[i] = T(t1[i] / (pl->dx * pl->dx));
+  double n = double(pl->nframes - 2);
+  n *= double(g.W + 1) * double(g.H + 1) * (g.ndim == 3 ? double(g.D + 1) : 1.0);
+  d.two_over_n = 2.0 / n;
+  d.nframes = pl->nframes;
+  d.stride = 2 * g.field;
+  return d;
+}
+int phys_grid(const Geom& g, int frames) {
+  int64_t blocks = (int64_t(g.D) * g.H * g.W * frames + kGenericThreads - 1) / kGenericThreads;
+  if (blocks > kMaxBlocks) blocks = kMaxBlocks;
+  return int(blocks < 1 ? 1 : blocks);
+}
+}  // namespace
+}  // extern "C++"
+
+size_t percnn_phys_loss_workspace_bytes(void) { return kWsPartials + size_t(kMaxBlocks) * sizeof(double); }
+
+int percnn_phys_loss_fwd(const percnn_phys_loss_t* pl, const void* frames, void* resid, void* loss_out, void* ws,
+                         void* stream) {
+  Geom g;
+  int rc = phys_check(pl, &g);
+  if (rc) return rc;
+  if (!frames || !loss_out || !ws) return fail(PERCNN_ERR_INVALID, "null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* w = static_cast<char*>(ws);
+  double* acc = reinterpret_cast<double*>(w + kWsAcc);
+  unsigned* counter = reinterpret_cast<unsigned*>(w + kWsCounter);
+  double* partials = reinterpret_cast<double*>(w + kWsPartials);
+  PERCNN_CUDA(cudaMemsetAsync(w, 0, kWsPartials, st));
+  const int grid = phys_grid(g, pl->nframes - 2);
+  if (pl->dtype == PERCNN_F32) {
+    const PhysLossDev<float> d = phys_dev<float>(pl, g);
+    if (g.ndim == 3)
+      k_phys_resid<float, 3><<<grid, kGenericThreads, 0, st>>>(g, d, static_cast<const float*>(frames), static_cast<float*>(resid), partials, counter, acc);
+    else
+      k_phys_resid<float, 2><<<grid, kGenericThreads, 0, st>>>(g, d, static_cast<const float*>(frames), static_cast<float*>(resid), partials, counter, acc);
+    PERCNN_CUDA(cudaGetLastError());
+    k_data_loss_finish<float><<<1, 32, 0, st>>>(acc, 0.5 * d.two_over_n, static_cast<float*>(loss_out));
+  } else {
+    const PhysLossDev<double> d = phys_dev<double>(pl, g);
+    if (g.ndim == 3)
+      k_phys_resid<double, 3><<<grid, kGenericThreads, 0, st>>>(g, d, static_cast<const double*>(frames), static_cast<double*>(resid), partials, counter, acc);
+    else
+      k_phys_resid<double, 2><<<grid, kGenericThreads, 0, st>>>(g, d, static_cast<const double*>(frames), static_cast<double*>(resid), partials, counter, acc);
+    PERCNN_CUDA(cudaGetLastError());
+    k_data_loss_finish<double><<<1, 32, 0, st>>>(acc, 0.5 * d.two_over_n, static_cast<double*>(loss_out));
+  }
+  PERCNN_CUDA(cudaGetLastError());
+  return PERCNN_OK;
+}
+
+int percnn_phys_loss_bwd(const percnn_phys_loss_t* pl, const void* frames, const void* resid, const void* gscale,
+                         void* g_frames, void* stream) {
+  Geom g;
+  int rc = phys_check(pl, &g);
+  if (rc) return rc;
+  if (!frames || !resid || !g_frames) return fail(PERCNN_ERR_INVALID, "null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = phys_grid(g, pl->nframes);
+  if (pl->dtype == PERCNN_F32) {
+    const PhysLossDev<float> d = phys_dev<float>(pl, g);
+    if (g.ndim == 3)
+      k_phys_grad<float, 3><<<grid, kGenericThreads, 0, st>>>(g, d, static_cast<const float*>(frames), static_cast<const float*>(resid), static_cast<const float*>(gscale), static_cast<float*>(g_frames));
+    else
+      k_phys_grad<float, 2><<<grid, kGenericThreads, 0, st>>>(g, d, static_cast<const float*>(frames), static_cast<const float*>(resid), static_cast<const float*>(gscale), static_cast<float*>(g_frames));
+  } else {
+    const PhysLossDev<double> d = phys_dev<double>(pl, g);
+    if (g.ndim == 3)
+      k_phys_grad<double, 3><<<grid, kGenericThreads, 0, st>>>(g, d, static_cast<const double*>(frames), static_cast<const double*>(resid), static_cast<const double*>(gscale), static_cast<double*>(g_frames));
+    else
+      k_phys_grad<double, 2><<<grid, kGenericThreads, 0, st>>>(g, d, static_cast<const double*>(frames), static_cast<const double*>(resid), static_cast<const double*>(gscale), static_cast<double*>(g_frames));
+  }
+  PERCNN_CUDA(cudaGetLastError());
+  return PERCNN_OK;
 }
 
 int percnn_rollout_fwd_host(percnn_plan_t* p, const void* params_host, const void* h0_host, void* traj_host,

@@ -3,7 +3,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .. import _lib
+from .. import _lib, losses
 from ..cells import FusedRCNN, PiCell
 
 
@@ -56,3 +56,15 @@ class RCNN(FusedRCNN):
         self.UpconvBlock = upscaler()
         self._setup(RCNNCell(input_channels=input_channels, hidden_channels=hidden_channels,
                              input_kernel_size=input_kernel_size), step, effective_step)
+
+
+class loss_generator(losses.LossGenerator):
+    """GS2D:241-330 `loss_generator(dt, dx)`: Gray-Scott residual with Du = 2e-5, Dv = Du/4, f = 1/25, k = 3/50."""
+
+    def __init__(self, dt=(1.0 / 2), dx=(1.0 / 100)):
+        super().__init__(losses.gray_scott_spec(2e-5, 2e-5 / 4, 1 / 25, 3 / 50, dt, dx))
+
+
+def loss_gen(output, loss_func):
+    """GS2D:340-353 on the un-padded trajectory (fused)."""
+    return loss_func(output)

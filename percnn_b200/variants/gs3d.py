@@ -3,7 +3,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .. import _lib
+from .. import _lib, losses
 from ..cells import FusedRCNN, PiCell
 
 
@@ -54,3 +54,16 @@ class RCNN(FusedRCNN):
         self.UpconvBlock = upscaler()
         self._setup(RCNNCell(input_channels=input_channels, hidden_channels=hidden_channels,
                              input_kernel_size=input_kernel_size), step, effective_step)
+
+
+class loss_generator(losses.LossGenerator):
+    """GS3D:264-327 `loss_generator(dt, dx)`: Gray-Scott residual with Du = 0.2, Dv = 0.1, f = 0.025, k = 0.055."""
+
+    def __init__(self, dt=0.5, dx=(100 / 48)):
+        super().__init__(losses.gray_scott_spec(0.2, 0.1, 0.025, 0.055, dt, dx))
+
+
+def loss_func(output, loss_generator):
+    """GS3D:334-345 on the un-padded trajectory (fused).  (The script names the function `loss_func` and the module
+    instance `loss_gen`.)"""
+    return loss_generator(output)

@@ -2,7 +2,7 @@
 import torch
 import torch.nn as nn
 
-from .. import _lib
+from .. import _lib, losses
 from ..cells import FusedRCNN, PiCell
 
 
@@ -42,3 +42,16 @@ class RCNN(FusedRCNN):
         fixed = {(k.replace("crnn_cell.", "rcnn_cell.", 1) if k.startswith("crnn_cell.") else k): v
                  for k, v in state_dict.items()}
         return super().load_state_dict(fixed, strict=strict, **kw)
+
+
+class loss_generator(losses.LossGenerator):
+    """FWD:265-342 `loss_generator(dt, dx)`: lambda-omega residual, 0.1 Lap + analytic reaction - d/dt."""
+
+    def __init__(self, dt=0.0125, dx=0.2):
+        super().__init__(losses.lambda_omega_spec(dt, dx))
+
+
+def loss_gen(output, loss_func):
+    """FWD:344-357: takes the UN-padded trajectory `torch.cat(outputs)`; padding, Laplacian, time difference,
+    reaction term and both MSEs happen inside one fused kernel (percnn_phys_loss_fwd)."""
+    return loss_func(output)

@@ -67,7 +67,51 @@ def train_case(name, tag, alias, shape, nsteps, lo=0.1, hi=0.9):
         print(f"{name:34s} f+b  FAILED: {str(e)[:120]}", flush=True)
 
 
+def train_fused_loss_case(name, tag, alias, shape, nsteps, lo=0.1, hi=0.9, tstride=5):
+    """Same training step as train_case but with the fused data loss (no dense gradient tape)."""
+    cell = make_cell(tag)
+    if alias:
+        cell.load_state_dict(load_weights(alias))
+    cell = cell.to(dev)
+    h0 = state(shape, cell.dtype, lo, hi).requires_grad_(True)
+    sel = [(s % tstride == 0) and s < nsteps for s in range(nsteps + 1)]
+    low = tuple((n + 1) // 2 for n in shape)
+    target = state(low, cell.dtype, lo, hi, seed=2).expand(sum(sel), *([-1] * (1 + len(shape)))).contiguous()
+
+    def step():
+        for p in cell.parameters():
+            p.grad = None
+        h0.grad = None
+        _, loss = cell.rollout_data_loss(h0, nsteps, target, sel, 2)
+        loss.backward()
+    ms = timed(step, reps=3)
+    ncell = int(np.prod(shape))
+    print(f"{name:34s} f+b* {nsteps:5d} steps: {ms:9.3f} ms  {ms/nsteps*1e3:8.2f} us/step  {nsteps/ms*1e3:10.0f} steps/s  "
+          f"{ncell*nsteps/ms/1e6:9.2f} Gcell-steps/s  (fused data loss)", flush=True)
+
+
+def train_phys_case(name, tag, alias, shape, nsteps, lo, hi):
+    """FWD:366-373: one epoch = rollout + physics-residual loss over the whole trajectory + backward."""
+    from percnn_b200.variants import gs2d, lambda_omega_fwd
+    mod = {"fwd": lambda_omega_fwd, "gs2d": gs2d}[tag]
+    cell = make_cell(tag)
+    if alias:
+        cell.load_state_dict(load_weights(alias))
+    cell = cell.to(dev)
+    h0 = state(shape, cell.dtype, lo, hi)
+    gen = mod.loss_generator()
+
+    def step():
+        for p in cell.parameters():
+            p.grad = None
+        out = cell.rollout(h0, nsteps)
+        mod.loss_gen(out, gen).backward()
+    ms = timed(step, reps=3)
+    print(f"{name:34s} f+b  {nsteps:5d} steps: {ms:9.3f} ms  {ms/nsteps*1e3:8.2f} us/step  (rollout + fused physics loss + adjoint)", flush=True)
+
+
 fwd_case("cfg1 lambda-omega 128^2 fp64", "fwd", "fwd", (128, 128), 200, -0.8, 0.8)
+train_phys_case("cfg1 lambda-omega 128^2 fp64 epoch", "fwd", "fwd", (128, 128), 200, -0.8, 0.8)
 fwd_case("cfg2 GS 256^2 fp32", "gs2d", "gs2d", (256, 256), 1000)
 fwd_case("cfg3i Burgers k5 512^2 fp32", "bur1", "bur1", (512, 512), 40, -0.5, 0.5)
 train_case("cfg3i Burgers k5 512^2 fp32", "bur1", "bur1", (512, 512), 40, -0.5, 0.5)
@@ -76,6 +120,7 @@ train_case("cfg3ii Burgers phys 512^2 fp64", "bur3", None, (512, 512), 40, -0.5,
 fwd_case("cfg4 GS3D 128^3 fp32", "gs3d", "gs3d", (128, 128, 128), 500)
 train_case("GS3D 128^3 fp32 (TMA adjoint)", "gs3d", "gs3d", (128, 128, 128), 20)
 train_case("GS3D 256^3 fp32 (TMA adjoint)", "gs3d", "gs3d", (256, 256, 256), 20)
+train_fused_loss_case("GS3D 256^3 fp32 (TMA adjoint)", "gs3d", "gs3d", (256, 256, 256), 20)
 train_case("GS2D 256^2 fp32", "gs2d", "gs2d", (256, 256), 200)
 fwd_case("ref-size GS3D 48^3", "gs3d", "gs3d", (48, 48, 48), 300)
 fwd_case("ref-size GS2D 100^2", "gs2d", "gs2d", (100, 100), 400)

@@ -212,6 +212,54 @@ def make_data_loss_cases():
     make_data_loss_case("lo3", (20, 24), 6, 26, 5, 2, amp=(-0.8, 0.8))
 
 
+def make_phys_case(alias, shape, nstep, seed, amp=(0.1, 0.9)):
+    """The scripts' physics-residual loss through the reference's own `loss_generator` + `loss_gen`/`loss_func`
+    (FWD:265-357, GS2D:241-353, GS3D:264-345) on a trajectory produced by the reference's own cell: the loss, its
+    gradient w.r.t. the trajectory, and the end-to-end gradients w.r.t. h0 and the cell parameters."""
+    mod = load_reference_module(alias)
+    cell = build_cell(alias, mod)
+    dtype = mod._default_dtype
+    # the shipped weights solve their PDE (rcnn_pde.pt gives a residual of 1e-15): jitter them so that the loss
+    # and every gradient are exercised away from zero
+    g = torch.Generator().manual_seed(seed + 100)
+    with torch.no_grad():
+        for n, prm in cell.named_parameters():
+            if prm.requires_grad:
+                prm.mul_(1.0 + 0.2 * (torch.rand(prm.shape, generator=g, dtype=torch.float64).to(prm.dtype) - 0.5))
+    h0 = smooth_state(shape, seed, dtype, *amp).requires_grad_(True)
+    outputs, _ = reference_rollout(cell, h0, nstep, list(range(nstep)))
+    output = torch.cat(tuple(outputs), dim=0)
+    torch.set_default_dtype(dtype)
+    try:
+        gen = mod.loss_generator()      # script defaults: dt, dx of that PDE
+        fn = mod.loss_func if alias == "gs3d" else mod.loss_gen
+        leaf = output.detach().clone().requires_grad_(True)
+        loss_leaf = fn(leaf, gen)
+        loss_leaf.backward()
+        loss = fn(output, gen)
+        (2.0 * loss).backward()
+    finally:
+        torch.set_default_dtype(torch.float32)
+    rec = {"h0": h0.detach().numpy(), "traj": output.detach().numpy(), "loss": np.array(loss.item()),
+           "g_traj": leaf.grad.numpy(), "gscale": np.array(2.0), "g_h0": h0.grad.numpy(), "nstep": np.array(nstep),
+           "dtype": np.array(str(dtype))}
+    for k, v in cell_state(cell).items():
+        rec["param/" + k] = v.numpy()
+    for n, prm in cell.named_parameters():
+        if prm.requires_grad:
+            rec["grad/" + n] = prm.grad.numpy()
+    name = f"phys_{alias}.npz"
+    np.savez_compressed(os.path.join(OUT, name), **rec)
+    print(f"{name}: shape={tuple(h0.shape)} steps={nstep} dtype={dtype} loss={loss.item():.6g} "
+          f"{os.path.getsize(os.path.join(OUT, name)) / 1024:.0f} KiB")
+
+
+def make_phys_cases():
+    make_phys_case("fwd", (18, 22), 5, 31, amp=(-0.8, 0.8))
+    make_phys_case("gs2d", (18, 22), 5, 32)
+    make_phys_case("gs3d", (6, 7, 9), 4, 33)
+
+
 def make_weights():
     """Cell weights of the shipped checkpoints at full size (bench + full-size property tests)."""
     for alias in CHECKPOINTS:
@@ -247,6 +295,9 @@ if __name__ == "__main__":
     if "--data-loss-only" in sys.argv:
         make_data_loss_cases()
         sys.exit(0)
+    if "--phys-only" in sys.argv:
+        make_phys_cases()
+        sys.exit(0)
     make_case("fwd", (20, 24), 6, 11, amp=(-0.8, 0.8))
     make_case("gs2d", (20, 24), 6, 12)
     make_case("gs3d", (6, 8, 12), 5, 13)
@@ -259,3 +310,4 @@ if __name__ == "__main__":
     make_weights()
     make_rcnn_case()
     make_data_loss_cases()
+    make_phys_cases()

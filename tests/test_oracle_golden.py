@@ -113,6 +113,27 @@ def test_data_loss_frames_follow_effective_step():
     assert po.data_loss_frames(9, range(9), 4, first_frames=2) == [0, 4]
 
 
+@pytest.mark.parametrize("tag", ["fwd", "gs2d", "gs3d"])
+def test_physics_loss_restatements_match_reference(tag):
+    """Both restatements of `loss_gen(output, loss_generator())` (FWD:288-357, GS2D:270-353, GS3D:286-345) against
+    the reference's own loss module run on the reference's own trajectory: value and dloss/doutput."""
+    import os
+    from tests.helpers import GOLDEN
+    z = np.load(os.path.join(GOLDEN, f"phys_{tag}.npz"))
+    fp64 = z["h0"].dtype == np.float64
+    out = torch.from_numpy(z["traj"]).requires_grad_(True)
+    loss = po.phys_loss_torch(out, tag)
+    loss.backward()
+    assert abs(loss.item() - float(z["loss"])) <= (1e-12 if fp64 else 2e-5) * abs(float(z["loss"]))
+    assert rel_l2(out.grad.numpy(), z["g_traj"]) <= (1e-11 if fp64 else 1e-4)
+    # numpy version in fp64 on the periodic grid with the double-counting weights (measured: 1e-7 / 2e-7 against
+    # the fp32 reference, 1e-14 against the fp64 one)
+    l64, g64 = po.phys_loss_np(z["traj"], tag)
+    assert abs(l64 - float(z["loss"])) <= (1e-12 if fp64 else 2e-6) * abs(float(z["loss"]))
+    assert rel_l2(g64, z["g_traj"]) <= (1e-11 if fp64 else 2e-6)
+    assert np.count_nonzero(z["g_traj"][-1]) == 0        # the last frame never enters (FWD:318-327)
+
+
 def test_stencil_tables_match_reference_weights():
     z, params, _ = load_golden("gs3d")
     w = params["W_laplace.weight"].numpy()
