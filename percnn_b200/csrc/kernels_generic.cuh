@@ -386,3 +386,142 @@ __global__ void __launch_bounds__(kMultiThreads) k_multi_step(Geom g, int slot, 
 }
 
 }  // namespace percnn
+
+// =====================================================================================================
+// Persistent multi-step ADJOINT for small grids: the backward twin of k_multi_step.  A training step on the 2-D
+// configs (and the reference's own 100^2 / 48^3 grids) is bound by one launch + one 22-value grid reduction per
+// time step (measured: 11 us per step at 128^2 fp64, of which the stencil is ~2 us).  Here ONE cooperative launch
+// walks all steps backwards; the gradient ping-pongs between two L2-resident buffers (ld.global.cg: they are
+// rewritten by other SMs during the kernel), the stored states / injected gradients / loss targets are read-only,
+// and the parameter-gradient sums stay in per-thread fp64 accumulators across ALL steps -- the block reduction
+// and the last-block fold run once per rollout instead of once per step.
+// =====================================================================================================
+namespace percnn {
+
+constexpr int kMaxMultiBwdSteps = 4096;   // selection masks travel as kernel parameters (2 x 516 B)
+
+template <typename T>
+struct MultiBwdArgs {
+  const T* tape;        // h_0 .. h_nsteps
+  const T* g_tape;      // dense gradients of the masked states, packed in increasing step order (nullable)
+  const T* g_init;      // G_nsteps (already holds dL/dh_nsteps or zeros)
+  T* ping;              // scratch gradient buffers; g_init may alias ping
+  T* pong;
+  T* g_h0;              // receives dL/dh_0
+  int nsteps;
+  int g_slots;          // number of masked states among 0 .. nsteps-1
+  int64_t stride;       // elements between tape slots
+  Inject<T> inj;        // fused data loss: target = FIRST packed frame; frames are 2 * lfield apart
+  int inj_slots;        // number of selected states among 0 .. nsteps-1
+  uint32_t gmask[kMaxMultiBwdSteps / 32 + 1];     // bit s: dense gradient present for state s
+  uint32_t selmask[kMaxMultiBwdSteps / 32 + 1];   // bit s: state s enters the fused data loss
+};
+
+template <int CELL>
+struct MultiBwdRed {
+  static constexpr int value = CELL == 0 ? kRedPiK1 : (CELL == 1 ? kRedBurgers : kRedLO);
+};
+
+template <typename T, int NDIM, int CELL>
+__global__ void __launch_bounds__(kMultiThreads) k_multi_step_bwd(Geom g, int slot, const __grid_constant__ MultiBwdArgs<T> m,
+                                                                  unsigned* counter, double* __restrict__ partials,
+                                                                  unsigned* __restrict__ red_counter, double* __restrict__ acc) {
+  constexpr int NRED = MultiBwdRed<CELL>::value;
+  const T* P = PrepView<T>::get(c_prep[slot]);
+  const int64_t ncell = int64_t(g.D) * g.H * g.W;
+  double racc[NRED];
+#pragma unroll
+  for (int i = 0; i < NRED; ++i) racc[i] = 0.0;
+  const T icoef = inject_coef(m.inj);
+  int gslot = m.g_slots, islot = m.inj_slots;
+  const T* src = m.g_init;
+  int flip = (m.g_init == m.ping) ? 1 : 0;
+  for (int s = m.nsteps - 1; s >= 0; --s) {
+    const T* gadd = nullptr;
+    if (m.g_tape != nullptr && ((m.gmask[s >> 5] >> (s & 31)) & 1u)) gadd = m.g_tape + int64_t(--gslot) * m.stride;
+    Inject<T> inj = m.inj;
+    inj.target = nullptr;
+    if (m.inj.target != nullptr && ((m.selmask[s >> 5] >> (s & 31)) & 1u)) inj.target = m.inj.target + int64_t(--islot) * 2 * m.inj.lfield;
+    T* dst = (s == 0) ? m.g_h0 : (flip ? m.pong : m.ping);
+    const T* h = m.tape + int64_t(s) * m.stride;
+    // fp32: per-step partial sums in fp32, folded into the fp64 accumulators after every step (as the per-step
+    // kernels do); fp64: accumulate in place (a second set of 22 doubles spilled)
+    constexpr bool kDirect = sizeof(T) == 8;
+    T red_step[kDirect ? 1 : NRED];
+    T* red;
+    if constexpr (kDirect) {
+      red = reinterpret_cast<T*>(racc);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NRED; ++i) red_step[i] = T(0);
+      red = red_step;
+    }
+    for (int64_t cell = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; cell < ncell;
+         cell += int64_t(gridDim.x) * blockDim.x) {
+      const CellOffsets<NDIM> o = cell_offsets<NDIM>(g, cell);
+      const Cross<T, NDIM> GU = gather_cg<T, NDIM>(src, o);
+      const Cross<T, NDIM> GV = gather_cg<T, NDIM>(src + g.field, o);
+      T gu, gv, u, v;
+      if constexpr (CELL == 1) {
+        const Cross<T, 2> U = gather<T, 2>(h, o);
+        const Cross<T, 2> V = gather<T, 2>(h + g.field, o);
+        u = U.c;
+        v = V.c;
+        burgers_bwd<T>(U, V, GU, GV, P, gu, gv, red);
+      } else {
+        u = __ldg(h + o.c);
+        v = __ldg(h + g.field + o.c);
+        if constexpr (CELL == 0)
+          pi_k1_bwd_poly<T>(u, v, GU.c, GV.c, lap_apply_T<T, NDIM>(GU, P), lap_apply_T<T, NDIM>(GV, P), P, gu, gv, red);
+        else
+          lo_bwd<T>(u, v, GU.c, GV.c, lap_apply_T<T, NDIM>(GU, P), lap_apply_T<T, NDIM>(GV, P), P, gu, gv, red);
+      }
+      if (gadd != nullptr) {
+        gu += __ldg(gadd + o.c);
+        gv += __ldg(gadd + g.field + o.c);
+      }
+      if (inj.target != nullptr) {
+        const int64_t r = cell / g.W;
+        inject_cell<T>(inj, icoef, NDIM == 3 ? int(r / g.H) : 0, NDIM == 3 ? int(r % g.H) : int(r), int(cell % g.W), u, v, gu, gv);
+      }
+      dst[o.c] = gu;
+      dst[g.field + o.c] = gv;
+    }
+    if constexpr (!kDirect) {
+#pragma unroll
+      for (int i = 0; i < NRED; ++i) racc[i] += double(red_step[i]);
+    }
+    src = dst;
+    flip ^= 1;
+    if (s > 0) grid_barrier(counter, unsigned(m.nsteps - s) * gridDim.x);
+  }
+  // one block reduction + last-block fold for the whole rollout (kMultiThreads threads per block)
+  __shared__ double sm[kMultiThreads / 32][NRED];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NRED; ++i) {
+    double d = racc[i];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) d += __shfl_down_sync(0xffffffffu, d, off);
+    if (lane == 0) sm[warp][i] = d;
+  }
+  __syncthreads();
+  if (threadIdx.x < NRED) {
+    double t = 0;
+#pragma unroll
+    for (int w = 0; w < kMultiThreads / 32; ++w) t += sm[w][threadIdx.x];
+    partials[size_t(blockIdx.x) * NRED + threadIdx.x] = t;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(red_counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    fold_partials(partials, gridDim.x, NRED, acc, 1.0);
+    if (threadIdx.x == 0) *red_counter = 0;
+  }
+}
+
+}  // namespace percnn

@@ -65,6 +65,7 @@ struct percnn_plan {
   int ty = 16, tz = 0;
   unsigned* d_sync = nullptr;   // grid-barrier counter of the persistent multi-step kernel
   int multi_grid = 0;           // co-resident grid size of that kernel (0 = not available)
+  int multi_bwd_grid = 0;       // same for the persistent adjoint kernel
   bool debug_split = false;   // PERCNN_TMA_SPLIT=1
   bool bwd_split_mono = false;   // PERCNN_BWD_SPLIT_MONO=1: monomial sums in their own streaming kernel
   bool pdl = true;   // programmatic dependent launch between consecutive step kernels (PERCNN_NO_PDL=1 disables)
@@ -360,20 +361,6 @@ int launch_multi_step(percnn_plan* p, const void* h0, void* tape, void* ping, vo
   return PERCNN_OK;
 }
 
-int step_fwd_any(percnn_plan* p, const void* src, void* dst, cudaStream_t st) {
-  if (p->use_tma) return launch_tma_fwd(p, static_cast<const float*>(src), static_cast<float*>(dst), 0, p->g.D, st);
-  if (p->desc.cell == PERCNN_CELL_PI && p->desc.ksize == 5) {
-    dim3 grid((p->g.W + k5::TILE_X - 1) / k5::TILE_X, (p->g.H + k5::TILE_Y - 1) / k5::TILE_Y);
-    k5::k_pi_k5_fwd<<<grid, k5::THREADS, k5::smem_bytes(p->desc.hidden), st>>>(
-        p->g, p->slot, p->desc.hidden, static_cast<const float*>(src), static_cast<float*>(dst), p->d_k5w);
-    PERCNN_CUDA(cudaGetLastError());
-    p->launches++;
-    return PERCNN_OK;
-  }
-  return p->elt == 4 ? step_fwd_t<float>(p, static_cast<const float*>(src), static_cast<float*>(dst), st)
-                     : step_fwd_t<double>(p, static_cast<const double*>(src), static_cast<double*>(dst), st);
-}
-
 // Type-erased description of the fused data-loss gradient of one state (see percnn_data_loss_t).
 struct InjectHost {
   const void* target = nullptr;   // that state's low-res frame
@@ -400,6 +387,81 @@ Inject<T> make_inject(const percnn_plan* p, const InjectHost* ih) {
   j.lw = lowres(p->g.W, ih->stride);
   j.lfield = lowres_field_elems(p, ih->stride);
   return j;
+}
+
+template <typename T>
+const void* multi_bwd_kernel(const percnn_plan* p) {
+  const int cell = p->desc.cell;
+  if (cell == PERCNN_CELL_PI)
+    return p->g.ndim == 3 ? (const void*)k_multi_step_bwd<T, 3, 0> : (const void*)k_multi_step_bwd<T, 2, 0>;
+  if (cell == PERCNN_CELL_BURGERS) return (const void*)k_multi_step_bwd<T, 2, 1>;
+  return (const void*)k_multi_step_bwd<T, 2, 2>;
+}
+// Whole backward rollout in one cooperative launch (see k_multi_step_bwd).  G_init must already hold dL/dh_nsteps.
+template <typename T>
+int launch_multi_bwd(percnn_plan* p, const void* tape, const void* g_tape, const uint8_t* gmask, const void* g_init,
+                     void* ping, void* pong, void* g_h0, const percnn_data_loss_t* dl, int64_t dl_n, int nsteps, char* ws,
+                     cudaStream_t st) {
+  static_assert(sizeof(MultiBwdArgs<T>) < 3500, "kernel parameter space");
+  MultiBwdArgs<T> m;
+  memset(&m, 0, sizeof(m));
+  m.tape = static_cast<const T*>(tape);
+  m.g_tape = static_cast<const T*>(g_tape);
+  m.g_init = static_cast<const T*>(g_init);
+  m.ping = static_cast<T*>(ping);
+  m.pong = static_cast<T*>(pong);
+  m.g_h0 = static_cast<T*>(g_h0);
+  m.nsteps = nsteps;
+  m.stride = p->state_elems;
+  m.inj.s = 1;
+  if (g_tape)
+    for (int s = 0; s < nsteps; ++s)
+      if (gmask[s]) {
+        m.gmask[s >> 5] |= 1u << (s & 31);
+        m.g_slots++;
+      }
+  if (dl) {
+    InjectHost ih;
+    ih.target = dl->target;
+    ih.gscale = dl->gscale;
+    ih.stride = dl->stride;
+    ih.n_total = dl_n;
+    m.inj = make_inject<T>(p, &ih);
+    for (int s = 0; s < nsteps; ++s)
+      if (dl->sel[s]) {
+        m.selmask[s >> 5] |= 1u << (s & 31);
+        m.inj_slots++;
+      }
+    if (m.inj_slots == 0) m.inj.target = nullptr;
+  }
+  PERCNN_CUDA(cudaMemsetAsync(p->d_sync, 0, sizeof(unsigned), st));
+  Geom g = p->g;
+  int slot = p->slot;
+  unsigned* counter = p->d_sync;
+  double* partials = reinterpret_cast<double*>(ws + kWsPartials);
+  unsigned* red_counter = reinterpret_cast<unsigned*>(ws + kWsCounter);
+  double* acc = reinterpret_cast<double*>(ws + kWsAcc);
+  void* args[] = {&g, &slot, &m, &counter, &partials, &red_counter, &acc};
+  const int64_t ncell = int64_t(g.D) * g.H * g.W;
+  int grid = int((ncell + kMultiThreads - 1) / kMultiThreads);
+  if (grid > p->multi_bwd_grid) grid = p->multi_bwd_grid;
+  PERCNN_CUDA(cudaLaunchCooperativeKernel(multi_bwd_kernel<T>(p), dim3(grid), dim3(kMultiThreads), args, 0, st));
+  p->launches++;
+  return PERCNN_OK;
+}
+
+int step_fwd_any(percnn_plan* p, const void* src, void* dst, cudaStream_t st) {
+  if (p->use_tma) return launch_tma_fwd(p, static_cast<const float*>(src), static_cast<float*>(dst), 0, p->g.D, st);
+  if (p->desc.cell == PERCNN_CELL_PI && p->desc.ksize == 5) {
+    dim3 grid((p->g.W + k5::TILE_X - 1) / k5::TILE_X, (p->g.H + k5::TILE_Y - 1) / k5::TILE_Y);
+    k5::k_pi_k5_fwd<<<grid, k5::THREADS, k5::smem_bytes(p->desc.hidden), st>>>(
+        p->g, p->slot, p->desc.hidden, static_cast<const float*>(src), static_cast<float*>(dst), p->d_k5w);
+    PERCNN_CUDA(cudaGetLastError());
+    p->launches++;
+    return PERCNN_OK;
+  }
+  return p->elt == 4 ? step_fwd_t<float>(p, static_cast<const float*>(src), static_cast<float*>(dst), st)
+                     : step_fwd_t<double>(p, static_cast<const double*>(src), static_cast<double*>(dst), st);
 }
 
 template <typename T>
@@ -492,11 +554,25 @@ int percnn_abi_version(void) { return PERCNN_ABI_VERSION; }
 const char* percnn_last_error(void) { return g_err.c_str(); }
 
 int percnn_device_ok(int device) {
+  // cudaGetDeviceProperties costs ~1 ms; the stand-alone loss entry points validate their device on every call,
+  // so the answer is cached per ordinal (a device's compute capability cannot change under a live process).
+  static std::mutex mu;
+  static signed char cache[64];   // 0 = unknown, 1 = sm_100, -1 = anything else
+  if (device < 0) return 0;
+  if (device < 64) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache[device] != 0) return cache[device] > 0 ? 1 : 0;
+  }
   int n = 0;
-  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return 0;
-  cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return 0;
-  return prop.major == 10 ? 1 : 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device >= n) return 0;
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess) return 0;
+  const int ok = major == 10 ? 1 : 0;
+  if (device < 64) {
+    std::lock_guard<std::mutex> lk(mu);
+    cache[device] = ok ? 1 : -1;
+  }
+  return ok;
 }
 
 int percnn_plan_create(const percnn_desc_t* d, percnn_plan_t** out) {
@@ -582,6 +658,11 @@ int percnn_plan_create(const percnn_desc_t* d, percnn_plan_t** out) {
       if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kMultiThreads, 0) == cudaSuccess && per_sm > 0) {
         if (cudaMalloc(&p->d_sync, 256) == cudaSuccess) p->multi_grid = p->sm_count;   // one block per SM
       }
+      const void* bfn = p->elt == 4 ? multi_bwd_kernel<float>(p) : multi_bwd_kernel<double>(p);
+      per_sm = 0;
+      if (p->multi_grid > 0 && !getenv("PERCNN_NO_MULTISTEP_BWD") &&
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bfn, kMultiThreads, 0) == cudaSuccess && per_sm > 0)
+        p->multi_bwd_grid = p->sm_count;
     }
     p->use_tma = d->cell == PERCNN_CELL_PI && d->ksize == 1 && d->ndim == 3 && d->dtype == PERCNN_F32 &&
                  !(d->flags & (PERCNN_FLAG_NO_TMA | PERCNN_FLAG_EVAL_BRANCH)) && g.W % tma3d::TX == 0 &&
@@ -969,6 +1050,13 @@ int percnn_rollout_bwd_loss(percnn_plan_t* p, const void* params, const void* ta
                                                               reinterpret_cast<double*>(pp[0]), make_inject<double>(p, &ih));
     PERCNN_CUDA(cudaGetLastError());
     p->launches++;
+  }
+  // small grids: the whole backward rollout as ONE persistent cooperative launch
+  if (nsteps >= 2 && nsteps <= kMaxMultiBwdSteps && multi_step_eligible(p) && p->multi_bwd_grid > 0) {
+    rc = p->elt == 4 ? launch_multi_bwd<float>(p, tape, g_tape, gmask, G, pp[0], pp[1], g_h0, dl, dl_n, nsteps, w, st)
+                     : launch_multi_bwd<double>(p, tape, g_tape, gmask, G, pp[0], pp[1], g_h0, dl, dl_n, nsteps, w, st);
+    if (rc) return rc;
+    return percnn_param_grads_finish(p, params, param_grads, ws, stream);
   }
   int flip = (G == pp[0]) ? 1 : 0;
   for (int s = nsteps - 1; s >= 0; --s) {

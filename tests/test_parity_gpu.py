@@ -317,3 +317,33 @@ def test_gradcheck_fp64_against_finite_differences():
             gnum.view(-1)[i] = (f(fp.view_as(h0)) - f(fm.view_as(h0))) / (2 * eps)
     idx = torch.arange(0, h0.numel(), 7, device=DEV)
     assert torch.allclose(h0.grad.view(-1)[idx], gnum.view(-1)[idx], rtol=1e-6, atol=1e-8)
+
+
+@pytest.mark.parametrize("tag", ["fwd", "gs2d", "gs3d", "bur3", "lo3", "lo3n"])
+def test_persistent_adjoint_equals_per_step_adjoint(tag, monkeypatch):
+    """Small grids run the whole backward rollout as one cooperative launch (k_multi_step_bwd); it must reproduce
+    the per-step adjoint kernels: dL/dh0 bit for bit (same arithmetic per cell), parameter gradients to fp64
+    summation-order noise."""
+    z, params, _ = load_golden(tag)
+    nstep = int(z["nstep"])
+    wts = torch.from_numpy(z["loss_weights"]).to(DEV)
+    res = []
+    for disable in ("", "1"):
+        if disable:
+            monkeypatch.setenv("PERCNN_NO_MULTISTEP_BWD", "1")
+        else:
+            monkeypatch.delenv("PERCNN_NO_MULTISTEP_BWD", raising=False)
+        engine.clear_plans()
+        cell = _cell(tag, params)
+        h0 = torch.from_numpy(z["h0"]).to(DEV).requires_grad_(True)
+        states = cell.rollout(h0, nstep)
+        launches0 = cell._plan(h0).launch_count
+        (states * wts).sum().backward()
+        launches = cell._plan(h0).launch_count - launches0
+        res.append((h0.grad.cpu().numpy(), {k: p.grad.cpu().numpy() for k, p in cell.named_parameters() if p.grad is not None},
+                    launches))
+    engine.clear_plans()
+    assert res[0][2] < res[1][2], "the persistent path should need fewer launches"
+    assert np.array_equal(res[0][0], res[1][0])
+    for k in res[1][1]:
+        assert rel_l2(res[0][1][k], res[1][1][k]) <= (1e-12 if z["h0"].dtype == np.float64 else 2e-6), k
