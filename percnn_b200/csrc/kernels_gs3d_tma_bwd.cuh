@@ -51,7 +51,8 @@ __device__ __forceinline__ void adjoint_plane(Consumer& c, const float* __restri
                                               float* __restrict__ dst, float* mirror, const float* __restrict__ hbase,
                                               const float* __restrict__ gadd, bool prefetch_next, bool valid,
                                               float2 (&seam_next)[2], float (&aacc)[2], float2* __restrict__ macc,
-                                              const Inject<float>& inj, int64_t inj_row, int xq) {
+                                              const Inject<float>& inj, int64_t inj_row, int xq,
+                                              const float* __restrict__ hsm = nullptr, int hsm_field = 0) {
   const float* P = c.P;
   mbar_wait(&c.full[c.s], c.parity);   // plane k has landed; planes k-4 .. k-1 are still resident
   const float2 seam_u = seam_next[0], seam_v = seam_next[1];
@@ -59,10 +60,15 @@ __device__ __forceinline__ void adjoint_plane(Consumer& c, const float* __restri
     ldg_f2_if(c.is_seam, seam_ptr, seam_next[0]);
     ldg_f2_if(c.is_seam, seam_ptr + field, seam_next[1]);
   }
-  const float4 hu = ldg128(hbase + off), hv = ldg128(hbase + off + field);
+  // stored state of this step: from global memory (L2-prefetched one plane ahead), or -- warp-specialised kernel --
+  // from the shared-memory ring the producer fills with TMA (hsm = this lane's quad in the current h stage)
+  const float4 hu = hsm != nullptr ? lds128(hsm) : ldg128(hbase + off);
+  const float4 hv = hsm != nullptr ? lds128(hsm + hsm_field) : ldg128(hbase + off + field);
   if (prefetch_next && (c.lane & 7) == 0) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(hbase + off + plane));
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(hbase + off + plane + field));
+    if (hsm == nullptr) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(hbase + off + plane));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(hbase + off + plane + field));
+    }
     if (gadd != nullptr) {
       asm volatile("prefetch.global.L2 [%0];" ::"l"(gadd + off + plane));
       asm volatile("prefetch.global.L2 [%0];" ::"l"(gadd + off + plane + field));
@@ -95,7 +101,8 @@ __device__ __forceinline__ void adjoint_plane(Consumer& c, const float* __restri
   }
   // plane k-4 is no longer needed by this warp (release only once the loads have completed, see mbar_arrive_after)
   __syncwarp();
-  if (c.lane == 0) mbar_arrive_after(&c.empty[(c.s + STAGES - 4) & (STAGES - 1)], Lu_lo.x + Lv_lo.x);
+  // (the h stage read above is recycled together with this G stage, so its loads join the dependency)
+  if (c.lane == 0) mbar_arrive_after(&c.empty[(c.s + STAGES - 4) & (STAGES - 1)], (Lu_lo.x + Lv_lo.x) + (hu.w + hv.w));
   float4 au4 = make_float4(0.f, 0.f, 0.f, 0.f), av4 = au4;
   if (gadd != nullptr) {
     au4 = ldg128(gadd + off);
@@ -388,6 +395,330 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
       __threadfence();
       if (lane < NR) {
         double s0 = 0, s1 = 0;   // two chains keep the loads in flight; fixed order
+        unsigned b = 0;
+        for (; b + 2 <= gridDim.x; b += 2) {
+          s0 += __ldcg(x.partials + size_t(b) * NR + lane);
+          s1 += __ldcg(x.partials + size_t(b + 1) * NR + lane);
+        }
+        if (b < gridDim.x) s0 += __ldcg(x.partials + size_t(b) * NR + lane);
+        x.acc[lane] += s0 + s1;
+      }
+      if (lane == 0) *x.counter = 0;
+    }
+  }
+}
+
+// =====================================================================================================
+// Warp-specialised variant ("mono warps").  ncu on k_gs3d_bwd_tma at 512^3 (profiles/r01_ncu_tma_bwd_512_details.txt):
+// the shared-memory pipe is the busiest unit (70 %), and 36 % of its wavefronts are the read-modify-write of the
+// per-lane monomial accumulators, which live in shared memory only because the stencil warps have no registers
+// left for them.  Here the 20 monomial sums move to two dedicated warps that do nothing else: they read the centre
+// rows of G from the ring and h from global memory and keep all 40 partial sums in registers.  The 14 stencil warps
+// lose ~100 instructions and 20 shared-memory accesses per plane.  Layout (640 threads, as the forward kernel):
+//   warps 0..13  stencil warps, one tile row each (adjoint_plane<FUSED, false>)
+//   warps 14,15  monomial warps, rows 14/15 + 2 i of the tile
+//   warps 16..19 producer warp-group (one lane issues the TMA loads), registers handed to the others (setmaxnreg)
+// Every consumer warp -- stencil or monomial -- waits on the same full barriers and releases plane k-4 after
+// iteration k, so the ring protocol is unchanged (empty barriers count ty + 2 arrivals).
+// =====================================================================================================
+constexpr int MW_STENCIL = 14;
+constexpr int MW_MONO = 2;
+constexpr int MW_CONSUMERS = MW_STENCIL + MW_MONO;
+constexpr int MW_THREADS = MW_CONSUMERS * 32 + 128;
+constexpr int MW_CONSUMER_REGS = 112;   // 512 * 112 + 128 * 24 <= 640 * 96 (setmaxnreg only redistributes the CTA's allocation)
+constexpr int MW_FLUSH = 8;             // planes between fp32 -> fp64 flushes of the monomial warps (<= 224 terms per lane sum)
+// The stored state h_t streams through its own small ring: plane (k - 4) of h travels with plane k of G (same full
+// barrier), is read during consumer iteration k and recycled with G plane k - 4, i.e. after that same iteration.
+// The producer reuses an h stage HSTAGES planes later, by which time it has waited for the G stage released in
+// iteration k: 4 stages are exactly enough.
+constexpr int HSTAGES = 4;
+constexpr int HSTAGE_FLOATS = 2 * MW_STENCIL * TX;
+constexpr int MW_OFF_HRING = STAGES * STAGE_BYTES;
+constexpr int MW_OFF_BARS = MW_OFF_HRING + HSTAGES * HSTAGE_FLOATS * 4;
+constexpr int MW_OFF_WACC = MW_OFF_BARS + 2 * STAGES * 8 + 64;
+constexpr int SMEM_BYTES_BWD_MW = MW_OFF_WACC + 16 * kRedPiK1 * 8 + 64;
+static_assert(SMEM_BYTES_BWD_MW <= 227 * 1024, "shared memory budget");
+
+template <int SLOT, bool FUSED>
+__global__ void __launch_bounds__(MW_THREADS, 1)
+k_gs3d_bwd_tma_mw(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_halo,
+                  const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ Params p,
+                  const __grid_constant__ BwdExtra x) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  float* ring = reinterpret_cast<float*>(smem_raw);
+  float* hring = reinterpret_cast<float*>(smem_raw + MW_OFF_HRING);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + MW_OFF_BARS);
+  uint64_t* empty = full + STAGES;
+  double* wacc = reinterpret_cast<double*>(smem_raw + MW_OFF_WACC);   // [16][22]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nmono = MW_MONO;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], p.ty + nmono);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 16 * kRedPiK1; i += MW_THREADS) wacc[i] = 0.0;
+  __syncthreads();
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int nitems = total_items(p);
+
+  if (warp >= MW_CONSUMERS) {
+    // ===== producer warp-group =====
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PRODUCER_REGS));
+    if (warp == MW_CONSUMERS && lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_main)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_halo)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_h)) : "memory");
+      uint32_t it = 0, hit = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const ItemCoord ic = decode_item(p, item);
+        if (FUSED && ic.seg < 2) {
+          wait_flag(p.my_flags + ic.seg, p.epoch_wait, p.scratch + 1);
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+        }
+        int yh[4] = {ic.y0 - 2, ic.y0 - 1, ic.y0 + p.ty, ic.y0 + p.ty + 1};
+#pragma unroll
+        for (int h = 0; h < 4; ++h) yh[h] = yh[h] < 0 ? yh[h] + p.H : (yh[h] >= p.H ? yh[h] - p.H : yh[h]);
+        const uint32_t bytes_main = 2u * uint32_t(p.ty) * TX * 4u, bytes_halo = 2u * 4u * TX * 4u;
+        for (int k = 0; k < ic.nz + 4; ++k, ++it) {
+          const int s = it % STAGES;
+          if (it >= STAGES) mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+          const bool with_halo = (k >= 2) && (k < ic.nz + 2);
+          const bool with_h = k >= 4;                  // state plane of output plane k - 4 travels with G plane k
+          const int pz = src_plane(p, ic.z0, k);
+          float* st = ring + s * STAGE_FLOATS;
+          mbar_expect_tx(&full[s], bytes_main + (with_halo ? bytes_halo : 0u) + (with_h ? bytes_main : 0u));
+#pragma unroll
+          for (int f = 0; f < 2; ++f) {
+            float* sf = st + f * ROWS * TX;
+            tma_load_4d(sf + 2 * TX, &tm_main, &full[s], ic.x0, ic.y0, pz, f);
+            if (with_halo) {
+              tma_load_4d(sf, &tm_halo, &full[s], ic.x0, yh[0], pz, f);
+              tma_load_4d(sf + TX, &tm_halo, &full[s], ic.x0, yh[1], pz, f);
+              tma_load_4d(sf + (p.ty + 2) * TX, &tm_halo, &full[s], ic.x0, yh[2], pz, f);
+              tma_load_4d(sf + (p.ty + 3) * TX, &tm_halo, &full[s], ic.x0, yh[3], pz, f);
+            }
+          }
+          if (with_h) {
+            float* hs = hring + (hit % HSTAGES) * HSTAGE_FLOATS;
+            const int hz = ic.z0 + (k - 4) + p.dst_zoff;   // the state buffers share the layout of the gradient buffers
+            tma_load_4d(hs, &tm_h, &full[s], ic.x0, ic.y0, hz, 0);
+            tma_load_4d(hs + MW_STENCIL * TX, &tm_h, &full[s], ic.x0, ic.y0, hz, 1);
+            ++hit;
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(MW_CONSUMER_REGS));
+  uint32_t hcur = 0;   // h stage of the output plane of the current iteration (advances with every k >= 4)
+  const bool is_mono = warp >= MW_STENCIL;
+  if (!is_mono && warp >= p.ty) return;   // tile shorter than 14 rows (after the aligned setmaxnreg)
+  const int nsync = (p.ty + nmono) * 32;  // consumer threads that reach the final reduction
+  const int64_t plane = int64_t(p.H) * p.W;
+  const int64_t field = p.dst_field;
+  Consumer c;
+  c.P = c_prep[SLOT].f;
+  c.ring = ring;
+  c.full = full;
+  c.empty = empty;
+  c.s = 0;
+  c.parity = 0;
+  c.row = warp;
+  c.lane = lane;
+  c.toff = uint32_t(warp) * uint32_t(p.W) + 4u * uint32_t(lane);
+  c.is_seam = (lane == 0) || (lane == 31);
+
+  if (is_mono) {
+    // ===== monomial warps: 20 sums  sum dt G_f u^a v^b  over the rows mono_id, mono_id + 2, ... of every plane =====
+    const int mono_id = warp - MW_STENCIL;
+    float2 au[10], av[10];   // (cells 0+2, cells 1+3) partial sums per monomial, field u / field v
+#pragma unroll
+    for (int m = 0; m < 10; ++m) au[m] = av[m] = make_float2(0.f, 0.f);
+    int since_flush = 0;
+    auto flush = [&]() {
+      const float dt = c.P[P_DT];
+#pragma unroll
+      for (int m = 0; m < 10; ++m) {
+        float tu = au[m].x + au[m].y, tv = av[m].x + av[m].y;
+        au[m] = av[m] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          tu += __shfl_down_sync(0xffffffffu, tu, o);
+          tv += __shfl_down_sync(0xffffffffu, tv, o);
+        }
+        if (lane == 0) {
+          wacc[warp * kRedPiK1 + 2 + m] += double(dt) * double(tu);
+          wacc[warp * kRedPiK1 + 12 + m] += double(dt) * double(tv);
+        }
+      }
+      since_flush = 0;
+    };
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const ItemCoord ic = decode_item(p, item);
+      // first row of this warp that is not a duplicate of the previous tile (last tile of a column is shifted back)
+      int r0 = mono_id;
+      while (r0 < p.ty && (ic.y0 + r0) < ic.ytile * p.ty) r0 += nmono;
+      const int nk = ic.nz + 4;
+      for (int k = 0; k < nk; ++k) {
+        mbar_wait(&c.full[c.s], c.parity);
+        if (k >= 4) {
+          const float* st = c.ring + ((c.s + STAGES - 2) & (STAGES - 1)) * STAGE_FLOATS + 2 * TX + 4 * lane;   // plane k-2, tile row 0
+          const float* hst = hring + hcur * HSTAGE_FLOATS + 4 * lane;   // state plane of this output plane, tile row 0
+          float keep = 0.f;
+          for (int r = (p.debug & 8) ? p.ty : r0; r < p.ty; r += nmono) {   // debug 8: timing experiment without the monomial work
+            const float4 Gu = lds128(st + r * TX), Gv = lds128(st + ROWS * TX + r * TX);
+            const float4 hu = lds128(hst + r * TX), hv = lds128(hst + MW_STENCIL * TX + r * TX);
+            keep = Gv.w + hv.w;
+            const float2 ul = lo(hu), uh = hi(hu), vl = lo(hv), vh = hi(hv);
+            const float2 gul = lo(Gu), guh = hi(Gu), gvl = lo(Gv), gvh = hi(Gv);
+            const float2 uul = __fmul2_rn(ul, ul), uuh = __fmul2_rn(uh, uh);
+            const float2 uvl = __fmul2_rn(ul, vl), uvh = __fmul2_rn(uh, vh);
+            const float2 vvl = __fmul2_rn(vl, vl), vvh = __fmul2_rn(vh, vh);
+#define PERCNN_MW_MONO(M, EL, EH)                                    \
+  {                                                                  \
+    const float2 el = EL, eh = EH;                                   \
+    au[M] = fma2(guh, eh, fma2(gul, el, au[M]));                     \
+    av[M] = fma2(gvh, eh, fma2(gvl, el, av[M]));                     \
+  }
+            au[0] = __fadd2_rn(au[0], __fadd2_rn(gul, guh));
+            av[0] = __fadd2_rn(av[0], __fadd2_rn(gvl, gvh));
+            PERCNN_MW_MONO(1, ul, uh)
+            PERCNN_MW_MONO(2, vl, vh)
+            PERCNN_MW_MONO(3, uul, uuh)
+            PERCNN_MW_MONO(4, uvl, uvh)
+            PERCNN_MW_MONO(5, vvl, vvh)
+            PERCNN_MW_MONO(6, __fmul2_rn(uul, ul), __fmul2_rn(uuh, uh))
+            PERCNN_MW_MONO(7, __fmul2_rn(uul, vl), __fmul2_rn(uuh, vh))
+            PERCNN_MW_MONO(8, __fmul2_rn(ul, vvl), __fmul2_rn(uh, vvh))
+            PERCNN_MW_MONO(9, __fmul2_rn(vvl, vl), __fmul2_rn(vvh, vh))
+#undef PERCNN_MW_MONO
+          }
+          // release plane k-4 like the stencil warps do (this warp has finished with every plane <= k-2); the
+          // data dependency on the last shared-memory load keeps the arrive behind it (see mbar_arrive_after)
+          __syncwarp();
+          if (lane == 0) mbar_arrive_after(&c.empty[(c.s + STAGES - 4) & (STAGES - 1)], keep);
+          hcur = (hcur + 1) & (HSTAGES - 1);
+          if (++since_flush >= MW_FLUSH) flush();
+        }
+        advance_stage(c);
+      }
+      __syncwarp();
+      if (lane == 0) {
+#pragma unroll
+        for (int j = 1; j <= 4; ++j) mbar_arrive(&c.empty[(c.s + STAGES - j) & (STAGES - 1)]);
+      }
+    }
+    flush();
+  } else {
+    // ===== stencil warps =====
+    const float* TP = c.P + (P_LAPT - P_LAP_C0);
+    float2 seam_next[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+    float aacc[2] = {0.f, 0.f};
+    int since_flush = 0;
+    auto flush = [&]() {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        float t = aacc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+        if (lane == 0) wacc[warp * kRedPiK1 + i] += double(t);
+        aacc[i] = 0.f;
+      }
+      since_flush = 0;
+    };
+    bool posted = !FUSED;
+    auto post_boundary_done = [&]() {
+      __threadfence_system();   // every storing warp fences its own peer stores (see the forward kernel)
+      asm volatile("bar.sync 1, %0;" ::"r"(p.ty * 32) : "memory");
+      if (warp == 0 && lane == 0) {
+        __threadfence_system();
+        const unsigned old = atomicAdd(p.scratch, 1u);
+        if (old == gridDim.x - 1) {
+          atomicExch(p.scratch, 0u);
+          __threadfence_system();
+          st_release_sys(p.post_lo_flag, p.epoch_post);
+          st_release_sys(p.post_hi_flag, p.epoch_post);
+        }
+      }
+    };
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const ItemCoord ic = decode_item(p, item);
+      if (FUSED && !posted && ic.seg == 2) {
+        post_boundary_done();
+        posted = true;
+      }
+      float* mirror = nullptr;
+      if (FUSED && ic.seg < 2) {
+        float* base = ic.seg == 0 ? p.peer_lo_dst : p.peer_hi_dst;
+        const int mz = ic.seg == 0 ? p.D + 2 + ic.z0 : ic.z0 - (p.D - 2);
+        mirror = base + (int64_t(mz) * p.H + ic.y0) * p.W + ic.x0 + c.toff;
+      }
+      const bool valid = (ic.y0 + warp) >= ic.ytile * p.ty;
+      const int inj_ly = (x.inj.target != nullptr && (ic.y0 + warp) % x.inj.s == 0) ? (ic.y0 + warp) / x.inj.s : -1;
+      const float* src_xy = p.src + int64_t(ic.y0) * p.W + ic.x0;
+      int64_t off = (int64_t(ic.z0 + p.dst_zoff) * p.H + ic.y0) * p.W + ic.x0 + c.toff;
+      int xs = (lane == 0) ? ic.x0 - 2 : ic.x0 + TX;
+      xs = xs < 0 ? xs + p.W : (xs >= p.W ? xs - p.W : xs);
+      const int seam_off = warp * p.W + xs - ic.x0;
+      const float* seam_ptr = src_xy + int64_t(src_plane(p, ic.z0, 2)) * plane + seam_off;
+      const int nk = ic.nz + 4;
+      for (int k = 0; k < nk; ++k) {
+        if (k < 4) {
+          mbar_wait(&c.full[c.s], c.parity);
+          if (k == 3) {
+            ldg_f2_if(c.is_seam, seam_ptr, seam_next[0]);
+            ldg_f2_if(c.is_seam, seam_ptr + p.src_field, seam_next[1]);
+          }
+        } else {
+          seam_ptr += plane;
+          int64_t inj_row = -1;
+          if (inj_ly >= 0) {
+            const int zg = ic.z0 + k - 4;
+            if (zg % x.inj.s == 0) inj_row = (int64_t(zg / x.inj.s) * x.inj.lh + inj_ly) * x.inj.lw;
+          }
+          adjoint_plane<FUSED, false>(c, TP, k <= ic.nz + 2, seam_ptr, field, plane, off, p.dst, mirror, x.h, x.gadd,
+                                      k + 1 < nk, valid, seam_next, aacc, nullptr, x.inj, inj_row, ic.x0 + 4 * lane,
+                                      hring + hcur * HSTAGE_FLOATS + warp * TX + 4 * lane, MW_STENCIL * TX);
+          hcur = (hcur + 1) & (HSTAGES - 1);
+          off += plane;
+          if (FUSED && mirror != nullptr) mirror += plane;
+          if (++since_flush >= BWD_FLUSH) flush();
+        }
+        advance_stage(c);
+      }
+      __syncwarp();
+      if (lane == 0) {
+#pragma unroll
+        for (int j = 1; j <= 4; ++j) mbar_arrive(&c.empty[(c.s + STAGES - j) & (STAGES - 1)]);
+      }
+    }
+    if (FUSED && !posted) post_boundary_done();
+    flush();
+  }
+  // ---- CTA result -> global partials; last CTA folds all CTAs in fixed order ----
+  asm volatile("bar.sync 2, %0;" ::"r"(nsync) : "memory");
+  __shared__ bool s_last;
+  constexpr int NR = kRedPiK1;
+  if (warp == 0) {
+    if (lane < NR) {
+      double s = 0;
+      for (int w = 0; w < MW_CONSUMERS; ++w) s += wacc[w * kRedPiK1 + lane];
+      x.partials[size_t(blockIdx.x) * NR + lane] = s;
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) s_last = (atomicAdd(x.counter, 1u) == gridDim.x - 1);
+    __syncwarp();
+    if (s_last) {
+      __threadfence();
+      if (lane < NR) {
+        double s0 = 0, s1 = 0;
         unsigned b = 0;
         for (; b + 2 <= gridDim.x; b += 2) {
           s0 += __ldcg(x.partials + size_t(b) * NR + lane);

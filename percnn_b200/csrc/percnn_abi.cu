@@ -68,6 +68,9 @@ struct percnn_plan {
   int multi_bwd_grid = 0;       // same for the persistent adjoint kernel
   bool debug_split = false;   // PERCNN_TMA_SPLIT=1
   bool bwd_split_mono = false;   // PERCNN_BWD_SPLIT_MONO=1: monomial sums in their own streaming kernel
+  bool bwd_mw = false;           // PERCNN_BWD_MW=1: warp-specialised adjoint (monomial warps + TMA ring for the stored
+                                 // state).  Measured 847 us vs 800 us per 512^3 step: the two monomial warps are the
+                                 // critical path (688 us without their work), see DESIGN.md 3.3 -- kept as an experiment.
   bool pdl = true;   // programmatic dependent launch between consecutive step kernels (PERCNN_NO_PDL=1 disables)
   int tz_override = 0, grid_override = 0;   // experiment knobs (PERCNN_TMA_TY / _TZ / _GRID environment variables)
   PrepBlock* d_prep = nullptr;
@@ -130,10 +133,10 @@ double tiling_cost(int nxt, int H, int depth, int nsm, int ty, int nzc, TmaTilin
   if (out) *out = TmaTiling{ty, tz, nyt, nz_chunks};
   return cost;
 }
-TmaTiling choose_tiling(int nxt, int H, int depth, int nsm, int fixed_ty) {
-  TmaTiling best{tma3d::BWD_WARPS, depth, (H + tma3d::BWD_WARPS - 1) / tma3d::BWD_WARPS, 1};
+TmaTiling choose_tiling(int nxt, int H, int depth, int nsm, int fixed_ty, int max_ty = tma3d::BWD_WARPS) {
+  TmaTiling best{max_ty, depth, (H + max_ty - 1) / max_ty, 1};
   double best_cost = 1e300;
-  for (int ty = (fixed_ty ? fixed_ty : 1); ty <= (fixed_ty ? fixed_ty : tma3d::BWD_WARPS); ++ty) {
+  for (int ty = (fixed_ty ? fixed_ty : 1); ty <= (fixed_ty ? fixed_ty : max_ty); ++ty) {
     if (ty > H) break;
     for (int nzc = 1; nzc <= depth; ++nzc) {
       TmaTiling t;
@@ -213,6 +216,20 @@ int launch_tma_fwd(percnn_plan* p, const float* src, float* dst, int z_lo, int z
   const CUtensorMap *mm, *hm;
   int rc = get_maps(p, src, &mm, &hm);
   if (rc) return rc;
+  CUtensorMap h_map;   // warp-specialised adjoint: the stored state streams through TMA as well (copied: the cache may recycle the slot)
+  memset(&h_map, 0, sizeof(h_map));
+  if (bwd && p->bwd_mw && !p->bwd_split_mono) {
+    const CUtensorMap main_copy = *mm, halo_copy = *hm;   // get_maps may evict these when it encodes the map for h
+    const CUtensorMap *h_main, *h_halo;
+    rc = get_maps(p, bwd->h, &h_main, &h_halo);
+    if (rc) return rc;
+    h_map = *h_main;
+    static thread_local CUtensorMap keep_main, keep_halo;
+    keep_main = main_copy;
+    keep_halo = halo_copy;
+    mm = &keep_main;
+    hm = &keep_halo;
+  }
   const Geom& g = p->g;
   tma3d::Params prm;
   memset(&prm, 0, sizeof(prm));
@@ -258,6 +275,9 @@ int launch_tma_fwd(percnn_plan* p, const float* src, float* dst, int z_lo, int z
     prm.epoch_wait = link->epoch_wait;
     prm.epoch_post = link->epoch_post;
     if (const char* e = getenv("PERCNN_FUSED_DEBUG")) prm.debug = atoi(e);
+  } else if (getenv("PERCNN_KERNEL_DEBUG")) {
+    prm.debug = atoi(getenv("PERCNN_KERNEL_DEBUG"));
+    add_segment(z_lo, z_hi);
   } else if (p->debug_split && z_lo == 0 && z_hi == g.D && g.D >= 5) {
     add_segment(0, 2);            // debugging aid: the fused step's three-segment schedule without any flags
     add_segment(g.D - 2, g.D);
@@ -274,7 +294,10 @@ int launch_tma_fwd(percnn_plan* p, const float* src, float* dst, int z_lo, int z
   switch (p->slot) {
 #define PERCNN_TMA_CASE(S) \
   case S:                                                                                                   \
-    if (bwd) {                                                                                              \
+    if (bwd && p->bwd_mw && !p->bwd_split_mono) {                                                           \
+      if (prm.fused) le = launch_pdl(tma3d::k_gs3d_bwd_tma_mw<S, true>, grid, tma3d::MW_THREADS, tma3d::SMEM_BYTES_BWD_MW, st, p->pdl, *mm, *hm, h_map, prm, *bwd); \
+      else le = launch_pdl(tma3d::k_gs3d_bwd_tma_mw<S, false>, grid, tma3d::MW_THREADS, tma3d::SMEM_BYTES_BWD_MW, st, p->pdl, *mm, *hm, h_map, prm, *bwd); \
+    } else if (bwd) {                                                                                       \
       if (p->bwd_split_mono) {                                                                              \
         if (prm.fused) le = launch_pdl(tma3d::k_gs3d_bwd_tma<S, true, false>, grid, tma3d::BWD_THREADS, tma3d::SMEM_BYTES_BWD, st, p->pdl, *mm, *hm, prm, *bwd); \
         else le = launch_pdl(tma3d::k_gs3d_bwd_tma<S, false, false>, grid, tma3d::BWD_THREADS, tma3d::SMEM_BYTES_BWD, st, p->pdl, *mm, *hm, prm, *bwd); \
@@ -690,6 +713,10 @@ int percnn_plan_create(const percnn_desc_t* d, percnn_plan_t** out) {
       ae = cudaFuncSetAttribute(tma3d::k_gs3d_bwd_tma<S, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma3d::SMEM_BYTES_BWD); \
     if (ae == cudaSuccess)                                                                                               \
       ae = cudaFuncSetAttribute(tma3d::k_gs3d_bwd_tma<S, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma3d::SMEM_BYTES_BWD); \
+    if (ae == cudaSuccess)                                                                                               \
+      ae = cudaFuncSetAttribute(tma3d::k_gs3d_bwd_tma_mw<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma3d::SMEM_BYTES_BWD_MW); \
+    if (ae == cudaSuccess)                                                                                               \
+      ae = cudaFuncSetAttribute(tma3d::k_gs3d_bwd_tma_mw<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma3d::SMEM_BYTES_BWD_MW); \
     break;
         PERCNN_TMA_ATTR(0) PERCNN_TMA_ATTR(1) PERCNN_TMA_ATTR(2) PERCNN_TMA_ATTR(3) PERCNN_TMA_ATTR(4) PERCNN_TMA_ATTR(5)
 #undef PERCNN_TMA_ATTR
@@ -697,8 +724,10 @@ int percnn_plan_create(const percnn_desc_t* d, percnn_plan_t** out) {
       if (ae != cudaSuccess) { rc = fail(PERCNN_ERR_CUDA, "cudaFuncSetAttribute(tma) failed"); break; }
       int fixed_ty = 0;
       if (const char* e = getenv("PERCNN_TMA_TY")) fixed_ty = atoi(e);
-      if (fixed_ty < 0 || fixed_ty > tma3d::BWD_WARPS || fixed_ty > g.H) fixed_ty = 0;
-      const TmaTiling til = choose_tiling(g.W / tma3d::TX, g.H, g.D, p->sm_count, fixed_ty);
+      if (const char* e = getenv("PERCNN_BWD_MW")) p->bwd_mw = atoi(e) != 0;
+      const int max_ty = p->bwd_mw ? tma3d::MW_STENCIL : tma3d::BWD_WARPS;   // the tiling is shared by fwd and adjoint kernels
+      if (fixed_ty < 0 || fixed_ty > max_ty || fixed_ty > g.H) fixed_ty = 0;
+      const TmaTiling til = choose_tiling(g.W / tma3d::TX, g.H, g.D, p->sm_count, fixed_ty, max_ty);
       p->ty = til.ty;
       p->tz = til.tz;
       if (const char* e = getenv("PERCNN_NO_PDL")) p->pdl = atoi(e) == 0;

@@ -1,0 +1,2 @@
+mkdir -p gpurun_out
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_gs3d_bwd_tma -s 2 -c 1 -f -o gpurun_out/r01h_ncu_bwd_mw_512 python scripts/profile_step.py --n 512 --steps 4 --bwd > gpurun_out/r01h_ncu.log 2>&1; tail -2 gpurun_out/r01h_ncu.log
