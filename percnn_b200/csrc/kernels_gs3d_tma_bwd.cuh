@@ -416,16 +416,22 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
 // rows of G from the ring and h from global memory and keep all 40 partial sums in registers.  The 14 stencil warps
 // lose ~100 instructions and 20 shared-memory accesses per plane.  Layout (640 threads, as the forward kernel):
 //   warps 0..13  stencil warps, one tile row each (adjoint_plane<FUSED, false>)
-//   warps 14,15  monomial warps, rows 14/15 + 2 i of the tile
-//   warps 16..19 producer warp-group (one lane issues the TMA loads), registers handed to the others (setmaxnreg)
+//   warps 14,15  monomial warps, set A: the six monomials of degree >= 2 except u^2 (uv v^2 u^3 u^2v uv^2 v^3), even / odd rows
+//   warp  16     producer: one lane issues the TMA loads
+//   warps 17,18  monomial warps, set B: 1 u v u^2 (few registers: they live in the producer warp-group), even / odd rows
+//   warp  19     idle
+// With only two monomial warps doing all ten monomials those warps were the critical path (profiles/
+// r01_adjoint_mw_experiment.txt): 63 instructions per row against the stencil warps' 330 per plane.
 // Every consumer warp -- stencil or monomial -- waits on the same full barriers and releases plane k-4 after
-// iteration k, so the ring protocol is unchanged (empty barriers count ty + 2 arrivals).
+// iteration k, so the ring protocol is unchanged (empty barriers count ty + 4 arrivals).
 // =====================================================================================================
 constexpr int MW_STENCIL = 14;
 constexpr int MW_MONO = 2;
 constexpr int MW_CONSUMERS = MW_STENCIL + MW_MONO;
 constexpr int MW_THREADS = MW_CONSUMERS * 32 + 128;
-constexpr int MW_CONSUMER_REGS = 112;   // 512 * 112 + 128 * 24 <= 640 * 96 (setmaxnreg only redistributes the CTA's allocation)
+constexpr int MW_CONSUMER_REGS = 104;   // 512 * 104 + 128 * 48 <= 640 * 96 (setmaxnreg only redistributes the CTA's allocation)
+constexpr int MW_PRODUCER_REGS = 48;    // producer warp-group: the TMA lane + two light monomial warps (set B)
+constexpr int MW_WACC_ROWS = 20;        // one row of fp64 sums per warp of the CTA
 constexpr int MW_FLUSH = 8;             // planes between fp32 -> fp64 flushes of the monomial warps (<= 224 terms per lane sum)
 // The stored state h_t streams through its own small ring: plane (k - 4) of h travels with plane k of G (same full
 // barrier), is read during consumer iteration k and recycled with G plane k - 4, i.e. after that same iteration.
@@ -436,8 +442,101 @@ constexpr int HSTAGE_FLOATS = 2 * MW_STENCIL * TX;
 constexpr int MW_OFF_HRING = STAGES * STAGE_BYTES;
 constexpr int MW_OFF_BARS = MW_OFF_HRING + HSTAGES * HSTAGE_FLOATS * 4;
 constexpr int MW_OFF_WACC = MW_OFF_BARS + 2 * STAGES * 8 + 64;
-constexpr int SMEM_BYTES_BWD_MW = MW_OFF_WACC + 16 * kRedPiK1 * 8 + 64;
+constexpr int SMEM_BYTES_BWD_MW = MW_OFF_WACC + MW_WACC_ROWS * kRedPiK1 * 8 + 64;
 static_assert(SMEM_BYTES_BWD_MW <= 227 * 1024, "shared memory budget");
+
+// Monomial warp: sums  sum dt G_f u^a v^b  for the monomials of SET over the tile rows row0, row0 + 2, ... of every
+// plane.  SET 0 ("A"): uv v^2 u^3 u^2v uv^2 v^3 (reduction slots 4..9); SET 1 ("B"): 1 u v u^2 (slots 0..3).
+// All partial sums stay in registers: (cells 0+2, cells 1+3) pairs per monomial and field, folded every MW_FLUSH planes.
+template <int SET>
+__device__ __forceinline__ void mono_warp_loop(Consumer& c, const Params& p, const float* __restrict__ hring,
+                                               double* __restrict__ wacc, int nitems, int row0, int warp, int lane) {
+  constexpr int NM = SET == 0 ? 6 : 4;
+  constexpr int M0 = SET == 0 ? 4 : 0;
+  float2 au[NM], av[NM];
+#pragma unroll
+  for (int m = 0; m < NM; ++m) au[m] = av[m] = make_float2(0.f, 0.f);
+  int since_flush = 0;
+  uint32_t hcur = 0;
+  auto flush = [&]() {
+    const float dt = c.P[P_DT];
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+      float tu = au[m].x + au[m].y, tv = av[m].x + av[m].y;
+      au[m] = av[m] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        tu += __shfl_down_sync(0xffffffffu, tu, o);
+        tv += __shfl_down_sync(0xffffffffu, tv, o);
+      }
+      if (lane == 0) {
+        wacc[warp * kRedPiK1 + 2 + M0 + m] += double(dt) * double(tu);
+        wacc[warp * kRedPiK1 + 12 + M0 + m] += double(dt) * double(tv);
+      }
+    }
+    since_flush = 0;
+  };
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const ItemCoord ic = decode_item(p, item);
+    // first row of this warp that is not a duplicate of the previous tile (last tile of a column is shifted back)
+    int r0 = row0;
+    while (r0 < p.ty && (ic.y0 + r0) < ic.ytile * p.ty) r0 += MW_MONO;
+    if (p.debug & 8) r0 = p.ty;   // timing experiment without the monomial work
+    const int nk = ic.nz + 4;
+    for (int k = 0; k < nk; ++k) {
+      mbar_wait(&c.full[c.s], c.parity);
+      if (k >= 4) {
+        const float* st = c.ring + ((c.s + STAGES - 2) & (STAGES - 1)) * STAGE_FLOATS + 2 * TX + 4 * lane;   // plane k-2, tile row 0
+        const float* hst = hring + hcur * HSTAGE_FLOATS + 4 * lane;   // state plane of this output plane, tile row 0
+        float keep = 0.f;
+        for (int r = r0; r < p.ty; r += MW_MONO) {
+          const float4 Gu = lds128(st + r * TX), Gv = lds128(st + ROWS * TX + r * TX);
+          const float4 hu = lds128(hst + r * TX), hv = lds128(hst + MW_STENCIL * TX + r * TX);
+          keep = Gv.w + hv.w;
+          const float2 ul = lo(hu), uh = hi(hu), vl = lo(hv), vh = hi(hv);
+          const float2 gul = lo(Gu), guh = hi(Gu), gvl = lo(Gv), gvh = hi(Gv);
+          const float2 uul = __fmul2_rn(ul, ul), uuh = __fmul2_rn(uh, uh);
+#define PERCNN_MW_MONO(M, EL, EH)                                    \
+  {                                                                  \
+    const float2 el = EL, eh = EH;                                   \
+    au[M] = fma2(guh, eh, fma2(gul, el, au[M]));                     \
+    av[M] = fma2(gvh, eh, fma2(gvl, el, av[M]));                     \
+  }
+          if (SET == 1) {
+            au[0] = __fadd2_rn(au[0], __fadd2_rn(gul, guh));
+            av[0] = __fadd2_rn(av[0], __fadd2_rn(gvl, gvh));
+            PERCNN_MW_MONO(1, ul, uh)
+            PERCNN_MW_MONO(2, vl, vh)
+            PERCNN_MW_MONO(3, uul, uuh)
+          } else {
+            const float2 uvl = __fmul2_rn(ul, vl), uvh = __fmul2_rn(uh, vh);
+            const float2 vvl = __fmul2_rn(vl, vl), vvh = __fmul2_rn(vh, vh);
+            PERCNN_MW_MONO(0, uvl, uvh)
+            PERCNN_MW_MONO(1, vvl, vvh)
+            PERCNN_MW_MONO(2, __fmul2_rn(uul, ul), __fmul2_rn(uuh, uh))
+            PERCNN_MW_MONO(3, __fmul2_rn(uul, vl), __fmul2_rn(uuh, vh))
+            PERCNN_MW_MONO(4, __fmul2_rn(ul, vvl), __fmul2_rn(uh, vvh))
+            PERCNN_MW_MONO(5, __fmul2_rn(vvl, vl), __fmul2_rn(vvh, vh))
+          }
+#undef PERCNN_MW_MONO
+        }
+        // release plane k-4 like the stencil warps do (this warp has finished with every plane <= k-2); the
+        // data dependency on the last shared-memory loads keeps the arrive behind them (see mbar_arrive_after)
+        __syncwarp();
+        if (lane == 0) mbar_arrive_after(&c.empty[(c.s + STAGES - 4) & (STAGES - 1)], keep);
+        hcur = (hcur + 1) & (HSTAGES - 1);
+        if (++since_flush >= MW_FLUSH) flush();
+      }
+      advance_stage(c);
+    }
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 1; j <= 4; ++j) mbar_arrive(&c.empty[(c.s + STAGES - j) & (STAGES - 1)]);
+    }
+  }
+  flush();
+}
 
 template <int SLOT, bool FUSED>
 __global__ void __launch_bounds__(MW_THREADS, 1)
@@ -451,7 +550,7 @@ k_gs3d_bwd_tma_mw(const __grid_constant__ CUtensorMap tm_main, const __grid_cons
   uint64_t* empty = full + STAGES;
   double* wacc = reinterpret_cast<double*>(smem_raw + MW_OFF_WACC);   // [16][22]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nmono = MW_MONO;
+  const int nmono = 2 * MW_MONO;   // monomial warps: two of set A (consumer warp-groups) + two of set B (producer warp-group)
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
@@ -459,15 +558,32 @@ k_gs3d_bwd_tma_mw(const __grid_constant__ CUtensorMap tm_main, const __grid_cons
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < 16 * kRedPiK1; i += MW_THREADS) wacc[i] = 0.0;
+  for (int i = threadIdx.x; i < MW_WACC_ROWS * kRedPiK1; i += MW_THREADS) wacc[i] = 0.0;
   __syncthreads();
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const int nitems = total_items(p);
 
+  const int nsync = (p.ty + nmono) * 32;   // consumer threads that reach the final reduction
   if (warp >= MW_CONSUMERS) {
-    // ===== producer warp-group =====
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PRODUCER_REGS));
+    // ===== producer warp-group: TMA lane (warp 16), light monomial warps (17, 18) =====
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(MW_PRODUCER_REGS));
+    if (warp == MW_CONSUMERS + 1 || warp == MW_CONSUMERS + 2) {
+      Consumer c;
+      c.P = c_prep[SLOT].f;
+      c.ring = ring;
+      c.full = full;
+      c.empty = empty;
+      c.s = 0;
+      c.parity = 0;
+      c.row = 0;
+      c.lane = lane;
+      c.toff = 0;
+      c.is_seam = false;
+      mono_warp_loop<1>(c, p, hring, wacc, nitems, warp - (MW_CONSUMERS + 1), warp, lane);   // set B: even / odd rows
+      asm volatile("bar.sync 2, %0;" ::"r"(nsync) : "memory");   // joins the consumers' final reduction barrier
+      return;
+    }
     if (warp == MW_CONSUMERS && lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_main)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_halo)) : "memory");
@@ -519,7 +635,6 @@ k_gs3d_bwd_tma_mw(const __grid_constant__ CUtensorMap tm_main, const __grid_cons
   uint32_t hcur = 0;   // h stage of the output plane of the current iteration (advances with every k >= 4)
   const bool is_mono = warp >= MW_STENCIL;
   if (!is_mono && warp >= p.ty) return;   // tile shorter than 14 rows (after the aligned setmaxnreg)
-  const int nsync = (p.ty + nmono) * 32;  // consumer threads that reach the final reduction
   const int64_t plane = int64_t(p.H) * p.W;
   const int64_t field = p.dst_field;
   Consumer c;
@@ -535,86 +650,7 @@ k_gs3d_bwd_tma_mw(const __grid_constant__ CUtensorMap tm_main, const __grid_cons
   c.is_seam = (lane == 0) || (lane == 31);
 
   if (is_mono) {
-    // ===== monomial warps: 20 sums  sum dt G_f u^a v^b  over the rows mono_id, mono_id + 2, ... of every plane =====
-    const int mono_id = warp - MW_STENCIL;
-    float2 au[10], av[10];   // (cells 0+2, cells 1+3) partial sums per monomial, field u / field v
-#pragma unroll
-    for (int m = 0; m < 10; ++m) au[m] = av[m] = make_float2(0.f, 0.f);
-    int since_flush = 0;
-    auto flush = [&]() {
-      const float dt = c.P[P_DT];
-#pragma unroll
-      for (int m = 0; m < 10; ++m) {
-        float tu = au[m].x + au[m].y, tv = av[m].x + av[m].y;
-        au[m] = av[m] = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          tu += __shfl_down_sync(0xffffffffu, tu, o);
-          tv += __shfl_down_sync(0xffffffffu, tv, o);
-        }
-        if (lane == 0) {
-          wacc[warp * kRedPiK1 + 2 + m] += double(dt) * double(tu);
-          wacc[warp * kRedPiK1 + 12 + m] += double(dt) * double(tv);
-        }
-      }
-      since_flush = 0;
-    };
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-      const ItemCoord ic = decode_item(p, item);
-      // first row of this warp that is not a duplicate of the previous tile (last tile of a column is shifted back)
-      int r0 = mono_id;
-      while (r0 < p.ty && (ic.y0 + r0) < ic.ytile * p.ty) r0 += nmono;
-      const int nk = ic.nz + 4;
-      for (int k = 0; k < nk; ++k) {
-        mbar_wait(&c.full[c.s], c.parity);
-        if (k >= 4) {
-          const float* st = c.ring + ((c.s + STAGES - 2) & (STAGES - 1)) * STAGE_FLOATS + 2 * TX + 4 * lane;   // plane k-2, tile row 0
-          const float* hst = hring + hcur * HSTAGE_FLOATS + 4 * lane;   // state plane of this output plane, tile row 0
-          float keep = 0.f;
-          for (int r = (p.debug & 8) ? p.ty : r0; r < p.ty; r += nmono) {   // debug 8: timing experiment without the monomial work
-            const float4 Gu = lds128(st + r * TX), Gv = lds128(st + ROWS * TX + r * TX);
-            const float4 hu = lds128(hst + r * TX), hv = lds128(hst + MW_STENCIL * TX + r * TX);
-            keep = Gv.w + hv.w;
-            const float2 ul = lo(hu), uh = hi(hu), vl = lo(hv), vh = hi(hv);
-            const float2 gul = lo(Gu), guh = hi(Gu), gvl = lo(Gv), gvh = hi(Gv);
-            const float2 uul = __fmul2_rn(ul, ul), uuh = __fmul2_rn(uh, uh);
-            const float2 uvl = __fmul2_rn(ul, vl), uvh = __fmul2_rn(uh, vh);
-            const float2 vvl = __fmul2_rn(vl, vl), vvh = __fmul2_rn(vh, vh);
-#define PERCNN_MW_MONO(M, EL, EH)                                    \
-  {                                                                  \
-    const float2 el = EL, eh = EH;                                   \
-    au[M] = fma2(guh, eh, fma2(gul, el, au[M]));                     \
-    av[M] = fma2(gvh, eh, fma2(gvl, el, av[M]));                     \
-  }
-            au[0] = __fadd2_rn(au[0], __fadd2_rn(gul, guh));
-            av[0] = __fadd2_rn(av[0], __fadd2_rn(gvl, gvh));
-            PERCNN_MW_MONO(1, ul, uh)
-            PERCNN_MW_MONO(2, vl, vh)
-            PERCNN_MW_MONO(3, uul, uuh)
-            PERCNN_MW_MONO(4, uvl, uvh)
-            PERCNN_MW_MONO(5, vvl, vvh)
-            PERCNN_MW_MONO(6, __fmul2_rn(uul, ul), __fmul2_rn(uuh, uh))
-            PERCNN_MW_MONO(7, __fmul2_rn(uul, vl), __fmul2_rn(uuh, vh))
-            PERCNN_MW_MONO(8, __fmul2_rn(ul, vvl), __fmul2_rn(uh, vvh))
-            PERCNN_MW_MONO(9, __fmul2_rn(vvl, vl), __fmul2_rn(vvh, vh))
-#undef PERCNN_MW_MONO
-          }
-          // release plane k-4 like the stencil warps do (this warp has finished with every plane <= k-2); the
-          // data dependency on the last shared-memory load keeps the arrive behind it (see mbar_arrive_after)
-          __syncwarp();
-          if (lane == 0) mbar_arrive_after(&c.empty[(c.s + STAGES - 4) & (STAGES - 1)], keep);
-          hcur = (hcur + 1) & (HSTAGES - 1);
-          if (++since_flush >= MW_FLUSH) flush();
-        }
-        advance_stage(c);
-      }
-      __syncwarp();
-      if (lane == 0) {
-#pragma unroll
-        for (int j = 1; j <= 4; ++j) mbar_arrive(&c.empty[(c.s + STAGES - j) & (STAGES - 1)]);
-      }
-    }
-    flush();
+    mono_warp_loop<0>(c, p, hring, wacc, nitems, warp - MW_STENCIL, warp, lane);   // set A: even / odd rows
   } else {
     // ===== stencil warps =====
     const float* TP = c.P + (P_LAPT - P_LAP_C0);
@@ -708,7 +744,7 @@ k_gs3d_bwd_tma_mw(const __grid_constant__ CUtensorMap tm_main, const __grid_cons
   if (warp == 0) {
     if (lane < NR) {
       double s = 0;
-      for (int w = 0; w < MW_CONSUMERS; ++w) s += wacc[w * kRedPiK1 + lane];
+      for (int w = 0; w < MW_WACC_ROWS; ++w) s += wacc[w * kRedPiK1 + lane];
       x.partials[size_t(blockIdx.x) * NR + lane] = s;
     }
     __threadfence();
