@@ -11,7 +11,8 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_size_t, c_uint8, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpercnn_b200.so")
+#: PERCNN_B200_LIB selects another build of the same library (A/B timing of kernel variants); default: in-tree
+LIB_PATH = os.environ.get("PERCNN_B200_LIB") or os.path.join(_HERE, "libpercnn_b200.so")
 
 ABI_VERSION = 1
 F32, F64 = 0, 1

@@ -455,10 +455,9 @@ k_gs3d_fwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
     int xs = (lane == 0) ? ic.x0 - 2 : ic.x0 + TX;
     xs = xs < 0 ? xs + p.W : (xs >= p.W ? xs - p.W : xs);
     const int seam_off = warp * p.W + xs - ic.x0;
-    // Source plane whose seam cells are fetched next (local plane 2 = the first output plane, then one plane per
-    // iteration).  These are always planes [z0, z0 + nz) of the item itself, so the pointer never needs the
-    // periodic wrap (the last prefetch, at k = nz + 2, reads plane z0 + nz - 1).
-    const float* seam_ptr = src_xy + int64_t(src_plane(p, ic.z0, 2)) * plane + seam_off;
+    int pz = src_plane(p, ic.z0, 2);   // source plane whose seam cells are fetched next (local plane 2 first)
+    const float* seam_ptr = src_xy + int64_t(pz) * plane + seam_off;   // advanced by one plane per iteration
+    const int64_t wrap_back = int64_t(p.D) * plane;
 
     warm_plane<0>(c, true, wu, wv);
     warm_plane<1>(c, true, wu, wv);
@@ -471,6 +470,10 @@ k_gs3d_fwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
 #define PERCNN_STEADY(RR)                                                                                     \
   {                                                                                                           \
     seam_ptr += plane;                                                                                        \
+    if (p.wrap_z && ++pz >= p.D) {                                                                            \
+      pz -= p.D;                                                                                              \
+      seam_ptr -= wrap_back;                                                                                  \
+    }                                                                                                         \
     steady_plane<RR, FUSED>(c, k >= ic.nz + 2, k <= ic.nz + 2, seam_ptr, p.src_field, out, mirror, p.dst_field, \
                             wu, wv, seam_next);                                                               \
     out += plane;                                                                                             \

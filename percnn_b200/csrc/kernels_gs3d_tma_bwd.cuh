@@ -101,8 +101,11 @@ __device__ __forceinline__ void adjoint_plane(Consumer& c, const float* __restri
   }
   // plane k-4 is no longer needed by this warp (release only once the loads have completed, see mbar_arrive_after)
   __syncwarp();
-  // (the h stage read above is recycled together with this G stage, so its loads join the dependency)
-  if (c.lane == 0) mbar_arrive_after(&c.empty[(c.s + STAGES - 4) & (STAGES - 1)], (Lu_lo.x + Lv_lo.x) + (hu.w + hv.w));
+  // (in the warp-specialised kernel the h stage read above is recycled together with this G stage, so its loads join
+  // the dependency; with h in global memory the release must NOT wait for those long-latency loads)
+  float release_dep = Lu_lo.x + Lv_lo.x;
+  if (hsm != nullptr) release_dep += hu.w + hv.w;
+  if (c.lane == 0) mbar_arrive_after(&c.empty[(c.s + STAGES - 4) & (STAGES - 1)], release_dep);
   float4 au4 = make_float4(0.f, 0.f, 0.f, 0.f), av4 = au4;
   if (gadd != nullptr) {
     au4 = ldg128(gadd + off);
