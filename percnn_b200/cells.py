@@ -191,6 +191,26 @@ class PhysicsCell(_FusedCell):
         return ch, ch
 
 
+def data_loss_selection(step: int, effective_step, time_stride: int, first_frames: Optional[int] = None):
+    """Which states `torch.cat(outputs)[0:-1:time_stride]` picks (GS3D:394-403): `outputs` is [h_0] followed by
+    h_{s+1} for every s < step in `effective_step` (GS3D:191-212), the slice drops the last entry and keeps every
+    time_stride-th one; `first_frames` mirrors `pred[:idx]` (GS2D:398-401).  Returns (frame_state, sel) with
+    outputs[i] = state frame_state[i] and sel[s] = state s enters the loss (step + 1 entries).  Pure host logic."""
+    if int(time_stride) < 1:
+        raise ValueError("time_stride must be >= 1")
+    eff = set(int(s) for s in effective_step)
+    frame_state = [0] + [s + 1 for s in range(int(step)) if s in eff]
+    picked = [frame_state[i] for i in range(0, len(frame_state) - 1, int(time_stride))]
+    if first_frames is not None:
+        picked = picked[:int(first_frames)]
+    if not picked:
+        raise ValueError("data loss selects no frame")
+    sel = [False] * (int(step) + 1)
+    for st in picked:
+        sel[st] = True
+    return frame_state, sel
+
+
 class FusedRCNN(nn.Module):
     """`RCNN.forward()` (GS2D:162-190): unroll `step` cell steps, collect the effective ones.
 
@@ -250,14 +270,7 @@ class FusedRCNN(nn.Module):
         kernels (`percnn_data_loss_fwd`, injection inside the adjoint), not by slicing a dense trajectory."""
         self.init_state = self._initial_state()
         cell: _FusedCell = getattr(self, self.cell_attr)
-        eff = set(int(s) for s in self.effective_step)
-        frame_state = [0] + [s + 1 for s in range(self.step) if s in eff]     # outputs[i] is state frame_state[i]
-        picked = [frame_state[i] for i in range(0, len(frame_state) - 1, int(time_stride))]
-        if not picked:
-            raise ValueError("data loss selects no frame")
-        sel = [False] * (self.step + 1)
-        for st in picked:
-            sel[st] = True
+        frame_state, sel = data_loss_selection(self.step, self.effective_step, time_stride)
         states, loss = cell.rollout_data_loss(self.init_state, self.step, truth_sub, sel, int(space_stride))
         outputs = [self.init_state] + [states[st:st + 1] for st in frame_state[1:]]
         second_last_state = states[self.step - 1:self.step].clone() if self.step >= 2 else []

@@ -126,3 +126,50 @@ def test_pack_params_is_state_dict_order():
     flat = engine.pack_params(cell._packed_tensors(), torch.float32)
     assert flat.numel() == 2 + 125 + 2 * (3 * (2 * 2 + 2) + 2 + 1)
     assert flat[0] == cell.CA.detach() and flat[2 + 62] == cell.W_laplace.weight.detach()[0, 0, 2, 2, 2]
+
+
+def test_data_loss_selection_matches_oracle_and_python_slicing():
+    """Host logic of FusedRCNN.forward_data_loss: list index -> state index through effective_step (GS3D:191-212,
+    394-403), against the oracle's restatement and against literally slicing a Python list."""
+    from oracle import percnn_oracle as po
+    from percnn_b200.cells import data_loss_selection
+    cases = [(7, [0, 2, 3, 6], 2, None), (6, range(6), 5, None), (31, range(31), 15, None), (30, range(30), 15, None),
+             (9, range(9), 4, 2), (12, [1, 5, 11], 1, None), (5, range(5), 7, None)]
+    for step, eff, ts, ff in cases:
+        frame_state, sel = data_loss_selection(step, eff, ts, ff)
+        outputs = ["h0"] + [f"h{s + 1}" for s in range(step) if s in set(eff)]      # what RCNN.forward returns
+        picked = outputs[0:-1:ts]
+        if ff is not None:
+            picked = picked[:ff]
+        want = [int(name[1:]) for name in picked]
+        assert [s for s in range(step + 1) if sel[s]] == want
+        assert want == po.data_loss_frames(step, eff, ts, ff)
+        assert [f"h{i}" for i in frame_state] == outputs
+        assert len(sel) == step + 1 and not sel[step] or step in want
+    import pytest
+    with pytest.raises(ValueError):
+        data_loss_selection(3, [], 1)           # outputs = [h0] only: `[0:-1]` is empty
+    with pytest.raises(ValueError):
+        data_loss_selection(3, range(3), 0)
+
+
+def test_physics_spec_polynomials_match_the_scripts_formulas():
+    """losses.lambda_omega_spec / gray_scott_spec pack the reaction terms of FWD:337-340 / GS2D:321-328 as cubics;
+    evaluate the packing on random points against the formulas written out."""
+    import numpy as np
+    from percnn_b200 import losses
+    g = np.random.default_rng(0)
+    u, v = g.uniform(-1, 1, 50), g.uniform(-1, 1, 50)
+    mono = [np.ones_like(u), u, v, u * u, u * v, v * v, u ** 3, u * u * v, u * v * v, v ** 3]
+    ev = lambda c: sum(ci * m for ci, m in zip(c, mono))
+    lo = losses.lambda_omega_spec()
+    a = u * u + v * v
+    np.testing.assert_allclose(ev(lo.poly_u), (1 - a) * u + a * v, atol=1e-14)
+    np.testing.assert_allclose(ev(lo.poly_v), -a * u + (1 - a) * v, atol=1e-14)
+    assert lo.diff == (0.1, 0.1) and lo.dt == 0.0125 and lo.dx == 0.2
+    gs = losses.gray_scott_spec(2e-5, 5e-6, 1 / 25, 3 / 50, 0.5, 0.01)
+    np.testing.assert_allclose(ev(gs.poly_u), -u * v * v + (1 / 25) * (1 - u), atol=1e-15)
+    np.testing.assert_allclose(ev(gs.poly_v), u * v * v - (1 / 25 + 3 / 50) * v, atol=1e-15)
+    from percnn_b200.variants import gs2d, gs3d, lambda_omega_fwd
+    assert gs3d.loss_generator().spec.diff == (0.2, 0.1) and gs2d.loss_generator().spec.dx == 0.01
+    assert lambda_omega_fwd.loss_generator(dt=0.1, dx=0.5).spec.dt == 0.1
