@@ -65,6 +65,27 @@ def exchange_ghosts(buf: torch.Tensor, nz: int, rank: int, world: int, group=Non
     return dist.batch_isend_irecv(ops)
 
 
+def slab_loss_spec(global_shape, z0: int, nz: int, nsteps: int, sel, stride: int) -> "engine.DataLossSpec":
+    """Slab-local view of the global fused data loss `mse(states[sel][:, :, ::s, ::s, ::s], truth)`: the sampling
+    lattice `::stride` of the global grid must coincide with the slab's own (slab origin and depth multiples of the
+    stride), and the mean runs over the GLOBAL number of sampled points, so that the ranks' partial sums simply add
+    up (one scalar all-reduce).  Pure host logic (tests/test_halo_gloo.py)."""
+    D, H, W = (int(n) for n in global_shape)
+    stride = int(stride)
+    if stride < 1:
+        raise ValueError("stride must be >= 1")
+    if z0 % stride or nz % stride:
+        raise ValueError(f"slab [{z0}, {z0 + nz}) does not respect the loss stride {stride}")
+    sel = tuple(bool(e) for e in sel)
+    if len(sel) != nsteps + 1:
+        raise ValueError("selection mask needs nsteps + 1 entries")
+    if sel[nsteps]:
+        raise NotImplementedError("the last state has no adjoint step; the scripts' `[0:-1:...]` never selects it")
+    low = [(n + stride - 1) // stride for n in (D, H, W)]
+    n_total = sum(sel) * 2 * low[0] * low[1] * low[2]
+    return engine.DataLossSpec(sel=sel, stride=stride, n_total=n_total)
+
+
 class SlabRollout:
     """Forward rollout of a 3-D Pi-block cell on one slab of a slab-decomposed periodic grid."""
 
@@ -271,19 +292,8 @@ class SlabRollout:
         return tape
 
     def _loss_spec(self, nsteps: int, sel, stride: int) -> "engine.DataLossSpec":
-        """Slab-local view of the global fused data loss: the sampling lattice `::stride` of the global grid must
-        coincide with the local one (slab origin and depth multiples of the stride), and the mean runs over the
-        GLOBAL number of sampled points."""
-        if self.z0 % stride or self.nz % stride:
-            raise ValueError(f"slab [{self.z0}, {self.z0 + self.nz}) does not respect the loss stride {stride}")
-        sel = tuple(bool(e) for e in sel)
-        if len(sel) != nsteps + 1:
-            raise ValueError("selection mask needs nsteps + 1 entries")
-        if sel[nsteps]:
-            raise NotImplementedError("the last state has no adjoint step; the scripts' `[0:-1:...]` never selects it")
         D, (H, W) = self.nz * self.world, self.plan.spatial[1:]
-        n_total = sum(sel) * 2 * ((D + stride - 1) // stride) * ((H + stride - 1) // stride) * ((W + stride - 1) // stride)
-        return engine.DataLossSpec(sel=sel, stride=int(stride), n_total=n_total)
+        return slab_loss_spec((D, H, W), self.z0, self.nz, nsteps, sel, stride)
 
     def data_loss(self, tape: torch.Tensor, target_sub: torch.Tensor, sel, stride: int) -> torch.Tensor:
         """Fused data loss over the whole (global) grid: `mse_loss(states[sel][:, :, ::s, ::s, ::s], truth_sub)` with

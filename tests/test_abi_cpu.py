@@ -173,3 +173,18 @@ def test_physics_spec_polynomials_match_the_scripts_formulas():
     from percnn_b200.variants import gs2d, gs3d, lambda_omega_fwd
     assert gs3d.loss_generator().spec.diff == (0.2, 0.1) and gs2d.loss_generator().spec.dx == 0.01
     assert lambda_omega_fwd.loss_generator(dt=0.1, dx=0.5).spec.dt == 0.1
+
+
+def test_fused_losses_fail_loudly_without_cuda():
+    """No CPU fallback anywhere on the product path: CPU tensors raise before any library call."""
+    import pytest
+    import torch
+    from percnn_b200 import losses
+    from percnn_b200.variants import gs2d, lambda_omega_fwd
+    with pytest.raises(RuntimeError, match="CUDA"):
+        losses.physics_loss(torch.zeros(4, 2, 8, 8, dtype=torch.float64), losses.lambda_omega_spec())
+    with pytest.raises(RuntimeError, match="CUDA"):
+        lambda_omega_fwd.loss_gen(torch.zeros(4, 2, 8, 8, dtype=torch.float64), lambda_omega_fwd.loss_generator())
+    cell = gs2d.RCNNCell(input_channels=2, hidden_channels=8, input_kernel_size=5)
+    with pytest.raises(RuntimeError, match="(?i)cuda"):
+        cell.rollout_data_loss(torch.zeros(1, 2, 16, 16), 3, torch.zeros(1, 2, 8, 8), [True, False, False, False], 2)
