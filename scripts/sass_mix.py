@@ -24,7 +24,9 @@ print("  ".join(f"{k}:{v}" for k, v in ops.most_common(28)))
 body = []
 inside = False
 idx = [i for i, l in enumerate(txt[start:end]) if "STG.E.128" in l]
-first = next(i for i, l in enumerate(txt[start:end]) if "LDS.128" in l)
+first = next((i for i, l in enumerate(txt[start:end]) if "LDS.128" in l), None)
+if not idx or first is None:      # kernels without 128-bit loads/stores: the whole-function mix above is all there is
+    sys.exit(0)
 bops = collections.Counter()
 nb = 0
 for l in txt[start + first:start + idx[-1] + 1]:
