@@ -6,8 +6,7 @@
 A bench "step" is ONE full rollout (ROLLOUT_STEPS = 500 fused time steps, cfg4's rollout length) of the
 V-GS3D cell (k=1, hc=2, fp32, shipped-checkpoint weights) on a 512^3 periodic grid (cfg5's grid; 1 GiB of
 state, 2 GiB ping-pong working set > L2 so every step streams from HBM).  With N > 1 the grid is
-slab-decomposed along D over N ranks (strong scaling, NCCL / peer-memory halo exchange of 2 ghost planes
-per side per step, overlapped with the interior kernel).
+slab-decomposed along D over N ranks (strong scaling; the ghost planes cross NVLink from inside the step kernel).
 
 value   = timesteps/sec with the state resident in HBM (CUDA events, max over ranks)
 e2e     = same metric through the host-buffer C-ABI call percnn_rollout_fwd_host (H2D of parameters and
@@ -15,6 +14,15 @@ e2e     = same metric through the host-buffer C-ABI call percnn_rollout_fwd_host
 roofline= algorithmic bytes (16 B/cell/step fp32) / event time per step kernel vs MEASURED_PEAKS.json
 cpu_baseline / --impl reference = the oracle port of the reference's CPU PyTorch op sequence (the
           reference is Python and cannot travel to the GPU box) on a bounded sample of the same workload.
+
+The same JSON line also carries, so that the driver's BENCH/SCALE records hold them:
+  configs      every other BASELINE.json config on one GPU (cfg1 128^2 fp64 x200, cfg2 256^2 x1000, cfg3 512^2
+               40-step BPTT for V-BUR1 and V-BUR3, cfg4 128^3 x500), each with the CPU port timed beside it (N = 1)
+  train_gs3d_512  cfg5 as stated: taped forward + fused data loss (GS3D:403 pattern) + hand-derived adjoint at
+               512^3 on N GPUs (40 B/cell algorithmic), per-timestep time and fraction of the HBM peak
+  cfg4_gs3d_128   cfg4 (128^3 x 500) on N GPUs
+  halo_check   N > 1: slab-decomposed forward AND training step vs a single-GPU recompute of the same global
+               field on every rank, bit for bit (dL/dh0, states) / to 1e-6 (parameter sums)
 """
 import argparse
 import json
@@ -36,6 +44,7 @@ WORKLOADS = {
     "gs3d_128": dict(shape=(128, 128, 128), desc="V-GS3D k=1 hc=2 fp32, 128^3 periodic, 500-step forward rollout (cfg4; L2-resident)"),
 }
 BYTES_PER_CELL_STEP = 16  # fp32, 2 fields, read once + write once
+GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
 def load_peaks():
@@ -46,11 +55,15 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def load_gs3d_weights():
+def load_weights(alias):
     import numpy as np
     import torch
-    z = np.load(os.path.join(ROOT, "tests", "golden", "weights_gs3d.npz"))
+    z = np.load(os.path.join(GOLDEN, f"weights_{alias}.npz"))
     return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+def load_gs3d_weights():
+    return load_weights("gs3d")
 
 
 def synthetic_state(shape, z0, nz, device, dtype, seed=0):
@@ -68,6 +81,25 @@ def synthetic_state(shape, z0, nz, device, dtype, seed=0):
     h = torch.stack((u, v))
     h += 0.01 * (torch.rand(h.shape, generator=g, device=device, dtype=dtype) - 0.5)
     return h
+
+
+def smooth_state_2d(n, device, dtype, seed, lo, hi):
+    """Smooth periodic 2-field state in [lo, hi] (a few Fourier modes + 1 % noise)."""
+    import math
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    ax = torch.arange(n, dtype=torch.float64) * (2 * math.pi / n)
+    x, y = torch.meshgrid(ax, ax, indexing="ij")
+    fields = []
+    for _ in range(2):
+        f = torch.zeros(n, n, dtype=torch.float64)
+        for kx in range(3):
+            for ky in range(3):
+                a, p1, p2 = torch.rand(3, generator=g, dtype=torch.float64)
+                f += (a - 0.5) * torch.sin(kx * x + 2 * math.pi * p1) * torch.cos(ky * y + 2 * math.pi * p2)
+        f = (f - f.min()) / (f.max() - f.min())
+        fields.append(lo + (hi - lo) * f + 0.01 * (hi - lo) * torch.rand(n, n, generator=g, dtype=torch.float64))
+    return torch.stack(fields)[None].to(dtype).to(device)
 
 
 class ClockSampler:
@@ -159,6 +191,45 @@ def cpu_reference_rate(shape, budget_s=12.0, steps=1, warmup=1):
                       f"{cores} threads) on a {d}x{H}x{W} periodic slab of the {D}x{H}x{W} grid, scaled by cells"}
 
 
+def cpu_config_baselines():
+    """The reference's CPU PyTorch op sequence (oracle port) on the other BASELINE.json configs, bounded samples.
+    Returns {cfg: {"value": timesteps/s, "unit", "cores", "kind", "sample"}}."""
+    import torch
+    from oracle import percnn_oracle as po
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    out = {}
+
+    def fwd(name, variant, params, h0, nsample, nfull):
+        with torch.no_grad():
+            h = po.cell_step_torch(h0, params, variant)      # warm-up
+            t0 = time.perf_counter()
+            for _ in range(nsample):
+                h = po.cell_step_torch(h, params, variant)
+            dt = time.perf_counter() - t0
+        out[name] = {"value": nsample / dt, "unit": "timesteps/s", "cores": cores, "kind": "port",
+                     "sample": f"{nsample} of {nfull} forward steps, full grid {tuple(h0.shape[2:])}, {h0.dtype}"}
+
+    def bptt(name, variant, params, h0, nsample, nfull):
+        p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "laplace" not in k.lower() and "filter" not in k else v)
+             for k, v in params.items()}
+        h = h0.clone().requires_grad_(True)
+        t0 = time.perf_counter()
+        outs, _ = po.rollout_torch(h, p, variant, nsample, range(nsample))
+        loss = torch.cat(outs, 0)[0:-1:5, :, ::2, ::2].pow(2).mean()
+        loss.backward()
+        dt = time.perf_counter() - t0
+        out[name] = {"value": nsample / dt, "unit": "timesteps/s (forward + autograd backward)", "cores": cores, "kind": "port",
+                     "sample": f"back-propagation through {nsample} of {nfull} steps, full grid {tuple(h0.shape[2:])}, {h0.dtype}"}
+
+    fwd("cfg1", "fwd", load_weights("fwd"), po.ic_spiral_2d(128), 200, 200)
+    fwd("cfg2", "gs2d", load_weights("gs2d"), po.ic_gs_2d(256, seed=0), 200, 1000)
+    bptt("cfg3i_train", "bur1", load_weights("bur1"), po.ic_fourier_2d(512, seed=1), 10, 40)
+    bptt("cfg3ii_train", "bur3", po.make_phys_params("bur3"), po.ic_fourier_2d(512, seed=1, dtype=torch.float64), 10, 40)
+    fwd("cfg4", "gs3d", load_gs3d_weights(), po.ic_gs_3d((128, 128, 128), seed=0), 5, 500)
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -185,6 +256,90 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
+
+def _time_ms(fn, reps, dev):
+    import torch
+    fn()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1) / reps
+
+
+def gpu_config_blocks(dev, peak):
+    """cfg1-cfg4 of BASELINE.json on ONE GPU (device-resident inputs, CUDA events around whole rollouts)."""
+    import torch
+    from percnn_b200.variants import burgers_stage1, burgers_stage3, gs2d, gs3d, lambda_omega_fwd
+    out = {}
+    kw = dict(input_channels=2, hidden_channels=4, output_channels=2, input_kernel_size=5, input_stride=1, input_padding=2)
+
+    def fwd(name, cell, h0, nsteps, desc):
+        cell = cell.to(dev)
+        emit = [False] * nsteps
+        with torch.no_grad():
+            ms = _time_ms(lambda: cell.rollout_emit(h0, nsteps, emit, want_final=True), 5, dev)
+        ncell = h0[0, 0].numel()
+        esz = h0.element_size()
+        out[name] = {"workload": desc, "timesteps_per_s": nsteps / (ms * 1e-3), "us_per_timestep": 1e3 * ms / nsteps,
+                     "ms_per_rollout": ms, "effective_GBps": ncell * 4 * esz * nsteps / (ms * 1e-3) / 1e9}
+
+    def train(name, cell, h0, nsteps, desc):
+        cell = cell.to(dev)
+        h0 = h0.clone().requires_grad_(True)
+        sel = [(s % 5 == 0) and s < nsteps for s in range(nsteps + 1)]
+        n = h0.shape[-1]
+        tgt = smooth_state_2d(n, dev, h0.dtype, 2, -0.5, 0.5)[:, :, ::2, ::2].expand(sum(sel), -1, -1, -1).contiguous()
+
+        def step():
+            for p in cell.parameters():
+                p.grad = None
+            h0.grad = None
+            _, loss = cell.rollout_data_loss(h0, nsteps, tgt, sel, 2)
+            loss.backward()
+
+        ms = _time_ms(step, 3, dev)
+        out[name] = {"workload": desc, "timesteps_per_s": nsteps / (ms * 1e-3), "us_per_timestep_fwd_plus_adjoint": 1e3 * ms / nsteps,
+                     "ms_per_training_step": ms}
+
+    def guarded(f, name, *a):
+        try:
+            f(name, *a)
+        except Exception as e:  # a secondary measurement must never break the headline line
+            out[name] = {"error": str(e)[:200]}
+
+    c1 = lambda_omega_fwd.RCNNCell(input_kernel_size=1, input_stride=1, input_padding=0)
+    c1.load_state_dict(load_weights("fwd"))
+    guarded(fwd, "cfg1", c1, smooth_state_2d(128, dev, torch.float64, 1, -0.8, 0.8), 200,
+            "2-D lambda-omega 128^2, fp64, hc=4, 200-step forward rollout")
+    c2 = gs2d.RCNNCell(2, 8, 5)
+    c2.load_state_dict(load_weights("gs2d"))
+    guarded(fwd, "cfg2", c2, smooth_state_2d(256, dev, torch.float32, 1, 0.1, 0.9), 1000,
+            "2-D Gray-Scott 256^2, fp32, hc=8, 1000-step forward rollout")
+    c3 = burgers_stage1.RCNNCell(**kw)
+    c3.load_state_dict(load_weights("bur1"))
+    h3 = smooth_state_2d(512, dev, torch.float32, 1, -0.5, 0.5)
+    guarded(fwd, "cfg3i_fwd", c3, h3, 40, "2-D Burgers 512^2, 5x5 Pi-block hc=16 fp32, 40-step forward")
+    guarded(train, "cfg3i_train", c3, h3, 40, "2-D Burgers 512^2, 5x5 Pi-block hc=16 fp32, back-propagation through 40 steps (fused data loss)")
+    c3b = burgers_stage3.RCNNCell(**kw)
+    h3b = smooth_state_2d(512, dev, torch.float64, 1, -0.5, 0.5)
+    guarded(fwd, "cfg3ii_fwd", c3b, h3b, 40, "2-D Burgers 512^2, d/dx d/dy advection stencil cell fp64, 40-step forward")
+    guarded(train, "cfg3ii_train", c3b, h3b, 40, "2-D Burgers 512^2, advection stencil cell fp64, back-propagation through 40 steps")
+    c4 = gs3d.RCNNCell(2, 2, 5)
+    c4.load_state_dict(load_gs3d_weights())
+    guarded(fwd, "cfg4", c4, synthetic_state((128, 128, 128), 0, 128, dev, torch.float32)[None], ROLLOUT_STEPS,
+            "3-D Gray-Scott 128^3, fp32, hc=2, 500-step forward rollout (L2-resident: a latency number, not an HBM one)")
+    return out
+
+
+def train_steps_for(world):
+    """Tape length of the cfg5 training measurement: as close to the script's 150 steps as one GPU's HBM allows
+    (1 GiB per stored state at N = 1)."""
+    return min(150, 30 * world)
+
 
 def run_ours(args):
     import torch
@@ -223,13 +378,24 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     extra = {}
+    T = train_steps_for(world)
+    sel = tuple((t % 15 == 0) and t < T for t in range(T + 1))       # GS3D:403: output[:-1:15, :, ::2, ::2, ::2]
+    train_note = ("cfg5 as stated: taped forward + fused data loss (every 15th state, ::2 in space, GS3D:403) + hand-derived "
+                  "adjoint with the loss gradient injected; 40 B/cell algorithmic (16 fwd + 24 adjoint, SURVEY 8d); the "
+                  "reference's autograd needs 146 B/cell/step of saved activations and cannot hold this grid")
     if world == 1:
         plan = engine.get_plan(cell._spec(), shape, dev)
         plan.params_load(flat)
         a = synthetic_state(shape, 0, D, dev, torch.float32)
         b = torch.empty_like(a)
-        launches0 = plan.launch_count
 
         def rollout():
             plan.rollout_fwd(a, ROLLOUT_STEPS, h_final=b)
@@ -264,35 +430,11 @@ def run_ours(args):
         e2e = {"value": ROLLOUT_STEPS / e2e_s, "unit": "timesteps/s",
                "h2d_bytes_per_step": int(h0_h.numel() * 4 + flat_h.numel() * 4), "d2h_bytes_per_step": int(fin.numel() * 4),
                "api": "percnn_rollout_fwd_host (pinned host buffers; H2D + 500 steps + D2H per bench step)"}
-        # ---- secondary: cfg4 (128^3, L2-resident) in the same run ---------------------------------
-        if args.workload == "gs3d_512":
+        del fin, h0_h
+        if args.workload == "gs3d_512" and not args.headline_only:
+            # ---- cfg5 as stated, on this one GPU: one training step at 512^3 ----
             try:
-                s4 = (128, 128, 128)
-                p4 = engine.get_plan(cell._spec(), s4, dev)
-                p4.params_load(flat)
-                a4 = synthetic_state(s4, 0, 128, dev, torch.float32)
-                b4 = torch.empty_like(a4)
-                for _ in range(3):
-                    p4.rollout_fwd(a4, ROLLOUT_STEPS, h_final=b4)
-                torch.cuda.synchronize(dev)
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for _ in range(5):
-                    p4.rollout_fwd(a4, ROLLOUT_STEPS, h_final=b4)
-                e1.record()
-                torch.cuda.synchronize(dev)
-                ms4 = e0.elapsed_time(e1) / 5
-                extra["cfg4_gs3d_128"] = {"timesteps_per_s": ROLLOUT_STEPS / (ms4 * 1e-3), "ms_per_rollout": ms4,
-                                          "effective_GBps": 128 ** 3 * BYTES_PER_CELL_STEP * ROLLOUT_STEPS / (ms4 * 1e-3) / 1e9,
-                                          "note": "33.5 MB per step: L2-resident and launch-bound, not an HBM number"}
-            except Exception as e:  # secondary measurement must never break the headline line
-                extra["cfg4_gs3d_128"] = {"error": str(e)[:200]}
-            # ---- secondary: one training step at 512^3 (cfg5's grid on one GPU): taped forward, fused data loss
-            # (GS3D:403 pattern: every 4th state, ::2 in space), hand-derived adjoint with the loss gradient injected
-            try:
-                T = 8
                 tape = torch.empty((T + 1, *plan.buffer_shape), dtype=torch.float32, device=dev)
-                sel = tuple((t % 4 == 0) and t < T for t in range(T + 1))
                 spec = engine.DataLossSpec(sel=sel, stride=2)
                 tgt = torch.rand((spec.nsel, *plan.lowres_shape(2)), device=dev)
 
@@ -303,22 +445,28 @@ def run_ours(args):
 
                 train_step()
                 torch.cuda.synchronize(dev)
+                reps = 2
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                for _ in range(3):
+                for _ in range(reps):
                     loss, (g_h0, g_flat) = train_step()
                 e1.record()
                 torch.cuda.synchronize(dev)
-                ms_t = e0.elapsed_time(e1) / 3 / T
+                ms_t = e0.elapsed_time(e1) / reps / T
                 assert torch.isfinite(g_flat).all() and torch.isfinite(loss)
                 extra["train_gs3d_512"] = {
-                    "ms_per_timestep_fwd_plus_adjoint": ms_t, "timesteps_per_s": 1e3 / ms_t, "tape_steps": T,
+                    "ms_per_timestep_fwd_plus_adjoint": ms_t, "timesteps_per_s": 1e3 / ms_t, "tape_steps": T, "n_gpus": 1,
                     "achieved_GBps": ncell * 40 / (ms_t * 1e-3) / 1e9, "frac_of_peak": ncell * 40 / (ms_t * 1e-3) / 1e9 / peak,
-                    "note": "40 B/cell algorithmic (16 fwd + 24 adjoint, SURVEY 8d); fused data loss on states 0 and 4, stride 2; "
-                            "the reference's autograd needs 146 B/cell/step of saved activations and cannot hold this grid"}
+                    "note": train_note}
                 del tape, tgt, g_h0
             except Exception as e:
                 extra["train_gs3d_512"] = {"error": str(e)[:200]}
+            torch.cuda.empty_cache()
+            del a, b
+            engine.clear_plans()
+            extra["configs"] = gpu_config_blocks(dev, peak)
+            if "cfg4" in extra["configs"]:
+                extra["cfg4_gs3d_128"] = dict(extra["configs"]["cfg4"], n_gpus=1)
     else:
         from percnn_b200 import halo
         slab = halo.SlabRollout(cell, shape, dev, rank, world)
@@ -336,10 +484,7 @@ def run_ours(args):
             barrier()
             launches = slab.launch_count - l0
         step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-        total_ms = ev[0].elapsed_time(ev[-1])
-        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+        total_ms = max_over_ranks(ev[0].elapsed_time(ev[-1]))
         assert torch.isfinite(slab.interior()).all()
         uses_tma = slab.plan.uses_tma
         # end-to-end: each rank uploads its slab from pinned host memory and downloads the final slab
@@ -351,12 +496,77 @@ def run_ours(args):
         slab.run(ROLLOUT_STEPS)
         out_h.copy_(slab.interior(), non_blocking=True)
         barrier()
-        e2e_s = time.perf_counter() - t0
-        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": ROLLOUT_STEPS / float(t.item()), "unit": "timesteps/s", "h2d_bytes_per_step": int(h_h.numel() * 4) * world,
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": ROLLOUT_STEPS / e2e_s, "unit": "timesteps/s", "h2d_bytes_per_step": int(h_h.numel() * 4) * world,
                "d2h_bytes_per_step": int(out_h.numel() * 4) * world, "api": "percnn_b200.halo.SlabRollout (per-rank pinned slabs)"}
         extra["halo"] = slab.describe()
+        del h_h, out_h
+        if args.workload == "gs3d_512" and not args.headline_only:
+            # ---- correctness of the multi-GPU path inside the timed artefact: slab vs single-GPU recompute ----
+            try:
+                extra["halo_check"] = halo_check(slab, cell, flat, shape, dev, world)
+            except Exception as e:
+                extra["halo_check"] = {"error": str(e)[:300]}
+            barrier()
+            # ---- cfg5 as stated: domain-decomposed training rollout on N GPUs ----
+            try:
+                spec_sel = sel
+                nsel = sum(spec_sel)
+                tgt = torch.rand((nsel, 2, slab.nz // 2, H // 2, W // 2), device=dev)
+                h0_slab = synthetic_state(shape, slab.z0, slab.nz, dev, torch.float32)
+                gscale = torch.tensor(10.0, device=dev)        # `10*loss_data` (GS3D:407)
+
+                def train_step():
+                    slab.set_state(h0_slab)
+                    tape = slab.rollout_tape(T)
+                    loss = slab.data_loss(tape, tgt, spec_sel, 2)
+                    g_h0, grads = slab.backward(tape, None, loss=(tgt, spec_sel, 2, gscale))
+                    return loss, grads
+
+                train_step()
+                barrier()
+                reps = 2
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    loss, grads = train_step()
+                e1.record()
+                barrier()
+                ms_t = max_over_ranks(e0.elapsed_time(e1)) / reps / T
+                ok = bool(torch.isfinite(grads).all() and torch.isfinite(loss))
+                extra["train_gs3d_512"] = {
+                    "ms_per_timestep_fwd_plus_adjoint": ms_t, "timesteps_per_s": 1e3 / ms_t, "tape_steps": T, "n_gpus": world,
+                    "achieved_GBps_per_gpu": ncell / world * 40 / (ms_t * 1e-3) / 1e9,
+                    "frac_of_peak_per_gpu": ncell / world * 40 / (ms_t * 1e-3) / 1e9 / peak, "finite": ok,
+                    "includes": "set_state (ghost exchange + barriers), taped forward, fused loss (1 scalar all-reduce), fused-halo adjoint, "
+                                "one 24-value all-reduce of the parameter sums", "note": train_note}
+                del tgt, h0_slab
+                slab._tape = None
+                slab._tape_shape = None
+            except Exception as e:
+                extra["train_gs3d_512"] = {"error": str(e)[:300]}
+            barrier()
+            torch.cuda.empty_cache()
+            # ---- cfg4 as stated: 128^3 x 500 steps on N GPUs ----
+            try:
+                s4 = (128, 128, 128)
+                slab4 = halo.SlabRollout(cell, s4, dev, rank, world)
+                slab4.set_state(synthetic_state(s4, slab4.z0, slab4.nz, dev, torch.float32))
+                for _ in range(3):
+                    slab4.run(ROLLOUT_STEPS)
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(5):
+                    slab4.run(ROLLOUT_STEPS)
+                e1.record()
+                barrier()
+                ms4 = max_over_ranks(e0.elapsed_time(e1)) / 5
+                extra["cfg4_gs3d_128"] = {"workload": "3-D Gray-Scott 128^3, fp32, hc=2, 500-step forward rollout, slab-decomposed",
+                                          "n_gpus": world, "timesteps_per_s": ROLLOUT_STEPS / (ms4 * 1e-3), "us_per_timestep": 1e3 * ms4 / ROLLOUT_STEPS,
+                                          "ms_per_rollout": ms4, "halo": slab4.describe(), "finite": bool(torch.isfinite(slab4.interior()).all())}
+            except Exception as e:
+                extra["cfg4_gs3d_128"] = {"error": str(e)[:300]}
 
     nsteps_total = ROLLOUT_STEPS * args.steps
     seconds = total_ms * 1e-3
@@ -374,29 +584,87 @@ def run_ours(args):
                    "weights": "tests/golden/weights_gs3d.npz (reference 3d_gs_rd checkpoint)", "tma_kernel": bool(uses_tma)},
         "cell_steps_per_sec": value * ncell,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "k_gs3d_fwd_tma",
+                     "traffic": None, "peak_source": peak_src, "kernel": "k_gs3d_fwd_tma" if world == 1 else "k_gs3d_fwd_slab",
                      "how": "16 B/cell x cells per GPU / (CUDA-event time of the rollout / launches)"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clk.summary(),
         "step_ms": step_ms,
     }
     line.update(extra)
     if rank == 0:
-        if world == 1 and not args.no_cpu_baseline:
-            r = cpu_reference_rate(shape, budget_s=15.0, steps=1, warmup=0)
-            line["cpu_baseline"] = {"value": r["cell_steps_per_s"] / ncell, "unit": "timesteps/s", "cores": r["cores"],
-                                    "kind": "port", "sample": r["sample"]}
-        prof = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(prof):
-            try:
-                with open(prof) as f:
-                    line["roofline"]["traffic"] = json.load(f).get(args.workload)
-            except Exception:
-                pass
+        if world == 1:
+            # dram bytes of one launch from the committed `ncu --set full` capture of THIS workload on one GPU
+            prof = os.path.join(ROOT, "profiles", "traffic.json")
+            if os.path.exists(prof):
+                try:
+                    with open(prof) as f:
+                        line["roofline"]["traffic"] = json.load(f).get(args.workload)
+                except Exception:
+                    pass
+            if not args.no_cpu_baseline:
+                r = cpu_reference_rate(shape, budget_s=15.0, steps=1, warmup=0)
+                line["cpu_baseline"] = {"value": r["cell_steps_per_s"] / ncell, "unit": "timesteps/s", "cores": r["cores"],
+                                        "kind": "port", "sample": r["sample"]}
+                if "configs" in line:
+                    try:
+                        for k, v in cpu_config_baselines().items():
+                            line["configs"].setdefault(k, {})["cpu_baseline"] = v
+                    except Exception as e:
+                        line["configs"]["cpu_baseline_error"] = str(e)[:200]
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def halo_check(slab, cell, flat, shape, dev, world):
+    """Slab-decomposed rollout and training step vs a single-GPU recompute of the SAME global field on every rank.
+    5 forward steps (both march directions, odd count) and a 4-step taped forward + fused-loss adjoint."""
+    import torch
+    import torch.distributed as dist
+    from percnn_b200 import engine
+    D, H, W = shape
+    z0, nz = slab.z0, slab.nz
+    full = synthetic_state(shape, 0, D, dev, torch.float32, seed=11)      # identical on every rank
+    plan1 = engine.get_plan(cell._spec(), shape, dev)
+    plan1.params_load(flat)
+    ref = torch.empty_like(full)
+    plan1.rollout_fwd(full, 5, h_final=ref)
+    slab.set_state(full[:, z0:z0 + nz])
+    slab.run(5)
+    fwd_ok = bool(torch.equal(slab.interior(), ref[:, z0:z0 + nz]))
+    del ref
+    # training step: T = 4, loss on states 0 and 2, stride 2
+    T = 4
+    sel = (True, False, True, False, False)
+    spec = engine.DataLossSpec(sel=sel, stride=2)
+    g = torch.Generator(device=dev).manual_seed(5)
+    tgt_full = torch.rand((2, *plan1.lowres_shape(2)), generator=g, device=dev)
+    tape1 = torch.empty((T + 1, *plan1.buffer_shape), dtype=torch.float32, device=dev)
+    plan1.rollout_fwd(full, T, tape=tape1)
+    loss1 = plan1.data_loss_fwd(tape1, T, spec, tgt_full)
+    g_h0_ref, g_flat_ref = plan1.rollout_bwd_loss(flat, tape1, T, spec, tgt_full)
+    slab.set_state(full[:, z0:z0 + nz])
+    tape = slab.rollout_tape(T)
+    tape_ok = bool(torch.equal(tape[:, :, 2:nz + 2], tape1[:, :, z0:z0 + nz]))
+    tgt_loc = tgt_full[:, :, z0 // 2:(z0 + nz) // 2].contiguous()
+    loss = slab.data_loss(tape, tgt_loc, sel, 2)
+    g_h0, grads = slab.backward(tape, None, loss=(tgt_loc, sel, 2, None))
+    gh_ok = bool(torch.equal(g_h0, g_h0_ref[:, z0:z0 + nz]))
+    gp_err = float((grads.double() - g_flat_ref.double()).norm() / g_flat_ref.double().norm())
+    loss_err = abs(float(loss) - float(loss1)) / abs(float(loss1))
+    slab._tape = None
+    slab._tape_shape = None
+    del tape, tape1, full
+    flags = torch.tensor([int(fwd_ok), int(tape_ok), int(gh_ok), int(gp_err < 1e-6), int(loss_err < 1e-6)], device=dev)
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    f = [bool(x) for x in flags.tolist()]
+    res = {"forward_5_steps": "bitwise" if f[0] else "MISMATCH", "taped_forward_4_steps": "bitwise" if f[1] else "MISMATCH",
+           "adjoint_dL_dh0": "bitwise" if f[2] else "MISMATCH", "param_grad_rel_err": gp_err, "param_grads_ok": f[3],
+           "loss_rel_err": loss_err, "loss_ok": f[4], "ranks": world, "grid": list(shape),
+           "against": "single-GPU recompute of the same global field on every rank (k_gs3d_fwd_tma / k_gs3d_bwd_tma)"}
+    res["ok"] = all(f)
+    return res
 
 
 def main():
@@ -407,6 +675,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="gs3d_512", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--headline-only", action="store_true", help="skip the secondary blocks (configs, training, halo check)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     return run_reference(args) if args.impl == "reference" else run_ours(args)

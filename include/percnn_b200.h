@@ -20,7 +20,9 @@
  *    reference's h[0] of shape [1,2,(D,)H,W].
  *  - `params` / `param_grads`: flat array of plan-dtype scalars = the cell's state_dict tensors
  *    concatenated in state_dict order (see percnn_param_count and DESIGN.md "parameter packing").
- *  - a plan is used from one host thread at a time; distinct plans are independent.
+ *  - a plan is used from one host thread AND one stream at a time (it owns one constant-memory parameter slot, one
+ *    grid-barrier counter and its tensor maps); distinct plans are independent.  Every entry point makes the
+ *    plan's device current for the duration of the call and restores the caller's device.
  */
 #ifndef PERCNN_B200_H_
 #define PERCNN_B200_H_
@@ -32,7 +34,7 @@
 extern "C" {
 #endif
 
-#define PERCNN_ABI_VERSION 1
+#define PERCNN_ABI_VERSION 2
 
 typedef enum {
   PERCNN_OK = 0,
@@ -116,25 +118,49 @@ int percnn_step_fwd(percnn_plan_t* plan, const void* h_in, void* h_out, void* st
 /* Same step restricted to interior planes [z_lo, z_hi) of the slowest axis (3-D TMA plans only).  Lets the
  * slab-mode driver launch the planes that do not touch ghost cells before the halo exchange lands. */
 int percnn_step_fwd_range(percnn_plan_t* plan, const void* h_in, void* h_out, int z_lo, int z_hi, void* stream);
-/* Slab-mode step with the halo exchange fused into the kernel (multi-GPU, peer-mapped buffers over NVLink):
- * the kernel computes the 2+2 boundary planes first and stores them both locally and into the neighbours'
- * ghost planes, raises the neighbours' flags (release, system scope) when all of them have landed, then
- * computes the interior.  Before touching its own ghost planes it waits (acquire) for my_flags >= epoch.
- * No NCCL call and no host round trip per step.  All pointers are device pointers; peer_* are peer mappings. */
+/* Slab-mode step with the halo exchange fused into the kernel (multi-GPU, peer-mapped buffers over NVLink; replaces
+ * nothing in the reference, which is single-GPU -- it is north_star's "domain-decomposed ... halo exchange of the
+ * ghost cells only").  ONE kernel per time step marches every tile through all local planes in a
+ * single pass; output planes 0,1 and D-2,D-1 are stored locally AND into the neighbours' ghost planes; when all
+ * tiles have stored a boundary pair the kernel raises that neighbour's flag (release, system scope).  Before its
+ * first TMA load of a ghost plane it waits (acquire) for my_flags >= epoch.  The march direction alternates with
+ * the parity of `epoch` (even: ascending z, odd: descending), so that every ghost plane is produced almost a full
+ * step before it is consumed and no NVLink latency is exposed.  A wait that exceeds its spin deadline sets the
+ * error word and TRAPS (the rollout must not continue on stale ghosts): the caller sees a CUDA error at its next
+ * synchronisation.  No NCCL call and no host round trip per step.  All pointers are device pointers. */
 typedef struct percnn_slab_link {
   void* peer_lo_out;        /* lower ring neighbour's h_out buffer (same [2][D+4][H][W] layout) */
   void* peer_hi_out;        /* upper ring neighbour's h_out buffer */
   const uint32_t* my_flags; /* [0]: epoch up to which my LOWER ghosts are valid, [1]: same for the UPPER ghosts */
   uint32_t* peer_lo_flags;  /* the lower neighbour's flags array (its [1] is raised by this step) */
   uint32_t* peer_hi_flags;  /* the upper neighbour's flags array (its [0] is raised by this step) */
-  uint32_t* scratch;        /* 2 local words, zero-initialised: CTA arrival counter, error word (spin deadline) */
-  uint32_t epoch;           /* waits for flags >= epoch, publishes epoch + 1 */
+  uint32_t* scratch;        /* 3 local words, zero-initialised: arrival counter (lower boundary), error word (spin
+                               deadline), arrival counter (upper boundary) */
+  uint32_t epoch;           /* waits for flags >= epoch, publishes epoch + 1; parity selects the march direction */
 } percnn_slab_link_t;
 int percnn_step_fwd_fused_halo(percnn_plan_t* plan, const void* h_in, void* h_out, const percnn_slab_link_t* link,
                                void* stream);
 /* Adjoint of the fused slab step: g_in's boundary planes are mirrored into the neighbours' g_in ghost planes. */
 int percnn_step_bwd_fused_halo(percnn_plan_t* plan, const void* h_in, const void* g_out, const void* g_add, void* g_in,
                                void* ws, const percnn_slab_link_t* link, void* stream);
+/* The ping-pong buffers of a slab rank and their peer mappings: everything a whole slab rollout needs. */
+typedef struct percnn_slab_ring {
+  void* buf[2];             /* my two state (or gradient) buffers, [2][D+4][H][W] each */
+  void* peer_lo_buf[2];     /* the lower neighbour's two buffers (peer-mapped) */
+  void* peer_hi_buf[2];     /* the upper neighbour's */
+  const uint32_t* my_flags; /* as in percnn_slab_link_t */
+  uint32_t* peer_lo_flags;
+  uint32_t* peer_hi_flags;
+  uint32_t* scratch;
+} percnn_slab_ring_t;
+/* RCNN.forward's loop (GS3D:186-214) on one slab: `nsteps` fused steps issued from ONE host call; step s reads
+ * buf[cur ^ (s & 1)], writes the other buffer and uses epoch + s.  The state ends in buf[cur ^ (nsteps & 1)]. */
+int percnn_slab_rollout_fwd(percnn_plan_t* plan, const percnn_slab_ring_t* ring, int cur, int nsteps, uint32_t epoch,
+                            void* stream);
+/* Same, keeping every state: step t reads tape slot t and writes slot t+1, mirroring the boundary planes into the
+ * neighbours' slot t+1 (`peer_*_tape` are the peer mappings of their tapes; slots are percnn_state_elems apart). */
+int percnn_slab_rollout_tape(percnn_plan_t* plan, void* tape, void* peer_lo_tape, void* peer_hi_tape,
+                             const percnn_slab_ring_t* ring, int nsteps, uint32_t epoch, void* stream);
 /* Adjoint of one step (replaces autograd through GS2D:105-121): g_in = g_add + (dh_out/dh_in)^T g_out
  * (g_add may be NULL), and the step's parameter-gradient sums are ACCUMULATED into the accumulator at the
  * head of `ws` (zeroed by percnn_param_grads_begin, read by percnn_param_grads_finish). */
@@ -192,6 +218,14 @@ int percnn_step_bwd_loss(percnn_plan_t* plan, const void* h_in, const void* g_ou
 int percnn_rollout_bwd_loss(percnn_plan_t* plan, const void* params, const void* tape, const void* g_tape,
                             const uint8_t* gmask, const percnn_data_loss_t* loss, int nsteps, void* g_h0,
                             void* param_grads, void* ws, void* stream);
+/* Back-propagation through a taped slab rollout (loss.backward() of GS3D:407 on one slab): ring->buf[0] holds
+ * dL/dh_nsteps with exchanged ghosts; step t = nsteps-1 .. 0 runs the fused-halo adjoint from buf[b] to buf[b ^ 1]
+ * (b starts at 0), so dL/dh_0 ends in buf[nsteps & 1].  `g_tape` (nullable): dense dL/d(tape slot t) in the ghosted
+ * layout, added at step t.  `loss` (nullable): fused data loss with the GLOBAL n_total; sel[nsteps] must be 0.
+ * Parameter sums accumulate at the head of `ws` (percnn_param_grads_begin before; all-reduce them across ranks and
+ * call percnn_param_grads_finish after). */
+int percnn_slab_rollout_bwd(percnn_plan_t* plan, const void* tape, const void* g_tape, const percnn_data_loss_t* loss,
+                            const percnn_slab_ring_t* ring, int nsteps, uint32_t epoch, void* ws, void* stream);
 
 /* ---- fused physics-residual loss ------------------------------------------ */
 /* `loss_gen(output, loss_generator(dt, dx))` of the scripts (FWD:288-357, the TRAINING loss of the forward-simulation

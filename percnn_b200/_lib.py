@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 #: PERCNN_B200_LIB selects another build of the same library (A/B timing of kernel variants); default: in-tree
 LIB_PATH = os.environ.get("PERCNN_B200_LIB") or os.path.join(_HERE, "libpercnn_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 F32, F64 = 0, 1
 CELL_PI, CELL_BURGERS, CELL_LO = 0, 1, 2
 COEF_RAW, COEF_SIGMOID = 0, 1
@@ -29,6 +29,7 @@ EXPORTS = (
     "percnn_param_grads_begin", "percnn_param_grads_finish", "percnn_rollout_fwd", "percnn_rollout_bwd",
     "percnn_rollout_fwd_host", "percnn_data_loss_fwd", "percnn_step_bwd_loss", "percnn_rollout_bwd_loss",
     "percnn_phys_loss_workspace_bytes", "percnn_phys_loss_fwd", "percnn_phys_loss_bwd",
+    "percnn_slab_rollout_fwd", "percnn_slab_rollout_tape", "percnn_slab_rollout_bwd",
 )
 
 
@@ -46,6 +47,14 @@ class SlabLink(ctypes.Structure):
     _fields_ = [
         ("peer_lo_out", c_void_p), ("peer_hi_out", c_void_p), ("my_flags", c_void_p), ("peer_lo_flags", c_void_p),
         ("peer_hi_flags", c_void_p), ("scratch", c_void_p), ("epoch", ctypes.c_uint32),
+    ]
+
+
+class SlabRing(ctypes.Structure):
+    """percnn_slab_ring_t"""
+    _fields_ = [
+        ("buf", c_void_p * 2), ("peer_lo_buf", c_void_p * 2), ("peer_hi_buf", c_void_p * 2), ("my_flags", c_void_p),
+        ("peer_lo_flags", c_void_p), ("peer_hi_flags", c_void_p), ("scratch", c_void_p),
     ]
 
 
@@ -110,6 +119,9 @@ def lib() -> ctypes.CDLL:
     L.percnn_data_loss_fwd.argtypes = [vp, vp, c_int, POINTER(DataLoss), vp, vp, vp]
     L.percnn_step_bwd_loss.argtypes = [vp, vp, vp, vp, vp, c_int, c_int64, vp, vp, vp, POINTER(SlabLink), vp]
     L.percnn_rollout_bwd_loss.argtypes = [vp, vp, vp, vp, POINTER(c_uint8), POINTER(DataLoss), c_int, vp, vp, vp, vp]
+    L.percnn_slab_rollout_fwd.argtypes = [vp, POINTER(SlabRing), c_int, c_int, ctypes.c_uint32, vp]
+    L.percnn_slab_rollout_tape.argtypes = [vp, vp, vp, vp, POINTER(SlabRing), c_int, ctypes.c_uint32, vp]
+    L.percnn_slab_rollout_bwd.argtypes = [vp, vp, vp, POINTER(DataLoss), POINTER(SlabRing), c_int, ctypes.c_uint32, vp, vp]
     L.percnn_phys_loss_workspace_bytes.restype = c_size_t
     L.percnn_phys_loss_fwd.argtypes = [POINTER(PhysLoss), vp, vp, vp, vp, vp]
     L.percnn_phys_loss_bwd.argtypes = [POINTER(PhysLoss), vp, vp, vp, vp, vp]

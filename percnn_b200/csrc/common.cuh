@@ -26,10 +26,12 @@ enum PrepIndex : int {
   P_PHYS = 16,     // Burgers: C1_u C2_u C1_v C2_v | dx taps[4] | dy taps[4]   (taps / dx, BUR3:78-80)
                    // LO:      C1..C5_u | C1..C5_v | C6_v
   P_BRANCH = 64,   // raw 1x1 weights for PERCNN_FLAG_EVAL_BRANCH: per field W1[hc][2] b1[hc] W2.. W3.. W4[hc] b4
-  P_LAPT = 384,    // [13] Laplacian taps mirrored along every axis (the adjoint stencil): c0, then [3][4]
-  P_SIZE = 400
+  P_LAPT = 392,    // [13] Laplacian taps mirrored along every axis (the adjoint stencil): c0, then [3][4]
+  P_SIZE = 408
 };
 constexpr int kMaxHidden = 16;
+static_assert(P_BRANCH + 2 * (10 * kMaxHidden + 1) <= P_LAPT, "the EVAL_BRANCH weight copy must not reach the mirrored taps");
+static_assert(P_LAPT + 13 <= P_SIZE, "prep block too small");
 constexpr int kPrepSlots = 6;
 
 struct PrepBlock {
@@ -37,9 +39,9 @@ struct PrepBlock {
   double d[P_SIZE];
 };
 
-// The library is one translation unit (percnn_abi.cu includes every kernel header), so the constant
-// block is defined here once.
-__constant__ PrepBlock c_prep[kPrepSlots];
+// The library is several translation units compiled in parallel; each holds its own copy of the block
+// (`static`: no cross-TU symbol) and percnn_params_load fills every copy (plan.h: *_load_prep).
+static __constant__ PrepBlock c_prep[kPrepSlots];
 
 // number of reduction quantities the adjoint kernels produce per step
 constexpr int kRedPiK1 = 22;     // S_Lu S_Lv | M^u_ab[10] | M^v_ab[10]

@@ -64,9 +64,11 @@ struct Params {
   const uint32_t* my_flags;  // [0] epoch up to which my lower ghosts are valid, [1] same for the upper ghosts
   uint32_t* post_lo_flag;    // lower neighbour's flags[1] (I write its upper ghosts)
   uint32_t* post_hi_flag;    // upper neighbour's flags[0]
-  uint32_t* scratch;         // [0] CTA arrival counter, [1] error word (spin deadline exceeded)
+  uint32_t* scratch;         // [0] arrival counter (lower boundary), [1] error word (spin deadline exceeded),
+                             // [2] arrival counter (upper boundary)
   uint32_t epoch_wait, epoch_post;
   int debug;                 // bisecting aid: 1 = no mirror stores, 2 = no flag wait, 4 = no flag post
+  uint32_t spin_limit;       // flag-wait spins before the kernel gives up (error word + trap)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -209,13 +211,17 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// Spin until *flag >= epoch (wrap-safe).  Bounded: a lost peer sets the error word instead of hanging the GPU.
-__device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t epoch, uint32_t* err) {
-  for (uint32_t spins = 0; spins < (1u << 26); ++spins) {
+// Spin until *flag >= epoch (wrap-safe).  Bounded: a lost peer must not hang the GPU, but carrying on with stale
+// ghost planes would silently corrupt the rollout, so the deadline is FATAL: the error word is set (for a
+// debugger / the peer) and the kernel traps, which surfaces as a CUDA error at the caller's next synchronisation.
+__device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t epoch, uint32_t* err, uint32_t spin_limit) {
+  for (uint32_t spins = 0; spins < spin_limit; ++spins) {
     if (int32_t(ld_acquire_sys(flag) - epoch) >= 0) return;
     __nanosleep(64);
   }
   atomicExch(err, 1u);
+  __threadfence_system();
+  __trap();
 }
 __device__ __forceinline__ int src_plane(const Params& p, int z0, int j) {
   // z0 + j + src_zoff lies in [-2, D + 1]; the host only picks this kernel for D >= 4, so one
@@ -269,7 +275,10 @@ __device__ __forceinline__ void warm_plane(Consumer& c, bool release_now, float4
 // Steady-state plane: local plane k arrives, output plane k-2 is produced.
 //   seam_ptr : this lane's seam cells in the source plane that will be the in-plane source NEXT iteration
 //   out      : this lane's quad in the output plane
-template <int R, bool FUSED>
+//   DOWN     : the item is marched towards decreasing z (slab kernel, odd steps): the window then holds the planes
+//              in descending order, so it is handed to lap_quad reversed -- the arithmetic (and its rounding)
+//              is the same whatever the direction
+template <int R, bool FUSED, bool DOWN = false>
 __device__ __forceinline__ void steady_plane(Consumer& c, bool drain, bool prefetch_seam, const float* seam_ptr,
                                              int64_t src_field, float* out, float* mirror, int64_t dst_field,
                                              float4 (&wu)[5], float4 (&wv)[5], float2 (&seam_next)[2]) {
@@ -291,8 +300,10 @@ __device__ __forceinline__ void steady_plane(Consumer& c, bool drain, bool prefe
   }
   const uint32_t s2 = (c.s + STAGES - 2) & (STAGES - 1);
   const float* sp = c.ring + s2 * STAGE_FLOATS + c.row * TX + 4 * c.lane;
-  const float4 wl_u[5] = {wu[(R + 0) % 5], wu[(R + 1) % 5], wu[(R + 2) % 5], wu[(R + 3) % 5], wu[(R + 4) % 5]};
-  const float4 wl_v[5] = {wv[(R + 0) % 5], wv[(R + 1) % 5], wv[(R + 2) % 5], wv[(R + 3) % 5], wv[(R + 4) % 5]};
+  const float4 wl_u[5] = {wu[(R + (DOWN ? 4 : 0)) % 5], wu[(R + (DOWN ? 3 : 1)) % 5], wu[(R + 2) % 5],
+                          wu[(R + (DOWN ? 1 : 3)) % 5], wu[(R + (DOWN ? 0 : 4)) % 5]};
+  const float4 wl_v[5] = {wv[(R + (DOWN ? 4 : 0)) % 5], wv[(R + (DOWN ? 3 : 1)) % 5], wv[(R + 2) % 5],
+                          wv[(R + (DOWN ? 1 : 3)) % 5], wv[(R + (DOWN ? 0 : 4)) % 5]};
   const float4 cu = wl_u[2], cv = wl_v[2];
   float2 Lu_lo, Lu_hi, Lv_lo, Lv_hi;
   {
@@ -333,7 +344,7 @@ __device__ __forceinline__ void steady_plane(Consumer& c, bool drain, bool prefe
 
 // SLOT is a template parameter so that every coefficient is a compile-time constant-bank address
 // (c[3][imm] / hoisted LDCU) instead of an indexed LDC per use.
-template <int SLOT, bool FUSED>
+template <int SLOT>
 __global__ void __launch_bounds__(THREADS, 1)
 k_gs3d_fwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_halo,
                const __grid_constant__ Params p) {
@@ -366,12 +377,6 @@ k_gs3d_fwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
       uint32_t it = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const ItemCoord ic = decode_item(p, item);
-        if (FUSED && ic.seg < 2 && !(p.debug & 2)) {
-          // the ghost planes this item reads are written by a neighbour GPU: wait for its flag, then order
-          // the TMA (async proxy) reads after the acquire
-          wait_flag(p.my_flags + ic.seg, p.epoch_wait, p.scratch + 1);
-          asm volatile("fence.proxy.async.global;" ::: "memory");
-        }
         int yh[4] = {ic.y0 - 2, ic.y0 - 1, ic.y0 + p.ty, ic.y0 + p.ty + 1};   // periodic halo rows
 #pragma unroll
         for (int h = 0; h < 4; ++h) yh[h] = yh[h] < 0 ? yh[h] + p.H : (yh[h] >= p.H ? yh[h] - p.H : yh[h]);
@@ -417,38 +422,8 @@ k_gs3d_fwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
   const int64_t plane = int64_t(p.H) * p.W;
   float4 wu[5], wv[5];
   float2 seam_next[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-  bool posted = !FUSED;
-  // Tell the neighbours that every boundary plane of this step has landed in their ghost planes: the consumer
-  // warps of this CTA meet, one thread publishes (release, system scope); the last CTA raises the flags.
-  auto post_boundary_done = [&]() {
-    // Every storing warp fences at system scope itself: its peer (NVLink) stores must be performed before the
-    // flag can be observed.  Relying on one thread's fence after the CTA barrier to cover the other warps'
-    // in-flight peer stores produced stale ghost planes on a neighbour (caught by the 2-GPU bitwise test).
-    __threadfence_system();
-    asm volatile("bar.sync 1, %0;" ::"r"(p.ty * 32) : "memory");
-    if (warp == 0 && lane == 0) {
-      __threadfence_system();
-      const unsigned old = atomicAdd(p.scratch, 1u);
-      if (old == gridDim.x - 1) {
-        atomicExch(p.scratch, 0u);
-        __threadfence_system();
-        st_release_sys(p.post_lo_flag, p.epoch_post);
-        st_release_sys(p.post_hi_flag, p.epoch_post);
-      }
-    }
-  };
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
     const ItemCoord ic = decode_item(p, item);
-    if (FUSED && !posted && ic.seg == 2) {
-      if (!(p.debug & 4)) post_boundary_done();
-      posted = true;
-    }
-    float* mirror = nullptr;
-    if (FUSED && ic.seg < 2 && !(p.debug & 1)) {
-      float* base = ic.seg == 0 ? p.peer_lo_dst : p.peer_hi_dst;
-      const int mz = ic.seg == 0 ? p.D + 2 + ic.z0 : ic.z0 - (p.D - 2);
-      mirror = base + (int64_t(mz) * p.H + ic.y0) * p.W + ic.x0 + c.toff;
-    }
     // uniform per-item bases; the per-lane part (toff / seam_off) never changes
     const float* src_xy = p.src + int64_t(ic.y0) * p.W + ic.x0;
     float* out = p.dst + (int64_t(ic.z0 + p.dst_zoff) * p.H + ic.y0) * p.W + ic.x0 + c.toff;
@@ -474,10 +449,9 @@ k_gs3d_fwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
       pz -= p.D;                                                                                              \
       seam_ptr -= wrap_back;                                                                                  \
     }                                                                                                         \
-    steady_plane<RR, FUSED>(c, k >= ic.nz + 2, k <= ic.nz + 2, seam_ptr, p.src_field, out, mirror, p.dst_field, \
+    steady_plane<RR, false>(c, k >= ic.nz + 2, k <= ic.nz + 2, seam_ptr, p.src_field, out, nullptr, p.dst_field, \
                             wu, wv, seam_next);                                                               \
     out += plane;                                                                                             \
-    if (FUSED && mirror != nullptr) mirror += plane;                                                          \
     ++k;                                                                                                      \
   }
     int k = 4;
@@ -491,7 +465,6 @@ k_gs3d_fwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
     if (k < nk) PERCNN_STEADY(3)
 #undef PERCNN_STEADY
   }
-  if (FUSED && !posted && !(p.debug & 4)) post_boundary_done();
 }
 
 }  // namespace tma3d

@@ -8,91 +8,41 @@
 #include <string>
 
 #include "kernels_generic.cuh"
-#include "kernels_gs3d_tma.cuh"
-#include "kernels_gs3d_tma_bwd.cuh"
 #include "kernels_phys_loss.cuh"
-#include "kernels_pi_k5.cuh"
-#include "kernels_prep.cuh"
+#include "plan.h"
 
 using namespace percnn;
 
 namespace {
-
 thread_local std::string g_err;
+
+// The six __constant__ parameter slots exist once per device (constant memory belongs to the context).
+constexpr int kMaxDevices = 64;
+std::mutex g_slot_mutex;
+bool g_slot_used[kMaxDevices][kPrepSlots] = {};
+
+// Makes the plan's device current for the duration of an entry point and restores the caller's device.
+struct DeviceGuard {
+  int prev = -1;
+  bool changed = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) changed = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (changed) cudaSetDevice(prev);
+  }
+};
+}  // namespace
+
+namespace percnn {
 int fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
 }
-#define PERCNN_CUDA(call)                                                                                   \
-  do {                                                                                                      \
-    cudaError_t e__ = (call);                                                                               \
-    if (e__ != cudaSuccess)                                                                                 \
-      return fail(PERCNN_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));                    \
-  } while (0)
-
-std::mutex g_slot_mutex;
-bool g_slot_used[kPrepSlots] = {false};
-
-constexpr int kMaxBlocks = 2048;
-constexpr size_t kWsAcc = 0;            // kRedMaxSmall doubles
-constexpr size_t kWsCounter = 256;      // one unsigned
-constexpr size_t kWsPartials = 512;     // kMaxBlocks * kRedMaxSmall doubles
-constexpr size_t kWsStates = kWsPartials + size_t(kMaxBlocks) * kRedMaxSmall * sizeof(double);
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-struct TmaMapPair {
-  const void* base = nullptr;
-  CUtensorMap main_map, halo_map;
-};
-
-}  // namespace
-
-struct percnn_plan {
-  percnn_desc_t desc;
-  Geom g;
-  PrepDesc pd;
-  int slot = -1;
-  int elt = 4;
-  int nred = 0;
-  int sm_count = 148;
-  int64_t nparams = 0;
-  int64_t state_elems = 0;
-  int64_t launches = 0;
-  bool use_tma = false;
-  int ty = 16, tz = 0;
-  unsigned* d_sync = nullptr;   // grid-barrier counter of the persistent multi-step kernel
-  int multi_grid = 0;           // co-resident grid size of that kernel (0 = not available)
-  int multi_bwd_grid = 0;       // same for the persistent adjoint kernel
-  bool debug_split = false;   // PERCNN_TMA_SPLIT=1
-  bool bwd_split_mono = false;   // PERCNN_BWD_SPLIT_MONO=1: monomial sums in their own streaming kernel
-  bool bwd_mw = false;           // PERCNN_BWD_MW=1: warp-specialised adjoint (monomial warps + TMA ring for the stored
-                                 // state).  Measured 847 us vs 800 us per 512^3 step: the two monomial warps are the
-                                 // critical path (688 us without their work), see DESIGN.md 3.3 -- kept as an experiment.
-  bool pdl = true;   // programmatic dependent launch between consecutive step kernels (PERCNN_NO_PDL=1 disables)
-  int tz_override = 0, grid_override = 0;   // experiment knobs (PERCNN_TMA_TY / _TZ / _GRID environment variables)
-  PrepBlock* d_prep = nullptr;
-  float* d_k5w = nullptr;
-  EncodeTiledFn encode = nullptr;
-  TmaMapPair maps[4];
-  int map_rr = 0;
-  // host-path scratch
-  void* h_params_dev = nullptr;
-  void* h_states = nullptr;
-  size_t h_states_bytes = 0;
-  cudaStream_t h_stream = nullptr;
-};
+}  // namespace percnn
 
 namespace {
 
-size_t state_bytes(const percnn_plan* p) { return size_t(p->state_elems) * p->elt; }
-
-bool is_k5(const percnn_plan* p) { return p->desc.cell == PERCNN_CELL_PI && p->desc.ksize == 5; }
-int k5_blocks(const percnn_plan* p) {
-  return ((p->g.W + k5::BT_X - 1) / k5::BT_X) * ((p->g.H + k5::BT_Y - 1) / k5::BT_Y);
-}
 // workspace: [accumulators | counter | per-block partials | two state-sized scratch buffers]
 size_t ws_header_bytes(const percnn_plan* p) {   // bytes zeroed by param_grads_begin
   return is_k5(p) ? (size_t(p->nparams) * sizeof(double) + 255) / 256 * 256 : kWsPartials;
@@ -113,209 +63,6 @@ int generic_grid(const percnn_plan* p, int per_sm = 8) {
   if (blocks > cap) blocks = cap;
   if (blocks > kMaxBlocks) blocks = kMaxBlocks;
   return int(blocks < 1 ? 1 : blocks);
-}
-
-// Work decomposition of the persistent TMA kernel.  A tile is 128 x ty cells, an item is a tile marched over
-// tz planes (+4 halo planes).  Measured on B200 (profiles/r01_sweep_tma.txt): it pays to keep every CTA on the
-// same planes at the same time (one item per CTA, all items in one round) -- 128 CTAs in lock-step beat 148
-// CTAs on staggered z-chunks by 23 % -- so the cost model charges extra for multi-round schedules.
-struct TmaTiling {
-  int ty, tz, nyt, nzc;
-};
-double tiling_cost(int nxt, int H, int depth, int nsm, int ty, int nzc, TmaTiling* out) {
-  const int nyt = (H + ty - 1) / ty;
-  const int tz = (depth + nzc - 1) / nzc;
-  const int nz_chunks = (depth + tz - 1) / tz;
-  const long items = long(nxt) * nyt * nz_chunks;
-  const long rounds = (items + nsm - 1) / nsm;
-  double cost = double(rounds) * (tz + 4) * (8.0 + 2.0 * ty + 4.0);   // fixed per-plane latency + rows in + rows out
-  if (rounds > 1) cost *= 1.25;
-  if (out) *out = TmaTiling{ty, tz, nyt, nz_chunks};
-  return cost;
-}
-TmaTiling choose_tiling(int nxt, int H, int depth, int nsm, int fixed_ty, int max_ty = tma3d::BWD_WARPS) {
-  TmaTiling best{max_ty, depth, (H + max_ty - 1) / max_ty, 1};
-  double best_cost = 1e300;
-  for (int ty = (fixed_ty ? fixed_ty : 1); ty <= (fixed_ty ? fixed_ty : max_ty); ++ty) {
-    if (ty > H) break;
-    for (int nzc = 1; nzc <= depth; ++nzc) {
-      TmaTiling t;
-      const double c = tiling_cost(nxt, H, depth, nsm, ty, nzc, &t);
-      if (c < best_cost) {
-        best_cost = c;
-        best = t;
-      }
-      if ((depth + nzc - 1) / nzc <= 2) break;
-    }
-  }
-  return best;
-}
-
-int get_maps(percnn_plan* p, const void* src, const CUtensorMap** main_map, const CUtensorMap** halo_map) {
-  for (auto& m : p->maps)
-    if (m.base == src) {
-      *main_map = &m.main_map;
-      *halo_map = &m.halo_map;
-      return PERCNN_OK;
-    }
-  TmaMapPair& m = p->maps[p->map_rr];
-  p->map_rr = (p->map_rr + 1) % 4;
-  const Geom& g = p->g;
-  const cuuint64_t planes = cuuint64_t(g.D + 2 * g.ghost);
-  cuuint64_t gdim[4] = {cuuint64_t(g.W), cuuint64_t(g.H), planes, 2};
-  cuuint64_t gstr[3] = {cuuint64_t(g.W) * 4, cuuint64_t(g.plane) * 4, cuuint64_t(g.field) * 4};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  cuuint32_t box_main[4] = {tma3d::TX, cuuint32_t(p->ty), 1, 1};
-  cuuint32_t box_halo[4] = {tma3d::TX, 1, 1, 1};   // halo rows go one by one so any tile origin wraps correctly
-  CUresult r = p->encode(&m.main_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(src), gdim, gstr, box_main,
-                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r == CUDA_SUCCESS)
-    r = p->encode(&m.halo_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(src), gdim, gstr, box_halo, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    m.base = nullptr;
-    return fail(PERCNN_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)));
-  }
-  m.base = src;
-  *main_map = &m.main_map;
-  *halo_map = &m.halo_map;
-  return PERCNN_OK;
-}
-
-// Launch with programmatic stream serialization allowed (the kernels call griddepcontrol.wait themselves).
-template <typename... KArgs>
-cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, bool pdl, KArgs... args) {
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(block);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, args...);
-}
-
-struct SlabLink {   // mirrors percnn_slab_link_t
-  float* peer_lo_dst = nullptr;
-  float* peer_hi_dst = nullptr;
-  const uint32_t* my_flags = nullptr;
-  uint32_t* post_lo_flag = nullptr;
-  uint32_t* post_hi_flag = nullptr;
-  uint32_t* scratch = nullptr;
-  uint32_t epoch_wait = 0, epoch_post = 0;
-};
-
-int launch_tma_fwd(percnn_plan* p, const float* src, float* dst, int z_lo, int z_hi, cudaStream_t st,
-                   const SlabLink* link = nullptr, const tma3d::BwdExtra* bwd = nullptr) {
-  const CUtensorMap *mm, *hm;
-  int rc = get_maps(p, src, &mm, &hm);
-  if (rc) return rc;
-  CUtensorMap h_map;   // warp-specialised adjoint: the stored state streams through TMA as well (copied: the cache may recycle the slot)
-  memset(&h_map, 0, sizeof(h_map));
-  if (bwd && p->bwd_mw && !p->bwd_split_mono) {
-    const CUtensorMap main_copy = *mm, halo_copy = *hm;   // get_maps may evict these when it encodes the map for h
-    const CUtensorMap *h_main, *h_halo;
-    rc = get_maps(p, bwd->h, &h_main, &h_halo);
-    if (rc) return rc;
-    h_map = *h_main;
-    static thread_local CUtensorMap keep_main, keep_halo;
-    keep_main = main_copy;
-    keep_halo = halo_copy;
-    mm = &keep_main;
-    hm = &keep_halo;
-  }
-  const Geom& g = p->g;
-  tma3d::Params prm;
-  memset(&prm, 0, sizeof(prm));
-  prm.src = src;
-  prm.dst = dst;
-  prm.D = g.D;
-  prm.H = g.H;
-  prm.W = g.W;
-  prm.src_planes = g.D + 2 * g.ghost;
-  prm.src_field = g.field;
-  prm.dst_field = g.field;
-  prm.src_zoff = g.ghost ? 0 : -2;
-  prm.dst_zoff = g.ghost;
-  prm.wrap_z = g.ghost ? 0 : 1;
-  prm.nxt = g.W / tma3d::TX;
-  prm.ty = p->ty;
-  prm.nyt = (g.H + p->ty - 1) / p->ty;
-  auto add_segment = [&](int lo, int hi) {
-    const int depth = hi - lo;
-    TmaTiling til = (lo == 0 && hi == g.D) ? TmaTiling{p->ty, p->tz, prm.nyt, (g.D + p->tz - 1) / p->tz}
-                                           : choose_tiling(prm.nxt, g.H, depth, p->sm_count, p->ty);
-    if (p->tz_override > 0) {
-      til.tz = p->tz_override < depth ? p->tz_override : depth;
-      til.nzc = (depth + til.tz - 1) / til.tz;
-    }
-    const int s = prm.nseg++;
-    prm.seg_lo[s] = lo;
-    prm.seg_hi[s] = hi;
-    prm.seg_tz[s] = til.tz;
-    prm.seg_nzc[s] = til.nzc;
-  };
-  if (link) {
-    add_segment(0, 2);
-    add_segment(g.D - 2, g.D);
-    add_segment(2, g.D - 2);
-    prm.fused = 1;
-    prm.peer_lo_dst = link->peer_lo_dst;
-    prm.peer_hi_dst = link->peer_hi_dst;
-    prm.my_flags = link->my_flags;
-    prm.post_lo_flag = link->post_lo_flag;
-    prm.post_hi_flag = link->post_hi_flag;
-    prm.scratch = link->scratch;
-    prm.epoch_wait = link->epoch_wait;
-    prm.epoch_post = link->epoch_post;
-    if (const char* e = getenv("PERCNN_FUSED_DEBUG")) prm.debug = atoi(e);
-  } else if (getenv("PERCNN_KERNEL_DEBUG")) {
-    prm.debug = atoi(getenv("PERCNN_KERNEL_DEBUG"));
-    add_segment(z_lo, z_hi);
-  } else if (p->debug_split && z_lo == 0 && z_hi == g.D && g.D >= 5) {
-    add_segment(0, 2);            // debugging aid: the fused step's three-segment schedule without any flags
-    add_segment(g.D - 2, g.D);
-    add_segment(2, g.D - 2);
-  } else {
-    add_segment(z_lo, z_hi);
-  }
-  prm.slot = p->slot;
-  int nitems = 0;
-  for (int s = 0; s < prm.nseg; ++s) nitems += prm.nxt * prm.nyt * prm.seg_nzc[s];
-  int grid = nitems < p->sm_count ? nitems : p->sm_count;
-  if (p->grid_override > 0 && p->grid_override < grid) grid = p->grid_override;
-  cudaError_t le = cudaSuccess;
-  switch (p->slot) {
-#define PERCNN_TMA_CASE(S) \
-  case S:                                                                                                   \
-    if (bwd && p->bwd_mw && !p->bwd_split_mono) {                                                           \
-      if (prm.fused) le = launch_pdl(tma3d::k_gs3d_bwd_tma_mw<S, true>, grid, tma3d::MW_THREADS, tma3d::SMEM_BYTES_BWD_MW, st, p->pdl, *mm, *hm, h_map, prm, *bwd); \
-      else le = launch_pdl(tma3d::k_gs3d_bwd_tma_mw<S, false>, grid, tma3d::MW_THREADS, tma3d::SMEM_BYTES_BWD_MW, st, p->pdl, *mm, *hm, h_map, prm, *bwd); \
-    } else if (bwd) {                                                                                       \
-      if (p->bwd_split_mono) {                                                                              \
-        if (prm.fused) le = launch_pdl(tma3d::k_gs3d_bwd_tma<S, true, false>, grid, tma3d::BWD_THREADS, tma3d::SMEM_BYTES_BWD, st, p->pdl, *mm, *hm, prm, *bwd); \
-        else le = launch_pdl(tma3d::k_gs3d_bwd_tma<S, false, false>, grid, tma3d::BWD_THREADS, tma3d::SMEM_BYTES_BWD, st, p->pdl, *mm, *hm, prm, *bwd); \
-      } else {                                                                                              \
-        if (prm.fused) le = launch_pdl(tma3d::k_gs3d_bwd_tma<S, true, true>, grid, tma3d::BWD_THREADS, tma3d::SMEM_BYTES_BWD, st, p->pdl, *mm, *hm, prm, *bwd); \
-        else le = launch_pdl(tma3d::k_gs3d_bwd_tma<S, false, true>, grid, tma3d::BWD_THREADS, tma3d::SMEM_BYTES_BWD, st, p->pdl, *mm, *hm, prm, *bwd); \
-      }                                                                                                     \
-    } else if (prm.fused) le = launch_pdl(tma3d::k_gs3d_fwd_tma<S, true>, grid, tma3d::THREADS, tma3d::SMEM_BYTES, st, p->pdl, *mm, *hm, prm); \
-    else le = launch_pdl(tma3d::k_gs3d_fwd_tma<S, false>, grid, tma3d::THREADS, tma3d::SMEM_BYTES, st, p->pdl, *mm, *hm, prm); \
-    break;
-    PERCNN_TMA_CASE(0) PERCNN_TMA_CASE(1) PERCNN_TMA_CASE(2) PERCNN_TMA_CASE(3) PERCNN_TMA_CASE(4) PERCNN_TMA_CASE(5)
-#undef PERCNN_TMA_CASE
-    default: return fail(PERCNN_ERR_INVALID, "bad parameter slot");
-  }
-  if (le != cudaSuccess) return fail(PERCNN_ERR_CUDA, std::string("TMA kernel launch: ") + cudaGetErrorString(le));
-  PERCNN_CUDA(cudaGetLastError());
-  p->launches++;
-  return PERCNN_OK;
 }
 
 template <typename T>
@@ -355,8 +102,13 @@ const void* multi_step_kernel(const percnn_plan* p) {
   if (cell == PERCNN_CELL_BURGERS) return (const void*)k_multi_step<T, 2, 1>;
   return (const void*)k_multi_step<T, 2, 2>;
 }
+// The persistent one-block-per-SM kernels pay a grid barrier per step; that only wins while the ping-pong working
+// set stays in L2 and a per-step launch would be latency-bound.  Larger non-TMA plans (fp64 3-D, W % 128 != 0)
+// run one generic kernel per step.
+constexpr size_t kMultiStepMaxStateBytes = size_t(40) << 20;
 bool multi_step_eligible(const percnn_plan* p) {
   if (p->use_tma || is_k5(p) || p->desc.slab_ghost) return false;
+  if (state_bytes(p) > kMultiStepMaxStateBytes) return false;
   if (p->desc.cell == PERCNN_CELL_PI && (p->desc.flags & PERCNN_FLAG_EVAL_BRANCH)) return false;
   return p->multi_grid > 0 && p->d_sync != nullptr;
 }
@@ -382,34 +134,6 @@ int launch_multi_step(percnn_plan* p, const void* h0, void* tape, void* ping, vo
   PERCNN_CUDA(cudaLaunchCooperativeKernel(multi_step_kernel<T>(p), dim3(grid), dim3(kMultiThreads), args, 0, st));
   p->launches++;
   return PERCNN_OK;
-}
-
-// Type-erased description of the fused data-loss gradient of one state (see percnn_data_loss_t).
-struct InjectHost {
-  const void* target = nullptr;   // that state's low-res frame
-  const void* gscale = nullptr;
-  int stride = 1;
-  int64_t n_total = 0;
-};
-int lowres(int n, int s) { return (n + s - 1) / s; }
-int64_t lowres_field_elems(const percnn_plan* p, int s) {
-  const Geom& g = p->g;
-  return int64_t(g.ndim == 3 ? lowres(g.D, s) : 1) * lowres(g.H, s) * lowres(g.W, s);
-}
-template <typename T>
-Inject<T> make_inject(const percnn_plan* p, const InjectHost* ih) {
-  Inject<T> j;
-  memset(&j, 0, sizeof(j));
-  j.s = 1;
-  if (!ih || !ih->target) return j;
-  j.target = static_cast<const T*>(ih->target);
-  j.gscale = static_cast<const T*>(ih->gscale);
-  j.two_over_n = 2.0 / double(ih->n_total);
-  j.s = ih->stride;
-  j.lh = lowres(p->g.H, ih->stride);
-  j.lw = lowres(p->g.W, ih->stride);
-  j.lfield = lowres_field_elems(p, ih->stride);
-  return j;
 }
 
 template <typename T>
@@ -474,15 +198,8 @@ int launch_multi_bwd(percnn_plan* p, const void* tape, const void* g_tape, const
 }
 
 int step_fwd_any(percnn_plan* p, const void* src, void* dst, cudaStream_t st) {
-  if (p->use_tma) return launch_tma_fwd(p, static_cast<const float*>(src), static_cast<float*>(dst), 0, p->g.D, st);
-  if (p->desc.cell == PERCNN_CELL_PI && p->desc.ksize == 5) {
-    dim3 grid((p->g.W + k5::TILE_X - 1) / k5::TILE_X, (p->g.H + k5::TILE_Y - 1) / k5::TILE_Y);
-    k5::k_pi_k5_fwd<<<grid, k5::THREADS, k5::smem_bytes(p->desc.hidden), st>>>(
-        p->g, p->slot, p->desc.hidden, static_cast<const float*>(src), static_cast<float*>(dst), p->d_k5w);
-    PERCNN_CUDA(cudaGetLastError());
-    p->launches++;
-    return PERCNN_OK;
-  }
+  if (p->use_tma) return tma_fwd_launch(p, static_cast<const float*>(src), static_cast<float*>(dst), 0, p->g.D, st, nullptr);
+  if (is_k5(p)) return k5_step_fwd(p, static_cast<const float*>(src), static_cast<float*>(dst), st);
   return p->elt == 4 ? step_fwd_t<float>(p, static_cast<const float*>(src), static_cast<float*>(dst), st)
                      : step_fwd_t<double>(p, static_cast<const double*>(src), static_cast<double*>(dst), st);
 }
@@ -515,39 +232,16 @@ int step_bwd_t(percnn_plan* p, const T* h, const T* gout, const T* gadd, T* gin,
 
 int step_bwd_any(percnn_plan* p, const void* h, const void* gout, const void* gadd, void* gin, void* ws, cudaStream_t st,
                  const SlabLink* link = nullptr, const InjectHost* ih = nullptr) {
-  if (p->use_tma) {
-    char* w = static_cast<char*>(ws);
-    tma3d::BwdExtra x;
-    x.h = static_cast<const float*>(h);
-    x.gadd = static_cast<const float*>(gadd);
-    x.partials = reinterpret_cast<double*>(w + kWsPartials);
-    x.counter = reinterpret_cast<unsigned*>(w + kWsCounter);
-    x.acc = reinterpret_cast<double*>(w + kWsAcc);
-    x.inj = make_inject<float>(p, ih);
-    if (p->bwd_split_mono) {  // the 20 stencil-free monomial sums as a separate streaming pass over h and G
-      const Geom& g = p->g;
-      const int64_t n4 = int64_t(g.D) * g.plane / 4;
-      int64_t blocks = (n4 + 255) / 256;
-      if (blocks > int64_t(p->sm_count) * 8) blocks = int64_t(p->sm_count) * 8;
-      tma3d::k_monomial_sums<<<int(blocks), 256, 0, st>>>(
-          x.h, static_cast<const float*>(gout), g.field, int64_t(g.ghost) * g.plane, n4, float(p->desc.dt),
-          reinterpret_cast<double*>(w + kWsPartials + 8192), reinterpret_cast<unsigned*>(w + kWsCounter + 64), x.acc);
-      PERCNN_CUDA(cudaGetLastError());
-      p->launches++;
-    }
-    return launch_tma_fwd(p, static_cast<const float*>(gout), static_cast<float*>(gin), 0, p->g.D, st, link, &x);
-  }
+  if (p->use_tma)
+    return tma_bwd_launch(p, static_cast<const float*>(h), static_cast<const float*>(gout), static_cast<const float*>(gadd),
+                          static_cast<float*>(gin), static_cast<char*>(ws), st, link, ih);
   if (link) return fail(PERCNN_ERR_UNSUPPORTED, "fused halo adjoint needs a TMA plan");
   if (is_k5(p)) {
     char* w = static_cast<char*>(ws);
-    double* acc = reinterpret_cast<double*>(w);
-    float* partials = reinterpret_cast<float*>(w + ws_header_bytes(p));
-    dim3 grid((p->g.W + k5::BT_X - 1) / k5::BT_X, (p->g.H + k5::BT_Y - 1) / k5::BT_Y);
-    const int np = int(p->nparams);
-    k5::k_pi_k5_bwd<<<grid, k5::BTHREADS, k5::bwd_smem_floats(p->desc.hidden, np) * sizeof(float), st>>>(
-        p->g, p->slot, p->desc.hidden, np, static_cast<const float*>(h), static_cast<const float*>(gout),
-        static_cast<const float*>(gadd), static_cast<float*>(gin), p->d_k5w, partials);
-    PERCNN_CUDA(cudaGetLastError());
+    int rc = k5_step_bwd(p, static_cast<const float*>(h), static_cast<const float*>(gout), static_cast<const float*>(gadd),
+                         static_cast<float*>(gin), reinterpret_cast<double*>(w),
+                         reinterpret_cast<float*>(w + ws_header_bytes(p)), st);
+    if (rc) return rc;
     if (ih && ih->target) {
       // the 5x5 adjoint sits at its register limit; the (rare, 1/s^2-sized) loss injection runs as its own pass
       k_inject_only<float><<<generic_grid(p), kGenericThreads, 0, st>>>(p->g, static_cast<const float*>(h),
@@ -555,9 +249,6 @@ int step_bwd_any(percnn_plan* p, const void* h, const void* gout, const void* ga
       PERCNN_CUDA(cudaGetLastError());
       p->launches++;
     }
-    k5::k5_reduce_partials<<<(np + 255) / 256, 256, 0, st>>>(partials, int(grid.x * grid.y), np, acc);
-    PERCNN_CUDA(cudaGetLastError());
-    p->launches += 2;
     return PERCNN_OK;
   }
   return p->elt == 4 ? step_bwd_t<float>(p, static_cast<const float*>(h), static_cast<const float*>(gout),
@@ -566,6 +257,23 @@ int step_bwd_any(percnn_plan* p, const void* h, const void* gout, const void* ga
                      : step_bwd_t<double>(p, static_cast<const double*>(h), static_cast<const double*>(gout),
                                           static_cast<const double*>(gadd), static_cast<double*>(gin),
                                           static_cast<char*>(ws), st, ih);
+}
+
+// percnn_slab_link_t -> SlabLink (checks included)
+int resolve_link(const percnn_plan* p, const percnn_slab_link_t* link, SlabLink* l) {
+  if (!p->use_tma || !p->desc.slab_ghost) return fail(PERCNN_ERR_UNSUPPORTED, "fused halo steps need a slab-mode TMA plan");
+  if (p->g.D < 4) return fail(PERCNN_ERR_UNSUPPORTED, "fused halo steps need at least 4 planes per rank");
+  if (!link->peer_lo_out || !link->peer_hi_out || !link->my_flags || !link->peer_lo_flags || !link->peer_hi_flags || !link->scratch)
+    return fail(PERCNN_ERR_INVALID, "incomplete slab link");
+  l->peer_lo_dst = static_cast<float*>(link->peer_lo_out);
+  l->peer_hi_dst = static_cast<float*>(link->peer_hi_out);
+  l->my_flags = link->my_flags;
+  l->post_lo_flag = link->peer_lo_flags + 1;   // I provide the lower neighbour's UPPER ghosts
+  l->post_hi_flag = link->peer_hi_flags + 0;   // and the upper neighbour's LOWER ghosts
+  l->scratch = link->scratch;
+  l->epoch_wait = link->epoch;
+  l->epoch_post = link->epoch + 1;
+  return PERCNN_OK;
 }
 
 }  // namespace
@@ -655,26 +363,24 @@ int percnn_plan_create(const percnn_desc_t* d, percnn_plan_t** out) {
     p->nred = kRedLO;
   }
   int rc = PERCNN_OK;
+  DeviceGuard guard(d->device);   // the caller's current device is restored on return
   do {
-    if (cudaSetDevice(d->device) != cudaSuccess) { rc = fail(PERCNN_ERR_CUDA, "cudaSetDevice failed"); break; }
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, d->device) != cudaSuccess) { rc = fail(PERCNN_ERR_CUDA, "cudaGetDeviceProperties failed"); break; }
-    p->sm_count = prop.multiProcessorCount;
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != d->device) { rc = fail(PERCNN_ERR_CUDA, "cudaSetDevice failed"); break; }
+    if (d->device >= kMaxDevices) { rc = fail(PERCNN_ERR_INVALID, "device ordinal too large"); break; }
+    if (cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, d->device) != cudaSuccess) { rc = fail(PERCNN_ERR_CUDA, "cudaDeviceGetAttribute failed"); break; }
     {
       std::lock_guard<std::mutex> lk(g_slot_mutex);
       for (int s = 0; s < kPrepSlots; ++s)
-        if (!g_slot_used[s]) { g_slot_used[s] = true; p->slot = s; break; }
+        if (!g_slot_used[d->device][s]) { g_slot_used[d->device][s] = true; p->slot = s; break; }
     }
-    if (p->slot < 0) { rc = fail(PERCNN_ERR_INVALID, "too many live plans (6 parameter slots)"); break; }
+    if (p->slot < 0) { rc = fail(PERCNN_ERR_INVALID, "too many live plans on this device (6 parameter slots)"); break; }
     if (cudaMalloc(&p->d_prep, sizeof(PrepBlock)) != cudaSuccess) { rc = fail(PERCNN_ERR_CUDA, "cudaMalloc(prep) failed"); break; }
-    if (d->cell == PERCNN_CELL_PI && d->ksize == 5) {
-      if (cudaMalloc(&p->d_k5w, size_t(k5_total_floats(d->hidden)) * 4) != cudaSuccess) { rc = fail(PERCNN_ERR_CUDA, "cudaMalloc(k5w) failed"); break; }
-      if (cudaFuncSetAttribute(k5::k_pi_k5_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               int(k5::smem_bytes(d->hidden))) != cudaSuccess) { rc = fail(PERCNN_ERR_CUDA, "cudaFuncSetAttribute(k5) failed"); break; }
-      if (cudaFuncSetAttribute(k5::k_pi_k5_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               int(k5::bwd_smem_floats(d->hidden, int(p->nparams)) * sizeof(float))) != cudaSuccess) { rc = fail(PERCNN_ERR_CUDA, "cudaFuncSetAttribute(k5 bwd) failed"); break; }
+    if (is_k5(p)) {
+      rc = k5_setup(p);
+      if (rc) break;
     }
-    if (!(d->cell == PERCNN_CELL_PI && d->ksize == 5) && !d->slab_ghost && !getenv("PERCNN_NO_MULTISTEP")) {
+    if (!is_k5(p) && !d->slab_ghost && !getenv("PERCNN_NO_MULTISTEP")) {
       int coop = 0, per_sm = 0;
       cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, d->device);
       const void* fn = p->elt == 4 ? multi_step_kernel<float>(p) : multi_step_kernel<double>(p);
@@ -688,53 +394,12 @@ int percnn_plan_create(const percnn_desc_t* d, percnn_plan_t** out) {
         p->multi_bwd_grid = p->sm_count;
     }
     p->use_tma = d->cell == PERCNN_CELL_PI && d->ksize == 1 && d->ndim == 3 && d->dtype == PERCNN_F32 &&
-                 !(d->flags & (PERCNN_FLAG_NO_TMA | PERCNN_FLAG_EVAL_BRANCH)) && g.W % tma3d::TX == 0 &&
+                 !(d->flags & (PERCNN_FLAG_NO_TMA | PERCNN_FLAG_EVAL_BRANCH)) && g.W % 128 == 0 &&
                  g.H >= 4 && g.D >= 4;
     if (p->use_tma) {
-      void* fn = nullptr;
-      cudaDriverEntryPointQueryResult qres;
-      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
-        rc = fail(PERCNN_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
-        break;
-      }
-      p->encode = reinterpret_cast<EncodeTiledFn>(fn);
-      cudaError_t ae = cudaSuccess;
-      switch (p->slot) {
-#define PERCNN_TMA_ATTR(S) \
-  case S:                                                                                                              \
-    ae = cudaFuncSetAttribute(tma3d::k_gs3d_fwd_tma<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma3d::SMEM_BYTES); \
-    if (ae == cudaSuccess)                                                                                               \
-      ae = cudaFuncSetAttribute(tma3d::k_gs3d_fwd_tma<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma3d::SMEM_BYTES); \
-    if (ae == cudaSuccess)                                                                                               \
-      ae = cudaFuncSetAttribute(tma3d::k_gs3d_bwd_tma<S, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma3d::SMEM_BYTES_BWD); \
-    if (ae == cudaSuccess)                                                                                               \
-      ae = cudaFuncSetAttribute(tma3d::k_gs3d_bwd_tma<S, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma3d::SMEM_BYTES_BWD); \
-    if (ae == cudaSuccess)                                                                                               \
-      ae = cudaFuncSetAttribute(tma3d::k_gs3d_bwd_tma<S, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma3d::SMEM_BYTES_BWD); \
-    if (ae == cudaSuccess)                                                                                               \
-      ae = cudaFuncSetAttribute(tma3d::k_gs3d_bwd_tma<S, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma3d::SMEM_BYTES_BWD); \
-    if (ae == cudaSuccess)                                                                                               \
-      ae = cudaFuncSetAttribute(tma3d::k_gs3d_bwd_tma_mw<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma3d::SMEM_BYTES_BWD_MW); \
-    if (ae == cudaSuccess)                                                                                               \
-      ae = cudaFuncSetAttribute(tma3d::k_gs3d_bwd_tma_mw<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma3d::SMEM_BYTES_BWD_MW); \
-    break;
-        PERCNN_TMA_ATTR(0) PERCNN_TMA_ATTR(1) PERCNN_TMA_ATTR(2) PERCNN_TMA_ATTR(3) PERCNN_TMA_ATTR(4) PERCNN_TMA_ATTR(5)
-#undef PERCNN_TMA_ATTR
-      }
-      if (ae != cudaSuccess) { rc = fail(PERCNN_ERR_CUDA, "cudaFuncSetAttribute(tma) failed"); break; }
-      int fixed_ty = 0;
-      if (const char* e = getenv("PERCNN_TMA_TY")) fixed_ty = atoi(e);
-      if (const char* e = getenv("PERCNN_BWD_MW")) p->bwd_mw = atoi(e) != 0;
-      const int max_ty = p->bwd_mw ? tma3d::MW_STENCIL : tma3d::BWD_WARPS;   // the tiling is shared by fwd and adjoint kernels
-      if (fixed_ty < 0 || fixed_ty > max_ty || fixed_ty > g.H) fixed_ty = 0;
-      const TmaTiling til = choose_tiling(g.W / tma3d::TX, g.H, g.D, p->sm_count, fixed_ty, max_ty);
-      p->ty = til.ty;
-      p->tz = til.tz;
-      if (const char* e = getenv("PERCNN_NO_PDL")) p->pdl = atoi(e) == 0;
-      if (const char* e = getenv("PERCNN_TMA_SPLIT")) p->debug_split = atoi(e) != 0;
-      if (const char* e = getenv("PERCNN_BWD_SPLIT_MONO")) p->bwd_split_mono = atoi(e) != 0;
-      if (const char* e = getenv("PERCNN_TMA_TZ")) p->tz_override = atoi(e);
-      if (const char* e = getenv("PERCNN_TMA_GRID")) p->grid_override = atoi(e);
+      rc = tma_fwd_setup(p);
+      if (!rc) rc = tma_bwd_setup(p);
+      if (rc) break;
     }
   } while (0);
   if (rc != PERCNN_OK) {
@@ -749,15 +414,16 @@ int percnn_plan_create(const percnn_desc_t* d, percnn_plan_t** out) {
 
 int percnn_plan_destroy(percnn_plan_t* p) {
   if (!p) return PERCNN_OK;
+  DeviceGuard guard(p->desc.device);
   if (p->d_prep) cudaFree(p->d_prep);
   if (p->d_k5w) cudaFree(p->d_k5w);
   if (p->d_sync) cudaFree(p->d_sync);
   if (p->h_params_dev) cudaFree(p->h_params_dev);
   if (p->h_states) cudaFree(p->h_states);
   if (p->h_stream) cudaStreamDestroy(p->h_stream);
-  if (p->slot >= 0) {
+  if (p->slot >= 0 && p->desc.device >= 0 && p->desc.device < kMaxDevices) {
     std::lock_guard<std::mutex> lk(g_slot_mutex);
-    g_slot_used[p->slot] = false;
+    g_slot_used[p->desc.device][p->slot] = false;
   }
   delete p;
   return PERCNN_OK;
@@ -776,14 +442,21 @@ size_t percnn_workspace_bytes(const percnn_plan_t* p, int nsteps) {
 
 int percnn_params_load(percnn_plan_t* p, const void* params, void* stream) {
   if (!p || !params) return fail(PERCNN_ERR_INVALID, "null plan or params");
+  DeviceGuard guard(p->desc.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (p->elt == 4)
     k_prep<float><<<1, 256, 0, st>>>(static_cast<const float*>(params), p->pd, p->d_prep, p->d_k5w);
   else
     k_prep<double><<<1, 256, 0, st>>>(static_cast<const double*>(params), p->pd, p->d_prep, p->d_k5w);
   PERCNN_CUDA(cudaGetLastError());
+  // every translation unit keeps its own copy of the constant block; fill the ones this plan's kernels read
   PERCNN_CUDA(cudaMemcpyToSymbolAsync(c_prep, p->d_prep, sizeof(PrepBlock), size_t(p->slot) * sizeof(PrepBlock),
                                       cudaMemcpyDeviceToDevice, st));
+  if (p->use_tma) {
+    PERCNN_CUDA(tma_fwd_load_prep(p->d_prep, p->slot, st));
+    PERCNN_CUDA(tma_bwd_load_prep(p->d_prep, p->slot, st));
+  }
+  if (is_k5(p)) PERCNN_CUDA(k5_load_prep(p->d_prep, p->slot, st));
   p->launches++;
   return PERCNN_OK;
 }
@@ -791,6 +464,7 @@ int percnn_params_load(percnn_plan_t* p, const void* params, void* stream) {
 int percnn_step_fwd(percnn_plan_t* p, const void* h_in, void* h_out, void* stream) {
   if (!p || !h_in || !h_out) return fail(PERCNN_ERR_INVALID, "null argument");
   if (h_in == h_out) return fail(PERCNN_ERR_INVALID, "step_fwd cannot run in place");
+  DeviceGuard guard(p->desc.device);
   return step_fwd_any(p, h_in, h_out, static_cast<cudaStream_t>(stream));
 }
 
@@ -801,29 +475,76 @@ int percnn_step_fwd_range(percnn_plan_t* p, const void* h_in, void* h_out, int z
   if (!p || !h_in || !h_out) return fail(PERCNN_ERR_INVALID, "null argument");
   if (!p->use_tma) return fail(PERCNN_ERR_UNSUPPORTED, "step_fwd_range needs a TMA plan");
   if (z_lo < 0 || z_hi > p->g.D || z_lo >= z_hi) return fail(PERCNN_ERR_INVALID, "bad plane range");
-  return launch_tma_fwd(p, static_cast<const float*>(h_in), static_cast<float*>(h_out), z_lo, z_hi,
-                        static_cast<cudaStream_t>(stream));
+  DeviceGuard guard(p->desc.device);
+  return tma_fwd_launch(p, static_cast<const float*>(h_in), static_cast<float*>(h_out), z_lo, z_hi,
+                        static_cast<cudaStream_t>(stream), nullptr);
 }
 
-// One fused slab step: boundary planes first (each also stored into the neighbour's ghost planes through the
-// peer mapping), flags raised from inside the kernel, interior last.  See percnn_slab_link_t.
+// One fused slab step: a single z-march (direction = parity of the epoch) whose boundary planes are also stored
+// into the neighbours' ghost planes through the peer mapping; flags raised from inside the kernel.
 int percnn_step_fwd_fused_halo(percnn_plan_t* p, const void* h_in, void* h_out, const percnn_slab_link_t* link, void* stream) {
   if (!p || !h_in || !h_out || !link) return fail(PERCNN_ERR_INVALID, "null argument");
-  if (!p->use_tma || !p->desc.slab_ghost) return fail(PERCNN_ERR_UNSUPPORTED, "fused halo steps need a slab-mode TMA plan");
-  if (p->g.D < 5) return fail(PERCNN_ERR_UNSUPPORTED, "fused halo steps need at least 5 planes per rank");
-  if (!link->peer_lo_out || !link->peer_hi_out || !link->my_flags || !link->peer_lo_flags || !link->peer_hi_flags || !link->scratch)
-    return fail(PERCNN_ERR_INVALID, "incomplete slab link");
   SlabLink l;
-  l.peer_lo_dst = static_cast<float*>(link->peer_lo_out);
-  l.peer_hi_dst = static_cast<float*>(link->peer_hi_out);
-  l.my_flags = link->my_flags;
-  l.post_lo_flag = link->peer_lo_flags + 1;   // I provide the lower neighbour's UPPER ghosts
-  l.post_hi_flag = link->peer_hi_flags + 0;   // and the upper neighbour's LOWER ghosts
-  l.scratch = link->scratch;
-  l.epoch_wait = link->epoch;
-  l.epoch_post = link->epoch + 1;
-  return launch_tma_fwd(p, static_cast<const float*>(h_in), static_cast<float*>(h_out), 0, p->g.D,
+  int rc = resolve_link(p, link, &l);
+  if (rc) return rc;
+  DeviceGuard guard(p->desc.device);
+  return tma_fwd_launch(p, static_cast<const float*>(h_in), static_cast<float*>(h_out), 0, p->g.D,
                         static_cast<cudaStream_t>(stream), &l);
+}
+
+// Whole slab-mode forward rollout: `nsteps` fused steps issued from one host call.  Step s reads
+// buf[cur ^ (s & 1)] and writes the other buffer (locally and, for the boundary planes, at both peers).
+int percnn_slab_rollout_fwd(percnn_plan_t* p, const percnn_slab_ring_t* ring, int cur, int nsteps, uint32_t epoch,
+                            void* stream) {
+  if (!p || !ring) return fail(PERCNN_ERR_INVALID, "null argument");
+  if (nsteps < 0 || (cur != 0 && cur != 1)) return fail(PERCNN_ERR_INVALID, "bad nsteps / cur");
+  DeviceGuard guard(p->desc.device);
+  for (int s = 0; s < nsteps; ++s) {
+    const int src = cur ^ (s & 1), dst = src ^ 1;
+    percnn_slab_link_t link;
+    link.peer_lo_out = ring->peer_lo_buf[dst];
+    link.peer_hi_out = ring->peer_hi_buf[dst];
+    link.my_flags = ring->my_flags;
+    link.peer_lo_flags = ring->peer_lo_flags;
+    link.peer_hi_flags = ring->peer_hi_flags;
+    link.scratch = ring->scratch;
+    link.epoch = epoch + uint32_t(s);
+    SlabLink l;
+    int rc = resolve_link(p, &link, &l);
+    if (rc) return rc;
+    if (!ring->buf[0] || !ring->buf[1]) return fail(PERCNN_ERR_INVALID, "incomplete slab ring");
+    rc = tma_fwd_launch(p, static_cast<const float*>(ring->buf[src]), static_cast<float*>(ring->buf[dst]), 0, p->g.D,
+                        static_cast<cudaStream_t>(stream), &l);
+    if (rc) return rc;
+  }
+  return PERCNN_OK;
+}
+
+// Taped slab rollout: step t reads tape slot t and writes slot t+1 (and the boundary planes of the peers' slot t+1).
+int percnn_slab_rollout_tape(percnn_plan_t* p, void* tape, void* peer_lo_tape, void* peer_hi_tape,
+                             const percnn_slab_ring_t* ring, int nsteps, uint32_t epoch, void* stream) {
+  if (!p || !tape || !peer_lo_tape || !peer_hi_tape || !ring) return fail(PERCNN_ERR_INVALID, "null argument");
+  if (nsteps < 0) return fail(PERCNN_ERR_INVALID, "nsteps must be >= 0");
+  DeviceGuard guard(p->desc.device);
+  const size_t sb = state_bytes(p);
+  for (int t = 0; t < nsteps; ++t) {
+    percnn_slab_link_t link;
+    link.peer_lo_out = static_cast<char*>(peer_lo_tape) + size_t(t + 1) * sb;
+    link.peer_hi_out = static_cast<char*>(peer_hi_tape) + size_t(t + 1) * sb;
+    link.my_flags = ring->my_flags;
+    link.peer_lo_flags = ring->peer_lo_flags;
+    link.peer_hi_flags = ring->peer_hi_flags;
+    link.scratch = ring->scratch;
+    link.epoch = epoch + uint32_t(t);
+    SlabLink l;
+    int rc = resolve_link(p, &link, &l);
+    if (rc) return rc;
+    rc = tma_fwd_launch(p, reinterpret_cast<const float*>(static_cast<char*>(tape) + size_t(t) * sb),
+                        reinterpret_cast<float*>(static_cast<char*>(tape) + size_t(t + 1) * sb), 0, p->g.D,
+                        static_cast<cudaStream_t>(stream), &l);
+    if (rc) return rc;
+  }
+  return PERCNN_OK;
 }
 
 // Adjoint counterpart of percnn_step_fwd_fused_halo: the gradient's boundary planes are mirrored into the
@@ -849,21 +570,61 @@ int percnn_step_bwd_loss(percnn_plan_t* p, const void* h_in, const void* g_out, 
     ih.stride = stride;
     ih.n_total = n_total;
   }
+  DeviceGuard guard(p->desc.device);
   if (!link) return step_bwd_any(p, h_in, g_out, g_add, g_in, ws, static_cast<cudaStream_t>(stream), nullptr, &ih);
-  if (!p->use_tma || !p->desc.slab_ghost) return fail(PERCNN_ERR_UNSUPPORTED, "fused halo steps need a slab-mode TMA plan");
-  if (p->g.D < 5) return fail(PERCNN_ERR_UNSUPPORTED, "fused halo steps need at least 5 planes per rank");
-  if (!link->peer_lo_out || !link->peer_hi_out || !link->my_flags || !link->peer_lo_flags || !link->peer_hi_flags || !link->scratch)
-    return fail(PERCNN_ERR_INVALID, "incomplete slab link");
   SlabLink l;
-  l.peer_lo_dst = static_cast<float*>(link->peer_lo_out);
-  l.peer_hi_dst = static_cast<float*>(link->peer_hi_out);
-  l.my_flags = link->my_flags;
-  l.post_lo_flag = link->peer_lo_flags + 1;
-  l.post_hi_flag = link->peer_hi_flags + 0;
-  l.scratch = link->scratch;
-  l.epoch_wait = link->epoch;
-  l.epoch_post = link->epoch + 1;
+  int rc = resolve_link(p, link, &l);
+  if (rc) return rc;
   return step_bwd_any(p, h_in, g_out, g_add, g_in, ws, static_cast<cudaStream_t>(stream), &l, &ih);
+}
+
+// Whole slab-mode backward rollout.  ring->buf[0] must hold G_nsteps (ghosts exchanged); step t = nsteps-1 .. 0 reads
+// the gradient from buf[b], the stored state from tape slot t and writes buf[b ^ 1]; dL/dh_0 ends in
+// buf[nsteps & 1].  `g_tape` (nullable): dense dL/d(tape[t]) in the ghosted layout, slot t added at step t.
+// `loss` (nullable): fused data loss, target frames of the selected states packed in increasing step order.
+// The caller zeroes the accumulator before (percnn_param_grads_begin) and all-reduces / finishes after.
+int percnn_slab_rollout_bwd(percnn_plan_t* p, const void* tape, const void* g_tape, const percnn_data_loss_t* loss,
+                            const percnn_slab_ring_t* ring, int nsteps, uint32_t epoch, void* ws, void* stream) {
+  if (!p || !tape || !ring || !ws) return fail(PERCNN_ERR_INVALID, "null argument");
+  if (nsteps < 1) return fail(PERCNN_ERR_INVALID, "nsteps must be >= 1");
+  if (!ring->buf[0] || !ring->buf[1]) return fail(PERCNN_ERR_INVALID, "incomplete slab ring");
+  if (loss && (!loss->target || !loss->sel || loss->stride < 1 || loss->n_total < 1))
+    return fail(PERCNN_ERR_INVALID, "slab data loss needs target, sel, stride >= 1 and the GLOBAL n_total");
+  DeviceGuard guard(p->desc.device);
+  const size_t sb = state_bytes(p);
+  const size_t frame_bytes = loss ? size_t(2 * lowres_field_elems(p, loss->stride)) * p->elt : 0;
+  int slot = 0;
+  if (loss)
+    for (int t = 0; t < nsteps; ++t) slot += loss->sel[t] ? 1 : 0;
+  int b = 0;
+  for (int t = nsteps - 1; t >= 0; --t) {
+    const int nxt = b ^ 1;
+    percnn_slab_link_t link;
+    link.peer_lo_out = ring->peer_lo_buf[nxt];
+    link.peer_hi_out = ring->peer_hi_buf[nxt];
+    link.my_flags = ring->my_flags;
+    link.peer_lo_flags = ring->peer_lo_flags;
+    link.peer_hi_flags = ring->peer_hi_flags;
+    link.scratch = ring->scratch;
+    link.epoch = epoch + uint32_t(nsteps - 1 - t);
+    SlabLink l;
+    int rc = resolve_link(p, &link, &l);
+    if (rc) return rc;
+    InjectHost ih;
+    if (loss && loss->sel[t]) {
+      --slot;
+      ih.target = static_cast<const char*>(loss->target) + size_t(slot) * frame_bytes;
+      ih.gscale = loss->gscale;
+      ih.stride = loss->stride;
+      ih.n_total = loss->n_total;
+    }
+    const char* add = g_tape ? static_cast<const char*>(g_tape) + size_t(t) * sb : nullptr;
+    rc = step_bwd_any(p, static_cast<const char*>(tape) + size_t(t) * sb, ring->buf[b], add, ring->buf[nxt], ws,
+                      static_cast<cudaStream_t>(stream), &l, &ih);
+    if (rc) return rc;
+    b = nxt;
+  }
+  return PERCNN_OK;
 }
 
 namespace {
@@ -890,6 +651,7 @@ int percnn_data_loss_fwd(percnn_plan_t* p, const void* tape, int nsteps, const p
   int64_t n = 0;
   int rc = check_data_loss(p, dl, nsteps, &nsel, &n);
   if (rc) return rc;
+  DeviceGuard guard(p->desc.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   char* w = static_cast<char*>(ws);
   double* acc = reinterpret_cast<double*>(w + kWsAcc);
@@ -929,6 +691,7 @@ int percnn_data_loss_fwd(percnn_plan_t* p, const void* tape, int nsteps, const p
 
 int percnn_param_grads_begin(percnn_plan_t* p, void* ws, void* stream) {
   if (!p || !ws) return fail(PERCNN_ERR_INVALID, "null argument");
+  DeviceGuard guard(p->desc.device);
   PERCNN_CUDA(cudaMemsetAsync(ws, 0, ws_header_bytes(p), static_cast<cudaStream_t>(stream)));
   return PERCNN_OK;
 }
@@ -937,21 +700,16 @@ int percnn_step_bwd(percnn_plan_t* p, const void* h_in, const void* g_out, const
                     void* stream) {
   if (!p || !h_in || !g_out || !g_in || !ws) return fail(PERCNN_ERR_INVALID, "null argument");
   if (g_out == g_in) return fail(PERCNN_ERR_INVALID, "step_bwd cannot run in place");
+  DeviceGuard guard(p->desc.device);
   return step_bwd_any(p, h_in, g_out, g_add, g_in, ws, static_cast<cudaStream_t>(stream));
 }
 
 int percnn_param_grads_finish(percnn_plan_t* p, const void* params, void* param_grads, void* ws, void* stream) {
   if (!p || !params || !param_grads || !ws) return fail(PERCNN_ERR_INVALID, "null argument");
+  DeviceGuard guard(p->desc.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const double* acc = reinterpret_cast<const double*>(static_cast<char*>(ws) + kWsAcc);
-  if (is_k5(p)) {
-    const int np = int(p->nparams);
-    k5::k5_finish<<<(np + 255) / 256, 256, 0, st>>>(static_cast<const float*>(params), acc, p->pd, np,
-                                                     static_cast<float*>(param_grads));
-    PERCNN_CUDA(cudaGetLastError());
-    p->launches++;
-    return PERCNN_OK;
-  }
+  if (is_k5(p)) return k5_grads_finish(p, static_cast<const float*>(params), acc, static_cast<float*>(param_grads), st);
   if (p->elt == 4)
     k_finish_small<float><<<1, 256, 0, st>>>(static_cast<const float*>(params), acc, p->pd, int(p->nparams),
                                              static_cast<float*>(param_grads));
@@ -969,7 +727,8 @@ int percnn_rollout_fwd(percnn_plan_t* p, const void* h0, void* traj, const uint8
   if (nsteps < 0) return fail(PERCNN_ERR_INVALID, "nsteps must be >= 0");
   if (traj && !emit) return fail(PERCNN_ERR_INVALID, "traj given without an emit mask");
   if (!tape && !ws) return fail(PERCNN_ERR_INVALID, "rollout_fwd needs a workspace unless a tape is given");
-  if (p->desc.slab_ghost) return fail(PERCNN_ERR_UNSUPPORTED, "slab-mode rollouts are driven step by step (halo exchange between steps)");
+  if (p->desc.slab_ghost) return fail(PERCNN_ERR_UNSUPPORTED, "slab-mode rollouts go through percnn_slab_rollout_fwd (halo exchange between steps)");
+  DeviceGuard guard(p->desc.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t sb = state_bytes(p);
   char* tp = static_cast<char*>(tape);
@@ -981,8 +740,12 @@ int percnn_rollout_fwd(percnn_plan_t* p, const void* h0, void* traj, const uint8
   if (tp && tp != h0) PERCNN_CUDA(cudaMemcpyAsync(tp, h0, sb, cudaMemcpyDeviceToDevice, st));
   // small grids: one persistent cooperative launch for the whole rollout (tape mode, or final-state-only mode)
   if (nsteps >= 2 && multi_step_eligible(p) && !traj && (tp || (h_final && pp[0]))) {
-    return p->elt == 4 ? launch_multi_step<float>(p, h0, tp, pp[0], pp[1], h_final, nsteps, st)
-                       : launch_multi_step<double>(p, h0, tp, pp[0], pp[1], h_final, nsteps, st);
+    int rc = p->elt == 4 ? launch_multi_step<float>(p, h0, tp, pp[0], pp[1], h_final, nsteps, st)
+                         : launch_multi_step<double>(p, h0, tp, pp[0], pp[1], h_final, nsteps, st);
+    if (rc) return rc;
+    // tape mode never touches h_final inside the kernel: hand the last slot over, as the per-step path does
+    if (tp && h_final) PERCNN_CUDA(cudaMemcpyAsync(h_final, tp + size_t(nsteps) * sb, sb, cudaMemcpyDeviceToDevice, st));
+    return PERCNN_OK;
   }
   const char* cur = tp ? tp : static_cast<const char*>(h0);
   int slot = 0, flip = 0;
@@ -1028,6 +791,7 @@ int percnn_rollout_bwd_loss(percnn_plan_t* p, const void* params, const void* ta
     int rcl = check_data_loss(p, dl, nsteps, &dl_nsel, &dl_n);
     if (rcl) return rcl;
   }
+  DeviceGuard guard(p->desc.device);
   const size_t dl_frame_bytes = dl ? size_t(2 * lowres_field_elems(p, dl->stride)) * p->elt : 0;
   int dl_slot = dl_nsel;   // walks the packed target frames backwards, like `slot` does for g_tape
   auto inject_for = [&](int s, InjectHost* ih) {
@@ -1167,6 +931,7 @@ int percnn_phys_loss_fwd(const percnn_phys_loss_t* pl, const void* frames, void*
   int rc = phys_check(pl, &g);
   if (rc) return rc;
   if (!frames || !loss_out || !ws) return fail(PERCNN_ERR_INVALID, "null argument");
+  DeviceGuard guard(pl->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   char* w = static_cast<char*>(ws);
   double* acc = reinterpret_cast<double*>(w + kWsAcc);
@@ -1201,6 +966,7 @@ int percnn_phys_loss_bwd(const percnn_phys_loss_t* pl, const void* frames, const
   int rc = phys_check(pl, &g);
   if (rc) return rc;
   if (!frames || !resid || !g_frames) return fail(PERCNN_ERR_INVALID, "null argument");
+  DeviceGuard guard(pl->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = phys_grid(g, pl->nframes);
   if (pl->dtype == PERCNN_F32) {
@@ -1224,7 +990,7 @@ int percnn_rollout_fwd_host(percnn_plan_t* p, const void* params_host, const voi
                             const uint8_t* emit, int nsteps, void* h_final_host) {
   if (!p || !params_host || !h0_host) return fail(PERCNN_ERR_INVALID, "null argument");
   if (traj_host && !emit) return fail(PERCNN_ERR_INVALID, "traj given without an emit mask");
-  PERCNN_CUDA(cudaSetDevice(p->desc.device));
+  DeviceGuard guard(p->desc.device);
   const size_t sb = (state_bytes(p) + 255) / 256 * 256;
   int nemit = 0;
   if (traj_host)

@@ -155,6 +155,28 @@ class Plan:
         check(self._L.percnn_step_bwd_fused_halo(self._h, h_in.data_ptr(), g_out.data_ptr(), _ptr(g_add), g_in.data_ptr(),
                                                  self.workspace().data_ptr(), ctypes.byref(link), _stream_ptr(self.device)))
 
+    # -- whole slab rollouts (one C call each; see percnn_b200.halo) ---------------------------------
+    def slab_rollout_fwd(self, ring, cur: int, nsteps: int, epoch: int) -> None:
+        check(self._L.percnn_slab_rollout_fwd(self._h, ctypes.byref(ring), int(cur), int(nsteps), int(epoch) & 0xFFFFFFFF,
+                                              _stream_ptr(self.device)))
+
+    def slab_rollout_tape(self, tape, peer_lo_tape, peer_hi_tape, ring, nsteps: int, epoch: int) -> None:
+        self._check_state(tape, "tape", nsteps + 1)
+        check(self._L.percnn_slab_rollout_tape(self._h, tape.data_ptr(), peer_lo_tape.data_ptr(), peer_hi_tape.data_ptr(),
+                                               ctypes.byref(ring), int(nsteps), int(epoch) & 0xFFFFFFFF,
+                                               _stream_ptr(self.device)))
+
+    def slab_rollout_bwd(self, tape, g_tape, spec, target, gscale, ring, nsteps: int, epoch: int) -> None:
+        """Fused-halo adjoint over the whole tape; the parameter sums accumulate in the workspace header."""
+        self._check_state(tape, "tape", nsteps + 1)
+        dl_ref, keep = None, None
+        if spec is not None:
+            dl, keep = self._data_loss_struct(spec, nsteps, target, gscale)
+            dl_ref = ctypes.byref(dl)
+        check(self._L.percnn_slab_rollout_bwd(self._h, tape.data_ptr(), _ptr(g_tape), dl_ref, ctypes.byref(ring), int(nsteps),
+                                              int(epoch) & 0xFFFFFFFF, self.workspace().data_ptr(), _stream_ptr(self.device)))
+        del keep
+
     def reduction_sums(self, n: int = 24) -> torch.Tensor:
         """fp64 view of the running parameter-gradient sums at the head of the workspace (for the all-reduce)."""
         return self.workspace()[:8 * n].view(torch.float64)

@@ -15,10 +15,12 @@ behind the interior kernel.  Transport:
   * "symm": peer-mapped buffers (torch.distributed._symmetric_memory): the boundary planes are copied
     straight into the neighbour's ghost planes over NVLink and a stream-ordered signal replaces the
     rendezvous -- no NCCL kernel, no host round trip;
-  * "fused" (default when peer mapping works): ONE kernel per step does the compute and the exchange -- it
-    computes the boundary planes first, stores them locally AND into the neighbour's ghost planes through the
-    peer mapping, raises the neighbour's flag from inside the kernel and then computes the interior; the next
-    step's kernel waits on its own flags before touching its ghost planes (percnn_step_fwd_fused_halo).
+  * "fused" (default when peer mapping works): ONE kernel per step does the compute and the exchange -- a single
+    z-march whose boundary planes are stored locally AND into the neighbour's ghost planes through the peer
+    mapping; the kernel raises the neighbour's flag when a boundary pair has landed and waits on its own flags
+    right before it first touches a ghost plane.  The march direction alternates from step to step, so every
+    ghost plane is produced almost a full step before it is needed (csrc/kernels_gs3d_slab.cuh), and the whole
+    rollout is issued from ONE C call (percnn_slab_rollout_fwd) -- no per-step Python.
 
 `exchange_ghosts` is device-agnostic (it only moves planes with torch.distributed), which is what the
 world_size-2 gloo tests exercise on CPU; the step kernels themselves are CUDA-only.
@@ -125,7 +127,7 @@ class SlabRollout:
                 self.symm = None
         self.epoch = 1
         if self.symm is not None:
-            self.transport = "symm" if transport == "symm" or self.nz < 5 else "fused"
+            self.transport = "symm" if transport == "symm" else "fused"
             both.zero_()
             self._words.zero_()
             self.bufs = [both[0], both[1]]
@@ -154,7 +156,7 @@ class SlabRollout:
         if self.transport == "fused":
             # ghosts of the current buffer are valid up to the current epoch on every rank
             self._words[0:2].fill_(self.epoch)
-            self._words[2:4].zero_()
+            self._words[2:5].zero_()
             torch.cuda.synchronize(self.device)
             dist.barrier(self.group)
 
@@ -167,8 +169,16 @@ class SlabRollout:
 
     def describe(self):
         H, W = self.plan.spatial[1:]
+        overlap = {
+            "fused": "one kernel per step: boundary planes are stored straight into the neighbours' ghost planes over NVLink "
+                     "from inside the z-march, flags raised/awaited in-kernel, march direction alternating per step; "
+                     "whole rollout issued by one C call (no second stream, no NCCL on the data path)",
+            "symm": "boundary kernels first, peer copies + stream signals on a second stream under the interior kernel",
+            "nccl": "boundary kernels first, grouped ncclSend/ncclRecv on a second stream under the interior kernel",
+            "local": "single rank: ghost planes are a local wrap copy",
+        }[self.transport]
         return {"transport": self.transport, "planes_per_rank": self.nz, "ghost_bytes_per_side_per_step": 2 * 2 * H * W * 4,
-                "cuda_graph": bool(self.use_graph), "overlap": "boundary planes first, exchange on a second stream under the interior kernel"}
+                "cuda_graph": bool(self.use_graph), "overlap": overlap}
 
     # -- exchange -------------------------------------------------------------------------------
     def _exchange_blocking(self, b: int) -> None:
@@ -232,32 +242,19 @@ class SlabRollout:
             self.plan.step_fwd_range(cur, nxt, 2, nz - 2)
         self.cur ^= 1
 
-    def _step_fused(self) -> None:
-        from ._lib import SlabLink
-        nxt = self.cur ^ 1
-        link = SlabLink()
-        link.peer_lo_out = self.peer_lo[nxt].data_ptr()
-        link.peer_hi_out = self.peer_hi[nxt].data_ptr()
-        link.my_flags = self._words.data_ptr()
-        link.peer_lo_flags = self._peer_lo_words.data_ptr()
-        link.peer_hi_flags = self._peer_hi_words.data_ptr()
-        link.scratch = self._words.data_ptr() + 8
-        link.epoch = self.epoch & 0xFFFFFFFF
-        self.plan.step_fwd_fused_halo(self.bufs[self.cur], self.bufs[nxt], link)
-        self.epoch += 1
-        self.cur = nxt
-
-    # -- training: forward with a tape, fused-halo adjoint ------------------------------------------
-    def _link(self, peer_lo_ptr: int, peer_hi_ptr: int):
-        from ._lib import SlabLink
-        link = SlabLink()
-        link.peer_lo_out, link.peer_hi_out = peer_lo_ptr, peer_hi_ptr
-        link.my_flags = self._words.data_ptr()
-        link.peer_lo_flags = self._peer_lo_words.data_ptr()
-        link.peer_hi_flags = self._peer_hi_words.data_ptr()
-        link.scratch = self._words.data_ptr() + 8
-        link.epoch = self.epoch & 0xFFFFFFFF
-        return link
+    def _ring(self):
+        """percnn_slab_ring_t over the two peer-mapped ping-pong buffers."""
+        from ._lib import SlabRing
+        r = SlabRing()
+        for i in range(2):
+            r.buf[i] = self.bufs[i].data_ptr()
+            r.peer_lo_buf[i] = self.peer_lo[i].data_ptr()
+            r.peer_hi_buf[i] = self.peer_hi[i].data_ptr()
+        r.my_flags = self._words.data_ptr()
+        r.peer_lo_flags = self._peer_lo_words.data_ptr()
+        r.peer_hi_flags = self._peer_hi_words.data_ptr()
+        r.scratch = self._words.data_ptr() + 8
+        return r
 
     def refresh_params(self) -> None:
         """Re-read the cell's parameters (call after an optimiser step)."""
@@ -284,10 +281,8 @@ class SlabRollout:
         tape[0].copy_(self.bufs[self.cur])
         torch.cuda.synchronize(self.device)
         dist.barrier(self.group)          # every rank's slot 0 (incl. ghosts) is in place before anyone mirrors into the tape
-        for t in range(nsteps):
-            link = self._link(self._tape_lo[t + 1].data_ptr(), self._tape_hi[t + 1].data_ptr())
-            self.plan.step_fwd_fused_halo(tape[t], tape[t + 1], link)
-            self.epoch += 1
+        self.plan.slab_rollout_tape(tape, self._tape_lo, self._tape_hi, self._ring(), nsteps, self.epoch)
+        self.epoch += nsteps
         self.bufs[self.cur].copy_(tape[nsteps])
         return tape
 
@@ -338,23 +333,14 @@ class SlabRollout:
             self.bufs[b][:, 2:nz + 2].copy_(g_tape[nsteps][:, 2:nz + 2])
         self._exchange_blocking(b)
         self._words[0:2].fill_(self.epoch)
-        self._words[2:4].zero_()
+        self._words[2:5].zero_()
         torch.cuda.synchronize(self.device)
         dist.barrier(self.group)
-        slot = spec.nsel if spec is not None else 0
-        for t in range(nsteps - 1, -1, -1):
-            nxt = b ^ 1
-            link = self._link(self.peer_lo[nxt].data_ptr(), self.peer_hi[nxt].data_ptr())
-            frame = None
-            if spec is not None and spec.sel[t]:
-                slot -= 1
-                frame = target_sub[slot]
-            plan.step_bwd_loss(tape[t], self.bufs[b], self.bufs[nxt], target_frame=frame,
-                               stride=spec.stride if frame is not None else 1,
-                               n_total=spec.n_total if frame is not None else 0, gscale=gscale,
-                               g_add=None if g_tape is None else g_tape[t], link=link)
-            self.epoch += 1
-            b = nxt
+        if g_tape is not None and (not g_tape.is_contiguous() or tuple(g_tape.shape) != tuple(tape.shape)):
+            raise ValueError("g_tape must be a contiguous tensor of the tape's shape")
+        plan.slab_rollout_bwd(tape, g_tape, spec, target_sub, gscale, self._ring(), nsteps, self.epoch)
+        self.epoch += nsteps
+        b = nsteps & 1
         g_h0 = self.bufs[b][:, 2:nz + 2].clone()
         sums = plan.reduction_sums()
         dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)     # one tiny all-reduce per backward pass
@@ -363,15 +349,17 @@ class SlabRollout:
         return g_h0, grads
 
     def error_word(self) -> int:
-        """Non-zero if a fused step gave up waiting for a neighbour (device-side spin deadline)."""
+        """Non-zero if a fused step gave up waiting for a neighbour (device-side spin deadline).  The kernel also
+        TRAPS in that case, so normally the caller sees a CUDA error at its next synchronisation instead."""
         return int(self._words[3].item()) if self.transport == "fused" else 0
 
     def run(self, nsteps: int) -> None:
         """Advance the slab by nsteps time steps.  Invariant on entry and exit: the ghosts of the current
         buffer are valid and every exchange signal has been consumed (set_state() establishes it)."""
         if self.transport == "fused":
-            for _ in range(nsteps):
-                self._step_fused()
+            self.plan.slab_rollout_fwd(self._ring(), self.cur, nsteps, self.epoch)
+            self.epoch += nsteps
+            self.cur ^= nsteps & 1
             return
         for i in range(nsteps):
             self._step(first=(i == 0))

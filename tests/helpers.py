@@ -76,3 +76,11 @@ def make_cell(tag):
 def cell_params_dict(cell):
     """{state_dict key: tensor on CPU} -- the oracle's parameter format."""
     return {k: v.detach().cpu() for k, v in cell.state_dict().items()}
+
+
+def state_checksum(t):
+    """Fingerprint of a seeded synthetic state (sum, sum |.|, sum of squares and 9 equally spaced samples): the full-size
+    goldens store it instead of the multi-MB state itself, the tests regenerate the state from its seed and compare."""
+    d = t.detach().double().reshape(-1)
+    idx = torch.linspace(0, d.numel() - 1, 9, dtype=torch.float64).long()
+    return np.concatenate([[float(d.sum()), float(d.abs().sum()), float((d * d).sum())], d[idx].numpy()])

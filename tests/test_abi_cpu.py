@@ -44,7 +44,7 @@ def test_plan_create_fails_loudly_without_a_gpu():
     L = _lib.lib()
     assert L.percnn_device_ok(0) == 0
     d = _lib.Desc()
-    d.abi_version, d.ndim, d.dtype, d.cell, d.ksize, d.hidden = 1, 2, 0, 0, 1, 4
+    d.abi_version, d.ndim, d.dtype, d.cell, d.ksize, d.hidden = _lib.ABI_VERSION, 2, 0, 0, 1, 4
     d.extent[0], d.extent[1], d.extent[2] = 1, 8, 8
     d.dt, d.dx, d.mu_up = 0.1, 0.1, 1.0
     h = ctypes.c_void_p()
@@ -60,7 +60,7 @@ def test_descriptor_validation_messages():
     d.abi_version = 99
     assert L.percnn_plan_create(ctypes.byref(d), ctypes.byref(h)) == 1
     assert b"abi_version" in L.percnn_last_error()
-    d.abi_version, d.ndim = 1, 4
+    d.abi_version, d.ndim = _lib.ABI_VERSION, 4
     assert L.percnn_plan_create(ctypes.byref(d), ctypes.byref(h)) == 1
     assert L.percnn_plan_create(None, ctypes.byref(h)) == 1
     assert L.percnn_param_count(None) == -1
