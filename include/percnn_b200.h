@@ -121,13 +121,20 @@ int percnn_step_fwd_range(percnn_plan_t* plan, const void* h_in, void* h_out, in
 /* Slab-mode step with the halo exchange fused into the kernel (multi-GPU, peer-mapped buffers over NVLink; replaces
  * nothing in the reference, which is single-GPU -- it is north_star's "domain-decomposed ... halo exchange of the
  * ghost cells only").  ONE kernel per time step marches every tile through all local planes in a
- * single pass; output planes 0,1 and D-2,D-1 are stored locally AND into the neighbours' ghost planes; when all
- * tiles have stored a boundary pair the kernel raises that neighbour's flag (release, system scope).  Before its
- * first TMA load of a ghost plane it waits (acquire) for my_flags >= epoch.  The march direction alternates with
- * the parity of `epoch` (even: ascending z, odd: descending), so that every ghost plane is produced almost a full
- * step before it is consumed and no NVLink latency is exposed.  A wait that exceeds its spin deadline sets the
- * error word and TRAPS (the rollout must not continue on stale ghosts): the caller sees a CUDA error at its next
- * synchronisation.  No NCCL call and no host round trip per step.  All pointers are device pointers. */
+ * single pass; a helper warp per CTA copies the boundary planes 0,1 and D-2,D-1 of the output into the neighbours'
+ * ghost planes and, when all tiles of a pair have landed, raises that neighbour's flag (release, system scope).
+ * Before its first TMA load of a ghost plane the kernel waits (acquire) for my_flags >= epoch.  The march direction
+ * alternates with the parity of `epoch` (even: ascending z, odd: descending), so that every ghost plane is produced
+ * almost a full step before it is consumed and no NVLink latency is exposed.  Inside a rollout the pair a step
+ * produces LAST is published by the next step's kernel (PERCNN_SLAB_DEFER_LATE / PERCNN_SLAB_FLUSH_PREV).  A wait
+ * that exceeds its spin deadline sets the error word and TRAPS (the rollout must not continue on stale ghosts): the
+ * caller sees a CUDA error at its next synchronisation.  No NCCL call and no host round trip per step.  All
+ * pointers are device pointers. */
+enum {                       /* percnn_slab_link_t.flags */
+  PERCNN_SLAB_FLUSH_PREV = 1,   /* the previous step (same rollout, epoch - 1) ran with DEFER_LATE: publish its last
+                                   boundary pair from h_in first (needs peer_lo_in / peer_hi_in) */
+  PERCNN_SLAB_DEFER_LATE = 2    /* leave the boundary pair produced last to the next step (which must FLUSH_PREV) */
+};
 typedef struct percnn_slab_link {
   void* peer_lo_out;        /* lower ring neighbour's h_out buffer (same [2][D+4][H][W] layout) */
   void* peer_hi_out;        /* upper ring neighbour's h_out buffer */
@@ -137,6 +144,9 @@ typedef struct percnn_slab_link {
   uint32_t* scratch;        /* 3 local words, zero-initialised: arrival counter (lower boundary), error word (spin
                                deadline), arrival counter (upper boundary) */
   uint32_t epoch;           /* waits for flags >= epoch, publishes epoch + 1; parity selects the march direction */
+  uint32_t flags;           /* PERCNN_SLAB_* */
+  void* peer_lo_in;         /* the neighbours' mappings of THEIR h_in buffers (only read with FLUSH_PREV) */
+  void* peer_hi_in;
 } percnn_slab_link_t;
 int percnn_step_fwd_fused_halo(percnn_plan_t* plan, const void* h_in, void* h_out, const percnn_slab_link_t* link,
                                void* stream);

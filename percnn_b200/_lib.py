@@ -46,7 +46,8 @@ class SlabLink(ctypes.Structure):
     """percnn_slab_link_t"""
     _fields_ = [
         ("peer_lo_out", c_void_p), ("peer_hi_out", c_void_p), ("my_flags", c_void_p), ("peer_lo_flags", c_void_p),
-        ("peer_hi_flags", c_void_p), ("scratch", c_void_p), ("epoch", ctypes.c_uint32),
+        ("peer_hi_flags", c_void_p), ("scratch", c_void_p), ("epoch", ctypes.c_uint32), ("flags", ctypes.c_uint32),
+        ("peer_lo_in", c_void_p), ("peer_hi_in", c_void_p),
     ]
 
 

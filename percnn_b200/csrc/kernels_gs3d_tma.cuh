@@ -69,6 +69,10 @@ struct Params {
   uint32_t epoch_wait, epoch_post;
   int debug;                 // bisecting aid: 1 = no mirror stores, 2 = no flag wait, 4 = no flag post
   uint32_t spin_limit;       // flag-wait spins before the kernel gives up (error word + trap)
+  float* peer_lo_src;        // the neighbours' mappings of the buffer that is `src` here (deferred boundary pair, see
+  float* peer_hi_src;        // kernels_gs3d_slab.cuh)
+  int flush_prev;            // 1: the previous step of this rollout deferred its last boundary pair to this kernel
+  int defer_late;            // 1: leave the boundary pair produced last to the next step's kernel
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -342,130 +346,7 @@ __device__ __forceinline__ void steady_plane(Consumer& c, bool drain, bool prefe
   advance_stage(c);
 }
 
-// SLOT is a template parameter so that every coefficient is a compile-time constant-bank address
-// (c[3][imm] / hoisted LDCU) instead of an indexed LDC per use.
-template <int SLOT>
-__global__ void __launch_bounds__(THREADS, 1)
-k_gs3d_fwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_halo,
-               const __grid_constant__ Params p) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  float* ring = reinterpret_cast<float*>(smem_raw);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + STAGES * STAGE_BYTES);
-  uint64_t* empty = full + STAGES;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], p.ty);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  // Programmatic dependent launch: the next step's grid may be scheduled while this one drains (its CTAs take
-  // the SMs our CTAs leave and run their prologue), and this grid touches global memory only after the previous
-  // one has completed (it wrote our input and reads the buffer we overwrite).
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  const int nitems = total_items(p);
-
-  if (warp >= TY) {
-    // ===== producer warp-group: one elected lane issues every TMA =====
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PRODUCER_REGS));
-    if (warp == TY && lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_main)) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_halo)) : "memory");
-      uint32_t it = 0;
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const ItemCoord ic = decode_item(p, item);
-        int yh[4] = {ic.y0 - 2, ic.y0 - 1, ic.y0 + p.ty, ic.y0 + p.ty + 1};   // periodic halo rows
-#pragma unroll
-        for (int h = 0; h < 4; ++h) yh[h] = yh[h] < 0 ? yh[h] + p.H : (yh[h] >= p.H ? yh[h] - p.H : yh[h]);
-        const uint32_t bytes_main = 2u * uint32_t(p.ty) * TX * 4u, bytes_halo = 2u * 4u * TX * 4u;
-        for (int k = 0; k < ic.nz + 4; ++k, ++it) {
-          const int s = it % STAGES;
-          if (it >= STAGES) mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
-          const bool with_halo = (k >= 2) && (k < ic.nz + 2);
-          const int pz = src_plane(p, ic.z0, k);
-          float* st = ring + s * STAGE_FLOATS;
-          mbar_expect_tx(&full[s], with_halo ? bytes_main + bytes_halo : bytes_main);
-#pragma unroll
-          for (int f = 0; f < 2; ++f) {
-            float* sf = st + f * ROWS * TX;
-            tma_load_4d(sf + 2 * TX, &tm_main, &full[s], ic.x0, ic.y0, pz, f);
-            if (with_halo) {
-              tma_load_4d(sf, &tm_halo, &full[s], ic.x0, yh[0], pz, f);
-              tma_load_4d(sf + TX, &tm_halo, &full[s], ic.x0, yh[1], pz, f);
-              tma_load_4d(sf + (p.ty + 2) * TX, &tm_halo, &full[s], ic.x0, yh[2], pz, f);
-              tma_load_4d(sf + (p.ty + 3) * TX, &tm_halo, &full[s], ic.x0, yh[3], pz, f);
-            }
-          }
-        }
-      }
-    }
-    return;
-  }
-
-  // ===== consumer warps =====
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONSUMER_REGS));
-  if (warp >= p.ty) return;   // tile shorter than 16 rows: the spare warps are done (after the aligned setmaxnreg)
-  Consumer c;
-  c.P = c_prep[SLOT].f;
-  c.ring = ring;
-  c.full = full;
-  c.empty = empty;
-  c.s = 0;
-  c.parity = 0;
-  c.row = warp;
-  c.lane = lane;
-  c.toff = uint32_t(warp) * uint32_t(p.W) + 4u * uint32_t(lane);
-  c.is_seam = (lane == 0) || (lane == 31);
-  const int64_t plane = int64_t(p.H) * p.W;
-  float4 wu[5], wv[5];
-  float2 seam_next[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-    const ItemCoord ic = decode_item(p, item);
-    // uniform per-item bases; the per-lane part (toff / seam_off) never changes
-    const float* src_xy = p.src + int64_t(ic.y0) * p.W + ic.x0;
-    float* out = p.dst + (int64_t(ic.z0 + p.dst_zoff) * p.H + ic.y0) * p.W + ic.x0 + c.toff;
-    int xs = (lane == 0) ? ic.x0 - 2 : ic.x0 + TX;
-    xs = xs < 0 ? xs + p.W : (xs >= p.W ? xs - p.W : xs);
-    const int seam_off = warp * p.W + xs - ic.x0;
-    int pz = src_plane(p, ic.z0, 2);   // source plane whose seam cells are fetched next (local plane 2 first)
-    const float* seam_ptr = src_xy + int64_t(pz) * plane + seam_off;   // advanced by one plane per iteration
-    const int64_t wrap_back = int64_t(p.D) * plane;
-
-    warm_plane<0>(c, true, wu, wv);
-    warm_plane<1>(c, true, wu, wv);
-    warm_plane<2>(c, false, wu, wv);
-    warm_plane<3>(c, false, wu, wv);
-    ldg_f2_if(c.is_seam, seam_ptr, seam_next[0]);
-    ldg_f2_if(c.is_seam, seam_ptr + p.src_field, seam_next[1]);
-
-    const int nk = ic.nz + 4;   // local planes 0 .. nz+3; outputs for k = 4 .. nz+3
-#define PERCNN_STEADY(RR)                                                                                     \
-  {                                                                                                           \
-    seam_ptr += plane;                                                                                        \
-    if (p.wrap_z && ++pz >= p.D) {                                                                            \
-      pz -= p.D;                                                                                              \
-      seam_ptr -= wrap_back;                                                                                  \
-    }                                                                                                         \
-    steady_plane<RR, false>(c, k >= ic.nz + 2, k <= ic.nz + 2, seam_ptr, p.src_field, out, nullptr, p.dst_field, \
-                            wu, wv, seam_next);                                                               \
-    out += plane;                                                                                             \
-    ++k;                                                                                                      \
-  }
-    int k = 4;
-    PERCNN_STEADY(4)
-    while (k + 5 <= nk) {
-      PERCNN_STEADY(0) PERCNN_STEADY(1) PERCNN_STEADY(2) PERCNN_STEADY(3) PERCNN_STEADY(4)
-    }
-    if (k < nk) PERCNN_STEADY(0)
-    if (k < nk) PERCNN_STEADY(1)
-    if (k < nk) PERCNN_STEADY(2)
-    if (k < nk) PERCNN_STEADY(3)
-#undef PERCNN_STEADY
-  }
-}
+// (the kernels themselves -- periodic and slab mode -- are in kernels_gs3d_slab.cuh: one body, three modes)
 
 }  // namespace tma3d
 }  // namespace percnn

@@ -23,6 +23,10 @@ constexpr int BWD_FLUSH = 32;
 constexpr int BWD_WARPS = 15;
 constexpr int BWD_THREADS = (BWD_WARPS + 1) * 32;
 constexpr int SMEM_BYTES_BWD = SMEM_BYTES + 16 * kRedPiK1 * 8 + 64 + 10 * BWD_THREADS * 8;
+// slab mode: the halo helper's staging rows come after everything else (half a boundary pair: two chunks per pair)
+constexpr int BWD_STAGE_OFF = (SMEM_BYTES_BWD + 127) / 128 * 128;   // TMA destinations are 128-byte aligned
+constexpr int SMEM_BYTES_BWD_SLAB = BWD_STAGE_OFF + SLAB_FIELD_PAIR_BYTES;
+static_assert(SMEM_BYTES_BWD_SLAB <= 227 * 1024, "shared memory budget of the slab adjoint");
 
 struct BwdExtra {
   const float* h;        // stored state of this step, same layout as the G buffers
@@ -186,12 +190,14 @@ __device__ __forceinline__ void adjoint_plane(Consumer& c, const float* __restri
   }
 }
 
-// FUSED: slab mode with the halo exchange of the gradient fused in (single z-march, direction DOWN on odd steps --
-// see kernels_gs3d_slab.cuh; the protocol is the forward kernel's).
+// FUSED: slab mode with the halo exchange of the gradient fused in (single z-march, direction DOWN on odd steps,
+// boundary pairs moved by a helper warp, the pair produced last deferred to the next step's kernel -- see
+// kernels_gs3d_slab.cuh; the protocol is the forward kernel's).  Slab plans keep ty <= SLAB_MAX_TY, so consumer warp
+// BWD_WARPS - 1 is free to be the helper.
 template <int SLOT, bool FUSED, bool DOWN>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_halo,
-               const __grid_constant__ Params p, const __grid_constant__ BwdExtra x) {
+               const __grid_constant__ Params p, const __grid_constant__ BwdExtra x, const __grid_constant__ SlabMaps sm) {
   static_assert(FUSED || !DOWN, "only the slab kernel marches downwards");
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   float* ring = reinterpret_cast<float*>(smem_raw);
@@ -204,6 +210,7 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], p.ty);
     }
+    if (FUSED) mbar_init(reinterpret_cast<uint64_t*>(smem_raw + SLAB_HELPER_OFF), 1);   // (sits in the padding before wacc)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   float2* macc_all = reinterpret_cast<float2*>(wacc + 16 * kRedPiK1);   // [10][BWD_THREADS] per-lane monomial sums
@@ -211,6 +218,8 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
   for (int m = 0; m < 10; ++m) macc_all[m * BWD_THREADS + threadIdx.x] = make_float2(0.f, 0.f);
   __syncthreads();
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // see the forward kernel
+  if (FUSED && warp == BWD_WARPS && lane == 0)   // the ghost pair this march starts from: overlaps the previous kernel's tail
+    wait_flag(p.my_flags + (DOWN ? 1 : 0), p.epoch_wait, p.scratch + 1, p.spin_limit);
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const int nitems = total_items(p);
 
@@ -230,23 +239,7 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
           const int s = it % STAGES;
           if (it >= STAGES) mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
           const bool with_halo = (k >= 2) && (k < ic.nz + 2);
-          int pz;
-          if (FUSED) {
-            const int zi = DOWN ? ic.z0 + ic.nz + 1 - k : ic.z0 + k - 2;   // interior index of local plane k
-            if (zi < 0 && wait_lo) {
-              wait_flag(p.my_flags + 0, p.epoch_wait, p.scratch + 1, p.spin_limit);
-              asm volatile("fence.proxy.async.global;" ::: "memory");
-              wait_lo = false;
-            }
-            if (zi >= p.D && wait_hi) {
-              wait_flag(p.my_flags + 1, p.epoch_wait, p.scratch + 1, p.spin_limit);
-              asm volatile("fence.proxy.async.global;" ::: "memory");
-              wait_hi = false;
-            }
-            pz = zi + 2;
-          } else {
-            pz = src_plane(p, ic.z0, k);
-          }
+          const int pz = FUSED ? slab_plane_index<DOWN>(p, ic, k, wait_lo, wait_hi) + 2 : src_plane(p, ic.z0, k);
           float* st = ring + s * STAGE_FLOATS;
           mbar_expect_tx(&full[s], with_halo ? bytes_main + bytes_halo : bytes_main);
 #pragma unroll
@@ -267,6 +260,11 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
   }
 
   // ===== consumer warps =====
+  if (FUSED && warp == BWD_WARPS - 1) {   // the helper warp moves the boundary pairs to the neighbours
+    slab_helper<DOWN, 1>(p, sm, lane, nitems, reinterpret_cast<uint64_t*>(smem_raw + SLAB_HELPER_OFF),
+                         reinterpret_cast<float*>(smem_raw + BWD_STAGE_OFF));
+    return;
+  }
   if (warp >= p.ty) return;
   Consumer c;
   c.P = c_prep[SLOT].f;
@@ -284,7 +282,6 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
   const int64_t plane = int64_t(p.H) * p.W;
   const int64_t zstep = DOWN ? -plane : plane;
   const int64_t field = p.dst_field;
-  const int ntiles = p.nxt * p.nyt;
   float2 seam_next[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
   float aacc[2] = {0.f, 0.f};
   int since_flush = 0;
@@ -323,12 +320,6 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
     const int64_t tile_off = int64_t(ic.y0) * p.W + ic.x0;
     const int zfirst = DOWN ? ic.z0 + ic.nz - 1 : ic.z0;   // interior index of the first output plane
     int64_t off = int64_t(zfirst + p.dst_zoff) * plane + tile_off + c.toff;   // this lane's quad, first output plane
-    float* mir_lo = nullptr;
-    float* mir_hi = nullptr;
-    if (FUSED) {   // see k_gs3d_fwd_slab
-      mir_lo = p.peer_lo_dst + int64_t(p.D + 2) * plane + tile_off + c.toff;
-      mir_hi = p.peer_hi_dst - int64_t(p.D - 2) * plane + tile_off + c.toff;
-    }
     int xs = (lane == 0) ? ic.x0 - 2 : ic.x0 + TX;
     xs = xs < 0 ? xs + p.W : (xs >= p.W ? xs - p.W : xs);
     const int seam_off = warp * p.W + xs - ic.x0;
@@ -348,18 +339,10 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
         seam_ptr += zstep;
         int64_t inj_row = -1;
         if (inj_ly >= 0 && zi % x.inj.s == 0) inj_row = (int64_t(zi / x.inj.s) * x.inj.lh + inj_ly) * x.inj.lw;
-        float* mirror = nullptr;
-        if (FUSED) {
-          if (zi < 2) mirror = mir_lo + int64_t(zi) * plane;
-          else if (zi >= p.D - 2) mirror = mir_hi + int64_t(zi) * plane;
-        }
-        adjoint_plane<FUSED, DOWN>(c, TP, k <= ic.nz + 2, seam_ptr, field, zstep, off, p.dst, mirror, x.h, x.gadd,
+        adjoint_plane<false, DOWN>(c, TP, k <= ic.nz + 2, seam_ptr, field, zstep, off, p.dst, nullptr, x.h, x.gadd,
                                    k + 1 < nk, valid, seam_next, aacc, macc, x.inj, inj_row, ic.x0 + 4 * lane);
         off += zstep;
-        if (FUSED) {
-          if (zi == (DOWN ? 0 : 1)) slab_post(p, warp, lane, p.scratch + 0, p.post_lo_flag, ntiles);
-          if (zi == (DOWN ? p.D - 2 : p.D - 1)) slab_post(p, warp, lane, p.scratch + 2, p.post_hi_flag, ntiles);
-        }
+        if (FUSED && k == 5) slab_consumer_signal<DOWN, 1>(p, item);   // first boundary pair stored: over to the helper
         zi += DOWN ? -1 : 1;
         if (++since_flush >= BWD_FLUSH) flush();
       }
@@ -372,10 +355,11 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
 #pragma unroll
       for (int j = 1; j <= 4; ++j) mbar_arrive(&c.empty[(c.s + STAGES - j) & (STAGES - 1)]);
     }
+    if (FUSED) slab_consumer_signal<DOWN, 2>(p, item);
   }
   flush();
   // ---- CTA result -> global partials; last CTA folds all CTAs in fixed order ----
-  asm volatile("bar.sync 2, %0;" ::"r"(p.ty * 32) : "memory");
+  asm volatile("bar.sync 3, %0;" ::"r"(p.ty * 32) : "memory");   // (ids 1, 2: slab helper hand-over)
   __shared__ bool s_last;
   constexpr int NR = kRedPiK1;
   if (warp == 0) {

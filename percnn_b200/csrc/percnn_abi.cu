@@ -273,6 +273,12 @@ int resolve_link(const percnn_plan* p, const percnn_slab_link_t* link, SlabLink*
   l->scratch = link->scratch;
   l->epoch_wait = link->epoch;
   l->epoch_post = link->epoch + 1;
+  l->flush_prev = (link->flags & PERCNN_SLAB_FLUSH_PREV) != 0;
+  l->defer_late = (link->flags & PERCNN_SLAB_DEFER_LATE) != 0;
+  l->peer_lo_src = static_cast<float*>(link->peer_lo_in);
+  l->peer_hi_src = static_cast<float*>(link->peer_hi_in);
+  if (l->flush_prev && (!l->peer_lo_src || !l->peer_hi_src))
+    return fail(PERCNN_ERR_INVALID, "PERCNN_SLAB_FLUSH_PREV needs peer_lo_in / peer_hi_in");
   return PERCNN_OK;
 }
 
@@ -509,6 +515,9 @@ int percnn_slab_rollout_fwd(percnn_plan_t* p, const percnn_slab_ring_t* ring, in
     link.peer_hi_flags = ring->peer_hi_flags;
     link.scratch = ring->scratch;
     link.epoch = epoch + uint32_t(s);
+    link.flags = (s > 0 ? PERCNN_SLAB_FLUSH_PREV : 0) | (s + 1 < nsteps ? PERCNN_SLAB_DEFER_LATE : 0);
+    link.peer_lo_in = ring->peer_lo_buf[src];
+    link.peer_hi_in = ring->peer_hi_buf[src];
     SlabLink l;
     int rc = resolve_link(p, &link, &l);
     if (rc) return rc;
@@ -536,6 +545,9 @@ int percnn_slab_rollout_tape(percnn_plan_t* p, void* tape, void* peer_lo_tape, v
     link.peer_hi_flags = ring->peer_hi_flags;
     link.scratch = ring->scratch;
     link.epoch = epoch + uint32_t(t);
+    link.flags = (t > 0 ? PERCNN_SLAB_FLUSH_PREV : 0) | (t + 1 < nsteps ? PERCNN_SLAB_DEFER_LATE : 0);
+    link.peer_lo_in = static_cast<char*>(peer_lo_tape) + size_t(t) * sb;
+    link.peer_hi_in = static_cast<char*>(peer_hi_tape) + size_t(t) * sb;
     SlabLink l;
     int rc = resolve_link(p, &link, &l);
     if (rc) return rc;
@@ -607,6 +619,9 @@ int percnn_slab_rollout_bwd(percnn_plan_t* p, const void* tape, const void* g_ta
     link.peer_hi_flags = ring->peer_hi_flags;
     link.scratch = ring->scratch;
     link.epoch = epoch + uint32_t(nsteps - 1 - t);
+    link.flags = (t < nsteps - 1 ? PERCNN_SLAB_FLUSH_PREV : 0) | (t > 0 ? PERCNN_SLAB_DEFER_LATE : 0);
+    link.peer_lo_in = ring->peer_lo_buf[b];
+    link.peer_hi_in = ring->peer_hi_buf[b];
     SlabLink l;
     int rc = resolve_link(p, &link, &l);
     if (rc) return rc;

@@ -22,6 +22,11 @@ struct TmaMapPair {
   CUtensorMap main_map, halo_map;
 };
 
+struct TmaPairMap {
+  const void* base = nullptr;
+  CUtensorMap map;
+};
+
 constexpr int kMaxBlocks = 2048;
 constexpr size_t kWsAcc = 0;            // kRedMaxSmall doubles
 constexpr size_t kWsCounter = 256;      // one unsigned
@@ -45,6 +50,9 @@ struct SlabLink {
   uint32_t* post_hi_flag = nullptr;
   uint32_t* scratch = nullptr;
   uint32_t epoch_wait = 0, epoch_post = 0;
+  float* peer_lo_src = nullptr;   // the neighbours' mappings of the buffers that correspond to my input (FLUSH_PREV)
+  float* peer_hi_src = nullptr;
+  bool flush_prev = false, defer_late = false;
 };
 
 }  // namespace percnn
@@ -74,6 +82,8 @@ struct percnn_plan {
   percnn_encode_tiled_fn encode = nullptr;
   percnn::TmaMapPair maps[4];
   int map_rr = 0;
+  percnn::TmaPairMap pair_maps[8];   // slab mode: per buffer, box = one field's boundary pair (halo helper)
+  int pair_rr = 0;
   // host-path scratch
   void* h_params_dev = nullptr;
   void* h_states = nullptr;
@@ -148,6 +158,7 @@ struct TmaTiling {
 };
 TmaTiling choose_tiling(int nxt, int H, int depth, int nsm, int fixed_ty, int max_ty, int min_chunk = 1);
 int get_maps(percnn_plan* p, const void* src, const CUtensorMap** main_map, const CUtensorMap** halo_map);
+int get_pair_map(percnn_plan* p, const void* base, CUtensorMap* out);   // box {128, ty, 2 planes, 1 field}
 
 // Launch with programmatic stream serialization allowed (the kernels call griddepcontrol.wait themselves).
 template <typename... KArgs>

@@ -79,6 +79,43 @@ int get_maps(percnn_plan* p, const void* src, const CUtensorMap** main_map, cons
   return PERCNN_OK;
 }
 
+int get_pair_map(percnn_plan* p, const void* base, CUtensorMap* out) {
+  for (auto& m : p->pair_maps)
+    if (m.base == base) {
+      *out = m.map;
+      return PERCNN_OK;
+    }
+  TmaPairMap& m = p->pair_maps[p->pair_rr];
+  p->pair_rr = (p->pair_rr + 1) % 8;
+  const Geom& g = p->g;
+  cuuint64_t gdim[4] = {cuuint64_t(g.W), cuuint64_t(g.H), cuuint64_t(g.D + 2 * g.ghost), 2};
+  cuuint64_t gstr[3] = {cuuint64_t(g.W) * 4, cuuint64_t(g.plane) * 4, cuuint64_t(g.field) * 4};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  cuuint32_t box[4] = {tma3d::TX, cuuint32_t(p->ty), 2, 1};
+  const CUresult r = p->encode(&m.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), gdim, gstr, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    m.base = nullptr;
+    return fail(PERCNN_ERR_CUDA, "cuTensorMapEncodeTiled (pair map) failed with CUresult " + std::to_string(int(r)));
+  }
+  m.base = base;
+  *out = m.map;
+  return PERCNN_OK;
+}
+
+// The halo helper's five tensor maps for one fused step (see tma3d::SlabMaps).
+int slab_fill_maps(percnn_plan* p, const SlabLink* link, const float* src, float* dst, bool down, tma3d::SlabMaps* sm) {
+  int rc = get_pair_map(p, dst, &sm->dst);
+  if (!rc) rc = get_pair_map(p, src, &sm->src);
+  if (!rc) rc = get_pair_map(p, down ? link->peer_hi_dst : link->peer_lo_dst, &sm->peer_e_dst);
+  if (!rc) rc = get_pair_map(p, down ? link->peer_lo_dst : link->peer_hi_dst, &sm->peer_l_dst);
+  if (rc) return rc;
+  if (link->flush_prev) return get_pair_map(p, down ? link->peer_hi_src : link->peer_lo_src, &sm->peer_e_src);
+  sm->peer_e_src = sm->peer_e_dst;   // never used without FLUSH_PREV; keep it a valid map
+  return PERCNN_OK;
+}
+
 cudaError_t tma_fwd_load_prep(const PrepBlock* d_prep, int slot, cudaStream_t st) {
   return cudaMemcpyToSymbolAsync(c_prep, d_prep, sizeof(PrepBlock), size_t(slot) * sizeof(PrepBlock),
                                  cudaMemcpyDeviceToDevice, st);
@@ -97,9 +134,9 @@ int tma_fwd_setup(percnn_plan* p) {
   case S:                                                                                                               \
     ae = cudaFuncSetAttribute(tma3d::k_gs3d_fwd_tma<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma3d::SMEM_BYTES); \
     if (ae == cudaSuccess)                                                                                              \
-      ae = cudaFuncSetAttribute(tma3d::k_gs3d_fwd_slab<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma3d::SMEM_BYTES); \
+      ae = cudaFuncSetAttribute(tma3d::k_gs3d_fwd_slab<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma3d::SMEM_BYTES_SLAB); \
     if (ae == cudaSuccess)                                                                                              \
-      ae = cudaFuncSetAttribute(tma3d::k_gs3d_fwd_slab<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma3d::SMEM_BYTES); \
+      ae = cudaFuncSetAttribute(tma3d::k_gs3d_fwd_slab<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma3d::SMEM_BYTES_SLAB); \
     break;
     PERCNN_TMA_ATTR(0) PERCNN_TMA_ATTR(1) PERCNN_TMA_ATTR(2) PERCNN_TMA_ATTR(3) PERCNN_TMA_ATTR(4) PERCNN_TMA_ATTR(5)
 #undef PERCNN_TMA_ATTR
@@ -108,7 +145,9 @@ int tma_fwd_setup(percnn_plan* p) {
   if (ae != cudaSuccess) return fail(PERCNN_ERR_CUDA, "cudaFuncSetAttribute(tma fwd) failed");
   int fixed_ty = 0;
   if (const char* e = getenv("PERCNN_TMA_TY")) fixed_ty = atoi(e);
-  const int max_ty = 15;   // tma3d::BWD_WARPS: the adjoint kernel runs 15 consumer warps and shares the tiling
+  // the adjoint kernel runs 15 consumer warps (tma3d::BWD_WARPS) and shares the tiling; slab plans keep one more
+  // warp free for the halo helper (tma3d::SLAB_MAX_TY)
+  const int max_ty = p->desc.slab_ghost ? tma3d::SLAB_MAX_TY : 15;
   if (fixed_ty < 0 || fixed_ty > max_ty || fixed_ty > p->g.H) fixed_ty = 0;
   // slab plans: both boundary pairs must sit inside one z-chunk each (fused halo kernels)
   const TmaTiling til = choose_tiling(p->g.W / tma3d::TX, p->g.H, p->g.D, p->sm_count, fixed_ty, max_ty,
@@ -167,6 +206,10 @@ int tma_fill_params(percnn_plan* p, tma3d::Params& prm, const float* src, float*
     prm.epoch_wait = link->epoch_wait;
     prm.epoch_post = link->epoch_post;
     prm.spin_limit = p->flag_spin_limit;
+    prm.peer_lo_src = link->peer_lo_src;
+    prm.peer_hi_src = link->peer_hi_src;
+    prm.flush_prev = link->flush_prev ? 1 : 0;
+    prm.defer_late = link->defer_late ? 1 : 0;
     if (const char* e = getenv("PERCNN_FUSED_DEBUG")) prm.debug = atoi(e);
   }
   prm.slot = p->slot;
@@ -183,14 +226,19 @@ int tma_fwd_launch(percnn_plan* p, const float* src, float* dst, int z_lo, int z
   if (rc) return rc;
   tma3d::Params prm;
   const int grid = tma_fill_params(p, prm, src, dst, z_lo, z_hi, link);
-  const bool down = link && (link->epoch_wait & 1u);   // the march direction alternates from step to step
+  bool down = link && (link->epoch_wait & 1u);   // the march direction alternates from step to step
+  tma3d::SlabMaps sm;
+  if (link) {
+    rc = slab_fill_maps(p, link, src, dst, down, &sm);
+    if (rc) return rc;
+  }
   cudaError_t le = cudaSuccess;
   switch (p->slot) {
 #define PERCNN_TMA_CASE(S)                                                                                              \
   case S:                                                                                                               \
     if (!link) le = launch_pdl(tma3d::k_gs3d_fwd_tma<S>, grid, tma3d::THREADS, tma3d::SMEM_BYTES, st, p->pdl, *mm, *hm, prm); \
-    else if (down) le = launch_pdl(tma3d::k_gs3d_fwd_slab<S, true>, grid, tma3d::THREADS, tma3d::SMEM_BYTES, st, p->pdl, *mm, *hm, prm); \
-    else le = launch_pdl(tma3d::k_gs3d_fwd_slab<S, false>, grid, tma3d::THREADS, tma3d::SMEM_BYTES, st, p->pdl, *mm, *hm, prm); \
+    else if (down) le = launch_pdl(tma3d::k_gs3d_fwd_slab<S, true>, grid, tma3d::THREADS, tma3d::SMEM_BYTES_SLAB, st, p->pdl, *mm, *hm, prm, sm); \
+    else le = launch_pdl(tma3d::k_gs3d_fwd_slab<S, false>, grid, tma3d::THREADS, tma3d::SMEM_BYTES_SLAB, st, p->pdl, *mm, *hm, prm, sm); \
     break;
     PERCNN_TMA_CASE(0) PERCNN_TMA_CASE(1) PERCNN_TMA_CASE(2) PERCNN_TMA_CASE(3) PERCNN_TMA_CASE(4) PERCNN_TMA_CASE(5)
 #undef PERCNN_TMA_CASE

@@ -125,8 +125,20 @@ class SlabRollout:
             dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
             if int(flag.item()) == 0:
                 self.symm = None
+        if world == 1 and transport == "fused":
+            # single rank, periodic ring of one: both neighbours are this rank itself, so the "peer" buffers are the
+            # local ones and the fused kernel mirrors its boundary planes into its own ghost planes.  Lets one GPU
+            # run (and time) exactly the kernel the multi-GPU path uses.
+            both = torch.zeros((2, *shape), dtype=torch.float32, device=self.device)
+            self._words = torch.zeros((8,), dtype=torch.int32, device=self.device)
+            self.symm = "self"
         self.epoch = 1
-        if self.symm is not None:
+        if self.symm == "self":
+            self.transport = "fused"
+            self.bufs = [both[0], both[1]]
+            self.peer_lo = self.peer_hi = both
+            self._peer_lo_words = self._peer_hi_words = self._words
+        elif self.symm is not None:
             self.transport = "symm" if transport == "symm" else "fused"
             both.zero_()
             self._words.zero_()
@@ -158,7 +170,8 @@ class SlabRollout:
             self._words[0:2].fill_(self.epoch)
             self._words[2:5].zero_()
             torch.cuda.synchronize(self.device)
-            dist.barrier(self.group)
+            if self.world > 1:
+                dist.barrier(self.group)
 
     def interior(self) -> torch.Tensor:
         return self.bufs[self.cur][:, 2:self.nz + 2]
@@ -268,19 +281,24 @@ class SlabRollout:
         if self.transport != "fused":
             raise NotImplementedError("rollout_tape needs the fused peer-memory transport")
         self.refresh_params()
-        import torch.distributed._symmetric_memory as symm_mem
         shape = (nsteps + 1, *self.plan.buffer_shape)
         if getattr(self, "_tape_shape", None) != shape:
-            self._tape = symm_mem.empty(shape, dtype=torch.float32, device=self.device)
-            hdl = symm_mem.rendezvous(self._tape, group=self.group if self.group is not None else dist.group.WORLD)
-            lo, hi = (self.rank - 1) % self.world, (self.rank + 1) % self.world
-            self._tape_lo = hdl.get_buffer(lo, shape, torch.float32)
-            self._tape_hi = hdl.get_buffer(hi, shape, torch.float32)
+            if self.symm == "self":
+                self._tape = torch.empty(shape, dtype=torch.float32, device=self.device)
+                self._tape_lo = self._tape_hi = self._tape
+            else:
+                import torch.distributed._symmetric_memory as symm_mem
+                self._tape = symm_mem.empty(shape, dtype=torch.float32, device=self.device)
+                hdl = symm_mem.rendezvous(self._tape, group=self.group if self.group is not None else dist.group.WORLD)
+                lo, hi = (self.rank - 1) % self.world, (self.rank + 1) % self.world
+                self._tape_lo = hdl.get_buffer(lo, shape, torch.float32)
+                self._tape_hi = hdl.get_buffer(hi, shape, torch.float32)
             self._tape_shape = shape
         tape = self._tape
         tape[0].copy_(self.bufs[self.cur])
         torch.cuda.synchronize(self.device)
-        dist.barrier(self.group)          # every rank's slot 0 (incl. ghosts) is in place before anyone mirrors into the tape
+        if self.world > 1:
+            dist.barrier(self.group)      # every rank's slot 0 (incl. ghosts) is in place before anyone mirrors into the tape
         self.plan.slab_rollout_tape(tape, self._tape_lo, self._tape_hi, self._ring(), nsteps, self.epoch)
         self.epoch += nsteps
         self.bufs[self.cur].copy_(tape[nsteps])
@@ -335,15 +353,17 @@ class SlabRollout:
         self._words[0:2].fill_(self.epoch)
         self._words[2:5].zero_()
         torch.cuda.synchronize(self.device)
-        dist.barrier(self.group)
+        if self.world > 1:
+            dist.barrier(self.group)
         if g_tape is not None and (not g_tape.is_contiguous() or tuple(g_tape.shape) != tuple(tape.shape)):
             raise ValueError("g_tape must be a contiguous tensor of the tape's shape")
         plan.slab_rollout_bwd(tape, g_tape, spec, target_sub, gscale, self._ring(), nsteps, self.epoch)
         self.epoch += nsteps
         b = nsteps & 1
         g_h0 = self.bufs[b][:, 2:nz + 2].clone()
-        sums = plan.reduction_sums()
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)     # one tiny all-reduce per backward pass
+        if self.world > 1:
+            sums = plan.reduction_sums()
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)     # one tiny all-reduce per backward pass
         grads = plan.param_grads_finish(self.flat)
         self.cur = 0   # the state buffers were used as gradient scratch: the caller must set_state() again
         return g_h0, grads

@@ -1,0 +1,77 @@
+"""The slab-mode (multi-GPU) kernels on ONE GPU: a ring of one rank is its own neighbour, so the fused-halo kernels
+mirror their boundary planes into their own ghost planes and wait on their own flags.  This runs exactly the
+kernels of the multi-GPU path (single z-march, alternating direction, in-kernel flags, C-side rollout loops) on
+the one-GPU test box; results must equal the periodic single-GPU kernels bit for bit."""
+import pytest
+import torch
+
+from percnn_b200 import engine, halo
+from tests.helpers import load_weights, make_cell
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+
+
+def _cell():
+    cell = make_cell("gs3d")
+    cell.load_state_dict(load_weights("gs3d"), strict=True)
+    return cell.to(DEV)
+
+
+def _state(shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand((2, *shape), generator=g) * 0.8 + 0.1).to(DEV)
+
+
+@pytest.mark.parametrize("shape,steps", [((40, 48, 256), 9), ((4, 16, 128), 6), ((7, 37, 128), 5), ((128, 128, 128), 8),
+                                         ((64, 512, 512), 3)])
+def test_self_ring_forward_is_bitwise_equal_to_periodic_kernel(shape, steps):
+    cell = _cell()
+    h0 = _state(shape, 3)
+    slab = halo.SlabRollout(cell, shape, DEV, 0, 1, transport="fused")
+    assert slab.transport == "fused"
+    with torch.no_grad():
+        ref = cell.rollout(h0[None], steps)[-1]
+    for rep in range(2):                       # the second run starts on the other march direction when steps is odd
+        slab.set_state(h0)
+        slab.run(steps)
+        assert torch.equal(slab.interior(), ref), (rep, float((slab.interior() - ref).abs().max()))
+    assert slab.error_word() == 0
+
+
+@pytest.mark.parametrize("shape", [(24, 48, 128), (64, 64, 256)])
+def test_self_ring_training_step_matches_periodic_adjoint(shape):
+    cell = _cell()
+    h0 = _state(shape, 4)
+    T = 5
+    sel = (True, False, True, False, True, False)
+    flat = engine.pack_params(cell._packed_tensors(), torch.float32)
+    plan1 = engine.get_plan(cell._spec(), shape, DEV)
+    plan1.params_load(flat)
+    spec = engine.DataLossSpec(sel=sel, stride=2)
+    g = torch.Generator(device=DEV).manual_seed(9)
+    tgt = torch.rand((3, *plan1.lowres_shape(2)), generator=g, device=DEV)
+    tape1 = torch.empty((T + 1, *plan1.buffer_shape), device=DEV)
+    plan1.rollout_fwd(h0, T, tape=tape1)
+    loss1 = plan1.data_loss_fwd(tape1, T, spec, tgt)
+    g_h0_ref, g_flat_ref = plan1.rollout_bwd_loss(flat, tape1, T, spec, tgt)
+
+    slab = halo.SlabRollout(cell, shape, DEV, 0, 1, transport="fused")
+    slab.set_state(h0)
+    tape = slab.rollout_tape(T)
+    nz = shape[0]
+    assert torch.equal(tape[:, :, 2:nz + 2], tape1)
+    loss = slab.data_loss(tape, tgt, sel, 2)
+    g_h0, grads = slab.backward(tape, None, loss=(tgt, sel, 2, None))
+    assert abs(float(loss) - float(loss1)) <= 1e-6 * abs(float(loss1))
+    assert torch.equal(g_h0, g_h0_ref)
+    rel = float((grads.double() - g_flat_ref.double()).norm() / g_flat_ref.double().norm())
+    assert rel <= 1e-6, rel
+    # dense gradient tape instead of the fused loss
+    w = torch.randn(tape.shape, generator=torch.Generator(device=DEV).manual_seed(2), device=DEV)
+    slab.set_state(h0)
+    tape = slab.rollout_tape(T)
+    g_h0d, gradsd = slab.backward(tape, w)
+    g_ref, gp_ref = plan1.rollout_bwd(flat, tape1, w[:, :, 2:nz + 2].contiguous(), [True] * (T + 1), T)
+    assert torch.equal(g_h0d, g_ref)
+    assert float((gradsd.double() - gp_ref.double()).norm() / gp_ref.double().norm()) <= 1e-6
