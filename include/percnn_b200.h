@@ -104,6 +104,10 @@ size_t percnn_workspace_bytes(const percnn_plan_t* plan, int nsteps);
 int percnn_plan_uses_tma(const percnn_plan_t* plan);
 /* Kernel launches issued by this plan since creation (bench "gpu_launches"). */
 int64_t percnn_plan_launch_count(const percnn_plan_t* plan);
+/* 1 if percnn_slab_rollout_fwd runs this (slab-mode) plan's rollouts of >= 2 steps as ONE persistent cooperative kernel
+ * (small slabs: the grid barrier doubles as the halo hand-shake) instead of one fused-halo kernel per step.  The
+ * persistent kernel is the gather kernel (PERCNN_FLAG_NO_TMA arithmetic), not the TMA z-march. */
+int percnn_plan_slab_persistent(const percnn_plan_t* plan);
 
 /* ---- parameters ------------------------------------------------------------------------------- */
 /* Digest the raw parameter tensors (device pointer, plan dtype) into the constant block the kernels

@@ -388,6 +388,111 @@ __global__ void __launch_bounds__(kMultiThreads) k_multi_step(Geom g, int slot, 
 }  // namespace percnn
 
 // =====================================================================================================
+// Persistent multi-step kernel for SMALL SLABS (multi-GPU, cfg4-class grids: 128^3 over 2..8 GPUs).  A slab of a
+// few MB holds a few microseconds of work per step, less than one kernel boundary plus the NVLink flag latency of
+// the per-step slab kernel (kernels_gs3d_slab.cuh) -- round 1 measured 128^3 getting SLOWER with more GPUs.  Here
+// ONE cooperative launch per rank runs the whole rollout: each step computes the slab (gather kernel, state in
+// L2), stores the boundary planes also into the neighbours' ghost planes (peer mapping, st.global), and the
+// per-step grid barrier doubles as the exchange point: block 0 waits for all blocks, raises both neighbours'
+// flags (st.release.sys), waits for its own two flags (ld.acquire.sys) and only then opens the barrier.  Flags and
+// epochs follow the protocol of the per-step kernels, so the two are interchangeable between rollout calls.
+// =====================================================================================================
+namespace percnn {
+
+struct SlabMultiArgs {
+  float* buf[2];              // my ping-pong state buffers [2][D+4][H][W]
+  float* peer_lo[2];          // lower / upper neighbour's mappings of theirs
+  float* peer_hi[2];
+  const uint32_t* my_flags;   // [0] lower ghosts valid up to epoch, [1] upper ghosts
+  uint32_t* post_lo_flag;     // lower neighbour's flags[1]
+  uint32_t* post_hi_flag;     // upper neighbour's flags[0]
+  uint32_t* err;              // error word (spin deadline)
+  uint32_t epoch0;
+  uint32_t spin_limit;
+  int nsteps;
+  int cur;                    // step s reads buf[cur ^ (s & 1)]
+};
+
+__global__ void __launch_bounds__(kMultiThreads) k_multi_step_slab(Geom g, int slot, SlabMultiArgs a, unsigned* counter) {
+  const float* P = PrepView<float>::get(c_prep[slot]);
+  const int64_t ncell = int64_t(g.D) * g.H * g.W;
+  unsigned* go = counter + 1;   // second word of the barrier block: last step every block may leave
+  for (int s = 0; s < a.nsteps; ++s) {
+    const int si = a.cur ^ (s & 1), di = si ^ 1;
+    const float* src = a.buf[si];
+    float* dst = a.buf[di];
+    float* plo = a.peer_lo[di];
+    float* phi = a.peer_hi[di];
+    bool wrote_peer = false;
+    for (int64_t cell = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; cell < ncell;
+         cell += int64_t(gridDim.x) * blockDim.x) {
+      const CellOffsets<3> o = cell_offsets<3>(g, cell);
+      const Cross<float, 3> U = gather_cg<float, 3>(src, o);
+      const Cross<float, 3> V = gather_cg<float, 3>(src + g.field, o);
+      float ou, ov;
+      pi_k1_fwd_poly<float>(U.c, V.c, lap_apply<float, 3>(U, P), lap_apply<float, 3>(V, P), P, ou, ov);
+      dst[o.c] = ou;
+      dst[g.field + o.c] = ov;
+      const int z = int(cell / g.plane);
+      if (z < 2) {                      // -> the lower neighbour's upper ghost planes D+2, D+3
+        const int64_t m = o.c + int64_t(g.D) * g.plane;
+        plo[m] = ou;
+        plo[g.field + m] = ov;
+        wrote_peer = true;
+      }
+      if (z >= g.D - 2) {               // -> the upper neighbour's lower ghost planes 0, 1
+        const int64_t m = o.c - int64_t(g.D) * g.plane;
+        phi[m] = ou;
+        phi[g.field + m] = ov;
+        wrote_peer = true;
+      }
+    }
+    if (wrote_peer) __threadfence_system();
+    // ---- grid barrier + halo hand-shake ----
+    const unsigned target = unsigned(s + 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(counter, 1u);
+      if (blockIdx.x == 0) {
+        unsigned v;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while (v < target * gridDim.x);
+        // one system-scope fence orders every block's (already fenced) peer stores before both flags; the flags
+        // themselves and the polling loads are relaxed, an acquire fence follows the poll: two NVLink round trips
+        // less than release-store + acquire-load per neighbour
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
+        const uint32_t e = a.epoch0 + uint32_t(s) + 1u;
+        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.post_lo_flag), "r"(e) : "memory");
+        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.post_hi_flag), "r"(e) : "memory");
+        for (uint32_t spins = 0;; ++spins) {
+          uint32_t w0, w1;
+          asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(w0) : "l"(a.my_flags + 0) : "memory");
+          asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(w1) : "l"(a.my_flags + 1) : "memory");
+          if (int32_t(w0 - e) >= 0 && int32_t(w1 - e) >= 0) break;
+          if (spins >= a.spin_limit) {   // a lost neighbour must not hang the GPU, nor may the rollout go on
+            atomicExch(a.err, 1u);
+            __threadfence_system();
+            __trap();
+          }
+        }
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(go), "r"(target) : "memory");
+      } else {
+        unsigned v;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(go) : "memory");
+        } while (v < target);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace percnn
+
+// =====================================================================================================
 // Persistent multi-step ADJOINT for small grids: the backward twin of k_multi_step.  A training step on the 2-D
 // configs (and the reference's own 100^2 / 48^3 grids) is bound by one launch + one 22-value grid reduction per
 // time step (measured: 11 us per step at 128^2 fp64, of which the stencil is ~2 us).  Here ONE cooperative launch

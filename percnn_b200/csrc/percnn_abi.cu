@@ -106,6 +106,7 @@ const void* multi_step_kernel(const percnn_plan* p) {
 // set stays in L2 and a per-step launch would be latency-bound.  Larger non-TMA plans (fp64 3-D, W % 128 != 0)
 // run one generic kernel per step.
 constexpr size_t kMultiStepMaxStateBytes = size_t(40) << 20;
+constexpr size_t kSmallSlabBytes = size_t(6) << 20;   // per-rank state (incl. ghosts) below which a slab rollout runs persistently
 bool multi_step_eligible(const percnn_plan* p) {
   if (p->use_tma || is_k5(p) || p->desc.slab_ghost) return false;
   if (state_bytes(p) > kMultiStepMaxStateBytes) return false;
@@ -399,6 +400,14 @@ int percnn_plan_create(const percnn_desc_t* d, percnn_plan_t** out) {
           cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bfn, kMultiThreads, 0) == cudaSuccess && per_sm > 0)
         p->multi_bwd_grid = p->sm_count;
     }
+    if (d->slab_ghost && d->cell == PERCNN_CELL_PI && d->ksize == 1 && d->ndim == 3 && d->dtype == PERCNN_F32 &&
+        !(d->flags & PERCNN_FLAG_EVAL_BRANCH) && !getenv("PERCNN_NO_MULTISTEP")) {
+      int coop = 0, per_sm = 0;
+      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, d->device);
+      if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_multi_step_slab, kMultiThreads, 0) == cudaSuccess &&
+          per_sm > 0 && cudaMalloc(&p->d_sync, 256) == cudaSuccess)
+        p->multi_slab_grid = p->sm_count;
+    }
     p->use_tma = d->cell == PERCNN_CELL_PI && d->ksize == 1 && d->ndim == 3 && d->dtype == PERCNN_F32 &&
                  !(d->flags & (PERCNN_FLAG_NO_TMA | PERCNN_FLAG_EVAL_BRANCH)) && g.W % 128 == 0 &&
                  g.H >= 4 && g.D >= 4;
@@ -439,6 +448,9 @@ int64_t percnn_param_count(const percnn_plan_t* p) { return p ? p->nparams : -1;
 int64_t percnn_state_elems(const percnn_plan_t* p) { return p ? p->state_elems : -1; }
 int percnn_plan_uses_tma(const percnn_plan_t* p) { return p && p->use_tma ? 1 : 0; }
 int64_t percnn_plan_launch_count(const percnn_plan_t* p) { return p ? p->launches : -1; }
+int percnn_plan_slab_persistent(const percnn_plan_t* p) {
+  return p && p->multi_slab_grid > 0 && state_bytes(p) <= kSmallSlabBytes && !getenv("PERCNN_SLAB_NO_PERSISTENT") ? 1 : 0;
+}
 
 size_t percnn_workspace_bytes(const percnn_plan_t* p, int nsteps) {
   (void)nsteps;
@@ -504,7 +516,42 @@ int percnn_slab_rollout_fwd(percnn_plan_t* p, const percnn_slab_ring_t* ring, in
                             void* stream) {
   if (!p || !ring) return fail(PERCNN_ERR_INVALID, "null argument");
   if (nsteps < 0 || (cur != 0 && cur != 1)) return fail(PERCNN_ERR_INVALID, "bad nsteps / cur");
+  if (!ring->buf[0] || !ring->buf[1]) return fail(PERCNN_ERR_INVALID, "incomplete slab ring");
   DeviceGuard guard(p->desc.device);
+  // Small slabs (a few microseconds of work per step): the whole rollout as ONE persistent cooperative kernel whose
+  // grid barrier is also the halo hand-shake (k_multi_step_slab); the per-step kernels pay a kernel boundary plus
+  // the NVLink flag latency per step, which such slabs cannot hide.
+  if (nsteps >= 2 && percnn_plan_slab_persistent(p)) {
+    if (!ring->peer_lo_buf[0] || !ring->peer_lo_buf[1] || !ring->peer_hi_buf[0] || !ring->peer_hi_buf[1] || !ring->my_flags ||
+        !ring->peer_lo_flags || !ring->peer_hi_flags || !ring->scratch)
+      return fail(PERCNN_ERR_INVALID, "incomplete slab ring");
+    SlabMultiArgs a;
+    for (int i = 0; i < 2; ++i) {
+      a.buf[i] = static_cast<float*>(ring->buf[i]);
+      a.peer_lo[i] = static_cast<float*>(ring->peer_lo_buf[i]);
+      a.peer_hi[i] = static_cast<float*>(ring->peer_hi_buf[i]);
+    }
+    a.my_flags = ring->my_flags;
+    a.post_lo_flag = ring->peer_lo_flags + 1;
+    a.post_hi_flag = ring->peer_hi_flags + 0;
+    a.err = ring->scratch + 1;
+    a.epoch0 = epoch;
+    a.spin_limit = p->flag_spin_limit;
+    a.nsteps = nsteps;
+    a.cur = cur;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    PERCNN_CUDA(cudaMemsetAsync(p->d_sync, 0, 8, st));
+    Geom g = p->g;
+    int slot = p->slot;
+    unsigned* counter = p->d_sync;
+    void* args[] = {&g, &slot, &a, &counter};
+    const int64_t ncell = int64_t(g.D) * g.H * g.W;
+    int grid = int((ncell + kMultiThreads - 1) / kMultiThreads);
+    if (grid > p->multi_slab_grid) grid = p->multi_slab_grid;
+    PERCNN_CUDA(cudaLaunchCooperativeKernel((const void*)k_multi_step_slab, dim3(grid), dim3(kMultiThreads), args, 0, st));
+    p->launches++;
+    return PERCNN_OK;
+  }
   for (int s = 0; s < nsteps; ++s) {
     const int src = cur ^ (s & 1), dst = src ^ 1;
     percnn_slab_link_t link;
@@ -521,7 +568,6 @@ int percnn_slab_rollout_fwd(percnn_plan_t* p, const percnn_slab_ring_t* ring, in
     SlabLink l;
     int rc = resolve_link(p, &link, &l);
     if (rc) return rc;
-    if (!ring->buf[0] || !ring->buf[1]) return fail(PERCNN_ERR_INVALID, "incomplete slab ring");
     rc = tma_fwd_launch(p, static_cast<const float*>(ring->buf[src]), static_cast<float*>(ring->buf[dst]), 0, p->g.D,
                         static_cast<cudaStream_t>(stream), &l);
     if (rc) return rc;

@@ -74,6 +74,7 @@ struct percnn_plan {
   unsigned* d_sync = nullptr;   // grid-barrier counter of the persistent multi-step kernels
   int multi_grid = 0;           // co-resident grid size of that kernel (0 = not available)
   int multi_bwd_grid = 0;       // same for the persistent adjoint kernel
+  int multi_slab_grid = 0;      // slab plans: co-resident grid of the persistent small-slab rollout kernel
   bool pdl = true;   // programmatic dependent launch between consecutive step kernels (PERCNN_NO_PDL=1 disables)
   int tz_override = 0, grid_override = 0;   // experiment knobs (PERCNN_TMA_TY / _TZ / _GRID environment variables)
   uint32_t flag_spin_limit = 1u << 26;      // PERCNN_FLAG_SPINS: spins before a fused-halo wait traps (tests shorten it)

@@ -113,6 +113,11 @@ class Plan:
         return (2, *s)
 
     @property
+    def slab_persistent(self) -> bool:
+        """Slab plans: rollouts of >= 2 steps run as one persistent cooperative kernel (small slabs)."""
+        return bool(self._L.percnn_plan_slab_persistent(self._h))
+
+    @property
     def launch_count(self) -> int:
         return int(self._L.percnn_plan_launch_count(self._h))
 

@@ -33,8 +33,12 @@ cell.load_state_dict(load_gs3d_weights())
 cell = cell.to(dev)
 slab = halo.SlabRollout(cell, shape, dev, rank, world, transport=a.transport)
 full = synthetic_state(shape, 0, shape[0], dev, torch.float32, seed=3)       # every rank builds the same global field
+from percnn_b200 import _lib  # noqa: E402
 with torch.no_grad():
+    if a.transport == "fused" and slab.plan.slab_persistent and a.steps >= 2:
+        cell._flags = _lib.FLAG_NO_TMA       # small slabs: persistent kernel = the gather kernel's arithmetic
     ref = cell.rollout(full[None], a.steps)[-1]
+    cell._flags = 0
 ok, err = True, 0.0
 for rep in range(a.repeat):
     slab.set_state(full[:, slab.z0:slab.z0 + slab.nz])

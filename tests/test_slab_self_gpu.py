@@ -5,7 +5,7 @@ the one-GPU test box; results must equal the periodic single-GPU kernels bit for
 import pytest
 import torch
 
-from percnn_b200 import engine, halo
+from percnn_b200 import _lib, engine, halo
 from tests.helpers import load_weights, make_cell
 
 pytestmark = pytest.mark.gpu
@@ -31,7 +31,15 @@ def test_self_ring_forward_is_bitwise_equal_to_periodic_kernel(shape, steps):
     slab = halo.SlabRollout(cell, shape, DEV, 0, 1, transport="fused")
     assert slab.transport == "fused"
     with torch.no_grad():
-        ref = cell.rollout(h0[None], steps)[-1]
+        tma_ref = cell.rollout(h0[None], steps)[-1]
+        ref = tma_ref
+        if slab.plan.slab_persistent:
+            # small slabs run the whole rollout as one persistent kernel built on the gather kernel: bit-identical
+            # to the single-GPU gather kernel, and within rounding of the TMA z-march
+            cell._flags = _lib.FLAG_NO_TMA
+            ref = cell.rollout(h0[None], steps)[-1]
+            cell._flags = 0
+            assert float((ref - tma_ref).abs().max() / tma_ref.abs().max()) <= 2e-6
     for rep in range(2):                       # the second run starts on the other march direction when steps is odd
         slab.set_state(h0)
         slab.run(steps)
