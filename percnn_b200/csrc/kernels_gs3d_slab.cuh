@@ -48,24 +48,18 @@ constexpr int SLAB_PRODUCER_REGS = PERCNN_EXP_PRODUCER_REGS;
 __device__ __forceinline__ void red_release_sys_max(uint32_t* p, uint32_t v) {
   asm volatile("red.release.sys.global.max.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// ---- the helper's tensor maps: every buffer once more with a box of one field's boundary PAIR ----
-// box = {128 cells, ty rows, 2 planes, 1 field}: one TMA load brings a field's pair of this tile into shared
-// memory, one TMA store sends it to the neighbour.  (Per-row bulk copies without a tensor map -- 56 loads + 56
-// stores per pair issued by one lane -- took longer than the register copy they replaced: 20-30 us per step.)
+// ---- the helper's tensor maps: my two buffers once more with a box of one field's boundary PAIR ----
+// box = {128 cells, ty rows, 2 planes, 1 field}: one TMA load brings a field's pair of this tile from the local
+// buffer (L2-resident, just written) into shared memory; the helper warp then sends it to the neighbour with plain
+// 128-bit stores through the peer mapping.  Measured alternatives (2 GPUs, 64 planes of 512^2 per rank, 52 us of
+// compute per step): TMA *stores* to the peer (cp.async.bulk.tensor ... bulk_group + wait_group) stretched every
+// step by 11 us -- the kernel cannot end before the NVLink writes of its bulk group have been acknowledged, and
+// they trickle; per-row bulk copies without a tensor map (56 + 56 instructions per pair from one lane) and a
+// register copy straight from global memory (two loads in flight per lane) both took 20-30 us per step.
 struct alignas(64) SlabMaps {
-  CUtensorMap src;          // my input buffer   (deferred pair of the previous step)
-  CUtensorMap dst;          // my output buffer  (early and late pair of this step)
-  CUtensorMap peer_e_src;   // early-side neighbour's buffer matching `src`
-  CUtensorMap peer_e_dst;   // early-side neighbour's buffer matching `dst`
-  CUtensorMap peer_l_dst;   // late-side neighbour's buffer matching `dst`
+  CUtensorMap src;   // my input buffer   (deferred pair of the previous step)
+  CUtensorMap dst;   // my output buffer  (early and late pair of this step)
 };
-
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(map)),
-               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
 
 // Staging area of the halo helper in shared memory (behind the ring and its barriers): one mbarrier + NBUF
 // field-pairs of 2 x ty x 128 floats.  The forward kernel stages both fields at once, the adjoint (less shared
@@ -75,75 +69,94 @@ constexpr int SLAB_STAGE_OFF = SLAB_HELPER_OFF + 128;
 constexpr int SLAB_FIELD_PAIR_BYTES = 2 * SLAB_MAX_TY * TX * 4;           // capacity per staged field-pair (ty = 14)
 constexpr int SMEM_BYTES_SLAB = SLAB_STAGE_OFF + 2 * SLAB_FIELD_PAIR_BYTES;
 
-// Move one boundary pair of this tile from a local buffer into a neighbour's ghost planes.
-//   from_plane / to_plane: buffer plane index of the pair's first plane in the local / peer buffer
+// Move one boundary pair of this tile from a local buffer into a neighbour's ghost planes (whole helper warp).
+//   from_plane: buffer plane index of the pair's first plane in the local buffer (tensor map `from`)
+//   to        : the pair's first plane in the peer buffer at this tile's (y0, x0), this lane's quad; `field` /
+//               `plane` / W are the peer buffer's strides (same layout as mine)
 template <int NBUF>
-__device__ __forceinline__ void slab_copy_pair(const CUtensorMap* from, int from_plane, const CUtensorMap* to, int to_plane,
-                                               int x0, int y0, int ty, uint64_t* bar, float* stage, uint32_t& phase) {
+__device__ __forceinline__ void slab_copy_pair(const CUtensorMap* from, int from_plane, float* __restrict__ to, int64_t field,
+                                               int64_t plane, int W, int x0, int y0, int ty, int lane, uint64_t* bar,
+                                               float* stage, uint32_t& phase, int debug) {
+  if (debug & 8) return;   // timing experiment: no copies
   const uint32_t bytes = 2u * uint32_t(ty) * TX * 4u;   // one field's pair as it lands in shared memory
 #pragma unroll
   for (int f0 = 0; f0 < 2; f0 += NBUF) {
-    mbar_expect_tx(bar, NBUF * bytes);
+    if (lane == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the staging rows were last read through the generic proxy
+      mbar_expect_tx(bar, NBUF * bytes);
 #pragma unroll
-    for (int i = 0; i < NBUF; ++i) tma_load_4d(stage + i * (SLAB_FIELD_PAIR_BYTES / 4), from, bar, x0, y0, from_plane, f0 + i);
+      for (int i = 0; i < NBUF; ++i) tma_load_4d(stage + i * (SLAB_FIELD_PAIR_BYTES / 4), from, bar, x0, y0, from_plane, f0 + i);
+    }
     mbar_wait(bar, phase);
     phase ^= 1u;
+    if (!(debug & 32)) {
 #pragma unroll
-    for (int i = 0; i < NBUF; ++i) tma_store_4d(to, stage + i * (SLAB_FIELD_PAIR_BYTES / 4), x0, y0, to_plane, f0 + i);
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // writes complete (and the staging area reusable)
+      for (int i = 0; i < NBUF; ++i) {
+        const float* sp = stage + i * (SLAB_FIELD_PAIR_BYTES / 4) + 4 * lane;
+        float* gp = to + int64_t(f0 + i) * field;
+        for (int pl = 0; pl < 2; ++pl)
+#pragma unroll 2
+          for (int r = 0; r < ty; ++r)
+            *reinterpret_cast<float4*>(gp + int64_t(pl) * plane + int64_t(r) * W) = lds128(sp + (pl * ty + r) * TX);
+      }
+    }
+    __syncwarp();
   }
 }
 
-// The elected lane's bulk stores have completed: make them visible system-wide, count this tile, and let the
-// last tile raise the neighbour's flag.
-__device__ __forceinline__ void slab_publish(uint32_t* counter, uint32_t* flag, uint32_t epoch, int ntiles) {
-  asm volatile("fence.proxy.async.global;" ::: "memory");
+// Every lane of the helper warp has issued its peer stores: each lane makes its own visible system-wide (round 1: a
+// single thread's fence did not cover other threads' in-flight NVLink stores), then the warp counts this tile and
+// the last tile raises the neighbour's flag.
+__device__ __forceinline__ void slab_publish(int lane, uint32_t* counter, uint32_t* flag, uint32_t epoch, int ntiles, int debug) {
+  if (debug & 16) return;   // timing experiment: no fences / atomics / flag
   __threadfence_system();
-  const unsigned old = atomicAdd(counter, 1u);
-  if (old == unsigned(ntiles) - 1u) {
-    atomicExch(counter, 0u);
-    __threadfence_system();
-    red_release_sys_max(flag, epoch);
+  __syncwarp();
+  if (lane == 0) {
+    const unsigned old = atomicAdd(counter, 1u);
+    if (old == unsigned(ntiles) - 1u) {
+      atomicExch(counter, 0u);
+      __threadfence_system();
+      red_release_sys_max(flag, epoch);
+    }
   }
 }
 
-// The helper warp's whole job for one kernel (shared by the forward and the adjoint slab kernels).  All 32 lanes
-// take part in the named barriers; lane 0 does the copying.
+// The helper warp's whole job for one kernel (shared by the forward and the adjoint slab kernels).
 template <bool DOWN, int NBUF>
 __device__ __forceinline__ void slab_helper(const Params& p, const SlabMaps& m, int lane, int nitems, uint64_t* bar, float* stage) {
   const int ntiles = p.nxt * p.nyt;
   const int nbar = (p.ty + 1) * 32;
+  const int64_t plane = int64_t(p.H) * p.W;
   // side 0: lower neighbour (my buffer planes 2,3 -> its ghost planes D+2,D+3); side 1: upper neighbour (my buffer
   // planes D,D+1 -> its ghost planes 0,1).  Buffer plane = interior plane + 2.
   constexpr int early = DOWN ? 1 : 0, late = DOWN ? 0 : 1;
   const int from_e = early == 0 ? 2 : p.D, to_e = early == 0 ? p.D + 2 : 0;
   const int from_l = late == 0 ? 2 : p.D, to_l = late == 0 ? p.D + 2 : 0;
+  float* const peer_e_src = early == 0 ? p.peer_lo_src : p.peer_hi_src;
+  float* const peer_e_dst = early == 0 ? p.peer_lo_dst : p.peer_hi_dst;
+  float* const peer_l_dst = late == 0 ? p.peer_lo_dst : p.peer_hi_dst;
   uint32_t phase = 0;
-  if (lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&m.dst)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&m.peer_e_dst)) : "memory");
-  }
+  if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&m.dst)) : "memory");
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
     const ItemCoord ic = decode_item(p, item);
     const bool own[2] = {ic.z0 == 0, ic.z0 + ic.nz == p.D};
+    const int64_t off = int64_t(ic.y0) * p.W + ic.x0 + 4 * lane;
     if (own[early]) {
-      if (p.flush_prev && lane == 0)   // the previous step left this pair (its LAST one) in what is now my input buffer
-        slab_copy_pair<NBUF>(&m.src, from_e, &m.peer_e_src, to_e, ic.x0, ic.y0, p.ty, bar, stage, phase);
+      if (p.flush_prev)   // the previous step left this pair (its LAST one) in what is now my input buffer
+        slab_copy_pair<NBUF>(&m.src, from_e, peer_e_src + int64_t(to_e) * plane + off, p.src_field, plane, p.W, ic.x0, ic.y0,
+                             p.ty, lane, bar, stage, phase, p.debug);
       asm volatile("bar.sync 1, %0;" ::"r"(nbar) : "memory");   // the consumers have stored the pair ...
-      if (lane == 0) {
-        asm volatile("fence.proxy.async.global;" ::: "memory");  // ... through the generic proxy; TMA reads it through the async one
-        slab_copy_pair<NBUF>(&m.dst, from_e, &m.peer_e_dst, to_e, ic.x0, ic.y0, p.ty, bar, stage, phase);
-        slab_publish(p.scratch + (early == 0 ? 0 : 2), early == 0 ? p.post_lo_flag : p.post_hi_flag, p.epoch_post, ntiles);
-      }
+      if (lane == 0) asm volatile("fence.proxy.async.global;" ::: "memory");   // ... through the generic proxy; TMA reads it through the async one
+      slab_copy_pair<NBUF>(&m.dst, from_e, peer_e_dst + int64_t(to_e) * plane + off, p.dst_field, plane, p.W, ic.x0, ic.y0, p.ty,
+                           lane, bar, stage, phase, p.debug);
+      slab_publish(lane, p.scratch + (early == 0 ? 0 : 2), early == 0 ? p.post_lo_flag : p.post_hi_flag, p.epoch_post, ntiles, p.debug);
     }
     if (own[late] && !p.defer_late) {
       asm volatile("bar.sync 2, %0;" ::"r"(nbar) : "memory");
-      if (lane == 0) {
-        asm volatile("fence.proxy.async.global;" ::: "memory");
-        slab_copy_pair<NBUF>(&m.dst, from_l, &m.peer_l_dst, to_l, ic.x0, ic.y0, p.ty, bar, stage, phase);
-        slab_publish(p.scratch + (late == 0 ? 0 : 2), late == 0 ? p.post_lo_flag : p.post_hi_flag, p.epoch_post, ntiles);
-      }
+      if (lane == 0) asm volatile("fence.proxy.async.global;" ::: "memory");
+      slab_copy_pair<NBUF>(&m.dst, from_l, peer_l_dst + int64_t(to_l) * plane + off, p.dst_field, plane, p.W, ic.x0, ic.y0, p.ty,
+                           lane, bar, stage, phase, p.debug);
+      slab_publish(lane, p.scratch + (late == 0 ? 0 : 2), late == 0 ? p.post_lo_flag : p.post_hi_flag, p.epoch_post, ntiles, p.debug);
     }
   }
 }

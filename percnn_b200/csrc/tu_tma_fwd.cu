@@ -104,16 +104,13 @@ int get_pair_map(percnn_plan* p, const void* base, CUtensorMap* out) {
   return PERCNN_OK;
 }
 
-// The halo helper's five tensor maps for one fused step (see tma3d::SlabMaps).
+// The halo helper's tensor maps for one fused step (see tma3d::SlabMaps).
 int slab_fill_maps(percnn_plan* p, const SlabLink* link, const float* src, float* dst, bool down, tma3d::SlabMaps* sm) {
+  (void)link;
+  (void)down;
   int rc = get_pair_map(p, dst, &sm->dst);
   if (!rc) rc = get_pair_map(p, src, &sm->src);
-  if (!rc) rc = get_pair_map(p, down ? link->peer_hi_dst : link->peer_lo_dst, &sm->peer_e_dst);
-  if (!rc) rc = get_pair_map(p, down ? link->peer_lo_dst : link->peer_hi_dst, &sm->peer_l_dst);
-  if (rc) return rc;
-  if (link->flush_prev) return get_pair_map(p, down ? link->peer_hi_src : link->peer_lo_src, &sm->peer_e_src);
-  sm->peer_e_src = sm->peer_e_dst;   // never used without FLUSH_PREV; keep it a valid map
-  return PERCNN_OK;
+  return rc;
 }
 
 cudaError_t tma_fwd_load_prep(const PrepBlock* d_prep, int slot, cudaStream_t st) {
