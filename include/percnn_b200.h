@@ -102,6 +102,9 @@ int64_t percnn_state_elems(const percnn_plan_t* plan);
 size_t percnn_workspace_bytes(const percnn_plan_t* plan, int nsteps);
 /* 1 if the plan runs the TMA z-marching kernel, 0 if the generic one (introspection for tests/bench). */
 int percnn_plan_uses_tma(const percnn_plan_t* plan);
+/* > 0 if rollouts of this (2-D) plan run on shared-memory tiles with temporal blocking: the number of time steps
+ * per pass (one grid barrier per pass); 0 if the gather kernels serve it. */
+int percnn_plan_uses_tile2d(const percnn_plan_t* plan);
 /* Kernel launches issued by this plan since creation (bench "gpu_launches"). */
 int64_t percnn_plan_launch_count(const percnn_plan_t* plan);
 /* 1 if percnn_slab_rollout_fwd runs this (slab-mode) plan's rollouts of >= 2 steps as ONE persistent cooperative kernel

@@ -413,7 +413,7 @@ struct SlabMultiArgs {
   int cur;                    // step s reads buf[cur ^ (s & 1)]
 };
 
-__global__ void __launch_bounds__(kMultiThreads) k_multi_step_slab(Geom g, int slot, SlabMultiArgs a, unsigned* counter) {
+static __global__ void __launch_bounds__(kMultiThreads) k_multi_step_slab(Geom g, int slot, SlabMultiArgs a, unsigned* counter) {
   const float* P = PrepView<float>::get(c_prep[slot]);
   const int64_t ncell = int64_t(g.D) * g.H * g.W;
   unsigned* go = counter + 1;   // second word of the barrier block: last step every block may leave

@@ -416,6 +416,10 @@ int percnn_plan_create(const percnn_desc_t* d, percnn_plan_t** out) {
       if (!rc) rc = tma_bwd_setup(p);
       if (rc) break;
     }
+    if (tile2d_eligible(p)) {
+      rc = tile2d_setup(p);
+      if (rc) break;
+    }
   } while (0);
   if (rc != PERCNN_OK) {
     std::string keep = g_err;
@@ -448,6 +452,7 @@ int64_t percnn_param_count(const percnn_plan_t* p) { return p ? p->nparams : -1;
 int64_t percnn_state_elems(const percnn_plan_t* p) { return p ? p->state_elems : -1; }
 int percnn_plan_uses_tma(const percnn_plan_t* p) { return p && p->use_tma ? 1 : 0; }
 int64_t percnn_plan_launch_count(const percnn_plan_t* p) { return p ? p->launches : -1; }
+int percnn_plan_uses_tile2d(const percnn_plan_t* p) { return p && p->use_tile2d ? p->t2_K : 0; }
 int percnn_plan_slab_persistent(const percnn_plan_t* p) {
   return p && p->multi_slab_grid > 0 && state_bytes(p) <= kSmallSlabBytes && !getenv("PERCNN_SLAB_NO_PERSISTENT") ? 1 : 0;
 }
@@ -475,6 +480,7 @@ int percnn_params_load(percnn_plan_t* p, const void* params, void* stream) {
     PERCNN_CUDA(tma_bwd_load_prep(p->d_prep, p->slot, st));
   }
   if (is_k5(p)) PERCNN_CUDA(k5_load_prep(p->d_prep, p->slot, st));
+  if (p->use_tile2d) PERCNN_CUDA(tile2d_load_prep(p->d_prep, p->slot, st));
   p->launches++;
   return PERCNN_OK;
 }
@@ -799,6 +805,14 @@ int percnn_rollout_fwd(percnn_plan_t* p, const void* h0, void* traj, const uint8
     pp[1] = pp[0] + (sb + 255) / 256 * 256;
   }
   if (tp && tp != h0) PERCNN_CUDA(cudaMemcpyAsync(tp, h0, sb, cudaMemcpyDeviceToDevice, st));
+  // 2-D cells: the whole rollout on shared-memory tiles, K time steps per pass, one launch (tape, emitted frames and/or
+  // the final state)
+  if (nsteps >= 2 && nsteps <= 4096 && p->use_tile2d && !(tp && traj) && (tp || pp[0]) && (tp || traj || h_final)) {
+    int rc = tile2d_rollout(p, tp ? tp : h0, tp ? nullptr : h_final, tp, traj, emit, pp[0], pp[1], nsteps, st);
+    if (rc) return rc;
+    if (tp && h_final) PERCNN_CUDA(cudaMemcpyAsync(h_final, tp + size_t(nsteps) * sb, sb, cudaMemcpyDeviceToDevice, st));
+    return PERCNN_OK;
+  }
   // small grids: one persistent cooperative launch for the whole rollout (tape mode, or final-state-only mode)
   if (nsteps >= 2 && multi_step_eligible(p) && !traj && (tp || (h_final && pp[0]))) {
     int rc = p->elt == 4 ? launch_multi_step<float>(p, h0, tp, pp[0], pp[1], h_final, nsteps, st)

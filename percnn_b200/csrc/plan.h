@@ -70,6 +70,7 @@ struct percnn_plan {
   int64_t launches = 0;
   bool use_tma = false;
   bool use_tile2d = false;      // 2-D shared-memory tiled kernels with temporal blocking (kernels_tile2d.cuh)
+  int t2_K = 0, t2_TH = 0, t2_TW = 0, t2_hy = 0, t2_hx = 0, t2_nty = 0, t2_ntx = 0, t2_smem = 0;
   int ty = 16, tz = 0;
   unsigned* d_sync = nullptr;   // grid-barrier counter of the persistent multi-step kernels
   int multi_grid = 0;           // co-resident grid size of that kernel (0 = not available)
@@ -148,10 +149,11 @@ int k5_grads_finish(percnn_plan* p, const float* params, const double* acc, floa
 cudaError_t tile2d_load_prep(const PrepBlock* d_prep, int slot, cudaStream_t st);
 bool tile2d_eligible(const percnn_plan* p);
 int tile2d_setup(percnn_plan* p);
-// Advances `nsteps` steps from src.  tape != nullptr: state s+1 is written to tape + (s+1) * stride for every step
-// (src must be tape slot 0); otherwise only the final state is written to dst (ping/pong are scratch states).
-int tile2d_rollout(percnn_plan* p, const void* src, void* dst, void* tape, void* ping, void* pong, int nsteps,
-                   cudaStream_t st);
+// Advances `nsteps` (>= 1, <= 4096) steps from h0 in ONE cooperative launch.  tape != nullptr: every state s+1 goes to
+// tape + (s+1) * state_elems (tape slot 0 must hold h0).  Otherwise: emitted states (emit[s] != 0, traj != nullptr) go to
+// consecutive traj slots, the last state to final_state (nullable only with a tape); ping / pong are scratch states.
+int tile2d_rollout(percnn_plan* p, const void* h0, void* final_state, void* tape, void* traj, const uint8_t* emit, void* ping,
+                   void* pong, int nsteps, cudaStream_t st);
 
 // ---- shared TMA host helpers (tma_host.cpp part of tu_tma_fwd.cu) ----
 struct TmaTiling {

@@ -113,6 +113,11 @@ class Plan:
         return (2, *s)
 
     @property
+    def tile2d_steps_per_pass(self) -> int:
+        """> 0: 2-D rollouts run on shared-memory tiles, this many time steps per pass; 0: gather kernels."""
+        return int(self._L.percnn_plan_uses_tile2d(self._h))
+
+    @property
     def slab_persistent(self) -> bool:
         """Slab plans: rollouts of >= 2 steps run as one persistent cooperative kernel (small slabs)."""
         return bool(self._L.percnn_plan_slab_persistent(self._h))
