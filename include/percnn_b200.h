@@ -122,6 +122,10 @@ int percnn_params_load(percnn_plan_t* plan, const void* params, void* stream);
 /* ---- one time step ---------------------------------------------------------------------------- */
 /* RCNNCell.forward (GS2D:105-121 and siblings): h_out = h_in + dt * (alpha * Lap(h_in) + Pi(h_in)). */
 int percnn_step_fwd(percnn_plan_t* plan, const void* h_in, void* h_out, void* stream);
+/* RCNNCell.forward_rk4 (BUR3:159-206, LO3:153-200; defined by the Stage-3 scripts, never called by them): one
+ * classical RK4 step h_out = h + dt (k1 + 2 k2 + 2 k3 + k4) / 6 of the physics cell's f_rhs, as four launches of the
+ * fused right-hand side (the intermediate states h + a k are formed on the fly).  `ws`: percnn_workspace_bytes. */
+int percnn_step_rk4(percnn_plan_t* plan, const void* h_in, void* h_out, void* ws, void* stream);
 /* Same step restricted to interior planes [z_lo, z_hi) of the slowest axis (3-D TMA plans only).  Lets the
  * slab-mode driver launch the planes that do not touch ghost cells before the halo exchange lands. */
 int percnn_step_fwd_range(percnn_plan_t* plan, const void* h_in, void* h_out, int z_lo, int z_hi, void* stream);

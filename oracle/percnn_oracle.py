@@ -223,15 +223,11 @@ def _circ_conv2d(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     return F.conv2d(F.pad(x, (2, 2, 2, 2), mode="circular"), w)
 
 
-def phys_cell_step_torch(h: torch.Tensor, p: Dict[str, torch.Tensor], v: Variant) -> torch.Tensor:
-    """One Euler step of a Stage-3 physics cell: `f_rhs` + `forward`.
-
-    Burgers BUR3:154-157,209-221; lambda-omega LO3:148-151,203-215.  The derivative filters hold
-    the un-scaled taps and the result is divided by `resol` afterwards (BUR3:78-80).
-    """
-    dt_ = h.dtype
+def phys_rhs_torch(u: torch.Tensor, vv: torch.Tensor, p: Dict[str, torch.Tensor], v: Variant):
+    """`f_rhs` of a Stage-3 physics cell: Burgers BUR3:154-157, lambda-omega LO3:148-151.  The derivative filters
+    hold the un-scaled taps and the result is divided by `resol` afterwards (BUR3:78-80)."""
+    dt_ = u.dtype
     lap_w = torch.tensor(laplace_stencil(2), dtype=dt_)
-    u, vv = h[:, 0:1], h[:, 1:2]
     lap = lambda x: _circ_conv2d(x, lap_w) / (v.dx ** 2)
     if v.kind == "burgers":
         dxw = torch.tensor(dx_stencil_2d(), dtype=dt_)
@@ -247,7 +243,26 @@ def phys_cell_step_torch(h: torch.Tensor, p: Dict[str, torch.Tensor], v: Variant
                + p["C4_v"] * u * vv ** 2 + p["C5_v"] * vv ** 3)
         if "C6_v" in p:
             f_v = f_v + p["C6_v"] * u
+    return f_u, f_v
+
+
+def phys_cell_step_torch(h: torch.Tensor, p: Dict[str, torch.Tensor], v: Variant) -> torch.Tensor:
+    """One Euler step of a Stage-3 physics cell: `f_rhs` + `forward` (BUR3:209-221, LO3:203-215)."""
+    u, vv = h[:, 0:1], h[:, 1:2]
+    f_u, f_v = phys_rhs_torch(u, vv, p, v)
     return torch.cat((u + v.dt * f_u, vv + v.dt * f_v), dim=1)
+
+
+def rk4_step_torch(h: torch.Tensor, p: Dict[str, torch.Tensor], variant: str) -> torch.Tensor:
+    """`RCNNCell.forward_rk4` (BUR3:159-206, LO3:153-200): classical RK4 on `f_rhs`, same operation order."""
+    v = VARIANTS[variant]
+    u0, v0 = h[:, 0:1], h[:, 1:2]
+    k1u, k1v = phys_rhs_torch(u0, v0, p, v)
+    k2u, k2v = phys_rhs_torch(u0 + k1u * v.dt / 2.0, v0 + k1v * v.dt / 2.0, p, v)
+    k3u, k3v = phys_rhs_torch(u0 + k2u * v.dt / 2.0, v0 + k2v * v.dt / 2.0, p, v)
+    k4u, k4v = phys_rhs_torch(u0 + k3u * v.dt, v0 + k3v * v.dt, p, v)
+    return torch.cat((u0 + v.dt * (k1u + 2 * k2u + 2 * k3u + k4u) / 6.0,
+                      v0 + v.dt * (k1v + 2 * k2v + 2 * k3v + k4v) / 6.0), dim=1)
 
 
 def cell_step_torch(h: torch.Tensor, p: Dict[str, torch.Tensor], variant: str) -> torch.Tensor:

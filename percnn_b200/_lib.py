@@ -29,7 +29,7 @@ EXPORTS = (
     "percnn_param_grads_begin", "percnn_param_grads_finish", "percnn_rollout_fwd", "percnn_rollout_bwd",
     "percnn_rollout_fwd_host", "percnn_data_loss_fwd", "percnn_step_bwd_loss", "percnn_rollout_bwd_loss",
     "percnn_phys_loss_workspace_bytes", "percnn_phys_loss_fwd", "percnn_phys_loss_bwd",
-    "percnn_slab_rollout_fwd", "percnn_slab_rollout_tape", "percnn_slab_rollout_bwd", "percnn_plan_slab_persistent", "percnn_plan_uses_tile2d",
+    "percnn_slab_rollout_fwd", "percnn_slab_rollout_tape", "percnn_slab_rollout_bwd", "percnn_plan_slab_persistent", "percnn_plan_uses_tile2d", "percnn_step_rk4",
 )
 
 
@@ -110,6 +110,7 @@ def lib() -> ctypes.CDLL:
     L.percnn_plan_launch_count.restype = c_int64
     L.percnn_params_load.argtypes = [vp, vp, vp]
     L.percnn_step_fwd.argtypes = [vp, vp, vp, vp]
+    L.percnn_step_rk4.argtypes = [vp, vp, vp, vp, vp]
     L.percnn_step_fwd_range.argtypes = [vp, vp, vp, c_int, c_int, vp]
     L.percnn_step_fwd_fused_halo.argtypes = [vp, vp, vp, POINTER(SlabLink), vp]
     L.percnn_step_bwd_fused_halo.argtypes = [vp, vp, vp, vp, vp, vp, POINTER(SlabLink), vp]

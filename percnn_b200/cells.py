@@ -179,16 +179,50 @@ class PhysicsCell(_FusedCell):
         """Reference RHS through stock convs (off the hot path; the fused kernel implements the same)."""
         raise NotImplementedError
 
-    def forward_rk4(self, h):
-        """Classical RK4 on f_rhs (BUR3:159-206) -- defined by the reference but never called; stock ops."""
+    def _rk4_stock(self, h):
+        """The reference's formulation through stock ops (BUR3:159-206): only used to differentiate forward_rk4."""
         u0, v0 = h[:, 0:1, ...], h[:, 1:2, ...]
         k1u, k1v = self.f_rhs(u0, v0)
         k2u, k2v = self.f_rhs(u0 + k1u * self.dt / 2.0, v0 + k1v * self.dt / 2.0)
         k3u, k3v = self.f_rhs(u0 + k2u * self.dt / 2.0, v0 + k2v * self.dt / 2.0)
         k4u, k4v = self.f_rhs(u0 + k3u * self.dt, v0 + k3v * self.dt)
-        ch = torch.cat((u0 + self.dt * (k1u + 2 * k2u + 2 * k3u + k4u) / 6.0,
-                        v0 + self.dt * (k1v + 2 * k2v + 2 * k3v + k4v) / 6.0), dim=1)
+        return torch.cat((u0 + self.dt * (k1u + 2 * k2u + 2 * k3u + k4u) / 6.0,
+                          v0 + self.dt * (k1v + 2 * k2v + 2 * k3v + k4v) / 6.0), dim=1)
+
+    def forward_rk4(self, h):
+        """Classical RK4 on f_rhs (BUR3:159-206, LO3:153-200) -- defined by the reference, never called by its scripts.
+        Forward: four launches of the fused right-hand side (percnn_step_rk4).  Backward (no reference script trains
+        through it): autograd of the stock-op formulation, recomputed from the saved input."""
+        plan = self._plan(h)
+        ch = _RK4Step.apply(self, plan, h, *self._packed_tensors())
         return ch, ch
+
+
+class _RK4Step(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cell, plan, h, *params):
+        flat = engine.pack_params(params, plan.spec.dtype)
+        plan.params_load(flat)
+        out = torch.empty(plan.buffer_shape, dtype=plan.spec.dtype, device=h.device)
+        plan.step_rk4(h.detach()[0].contiguous(), out)
+        ctx.cell = cell
+        ctx.params = params
+        ctx.save_for_backward(h.detach())
+        return out[None]
+
+    @staticmethod
+    def backward(ctx, g):
+        (h,) = ctx.saved_tensors
+        cell = ctx.cell
+        wanted = [i for i, p in enumerate(ctx.params) if ctx.needs_input_grad[3 + i]]
+        with torch.enable_grad():
+            hh = h.clone().requires_grad_(True)
+            out = cell._rk4_stock(hh)
+            grads = torch.autograd.grad(out, [hh] + [ctx.params[i] for i in wanted], g, allow_unused=True)
+        pg = [None] * len(ctx.params)
+        for i, gr in zip(wanted, grads[1:]):
+            pg[i] = gr
+        return (None, None, grads[0] if ctx.needs_input_grad[2] else None, *pg)
 
 
 def data_loss_selection(step: int, effective_step, time_stride: int, first_frames: Optional[int] = None):

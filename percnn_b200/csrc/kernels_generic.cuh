@@ -301,6 +301,58 @@ __global__ void __launch_bounds__(kGenericThreads) k_lo_bwd(Geom g, int slot, co
   reduce_into_acc<T, kRedLO>(red, partials, counter, acc);
 }
 
+// ---- Stage-3 physics cells, classical RK4 step (forward_rk4, BUR3:159-206 / LO3: same) ------------------------
+// One launch per stage.  Stage i evaluates k_i = f_rhs(h + a * k_{i-1}) (the intermediate state is formed on the fly
+// for the whole cross neighbourhood, never stored), keeps k_i for the next stage and accumulates k1 + 2 k2 + 2 k3 in
+// `acc`; the last stage writes acc <- h + dt * (acc + k4) / 6 in the reference's operation order.  `acc` is the
+// caller's output buffer, so an RK4 step needs two state-sized scratch buffers (k ping-pong) instead of the ~12
+// full-size temporaries of the stock-op version.
+//   stage 0: kprev == nullptr, acc = k1;  stages 1, 2: acc += 2 k;  stage 3 (last): output.   CELL: 1 = Burgers, 2 = lambda-omega
+template <typename T, int CELL>
+__global__ void __launch_bounds__(kGenericThreads) k_rk4_stage(Geom g, int slot, const T* __restrict__ h, const T* __restrict__ kprev,
+                                                               T a, T* __restrict__ kout, T* __restrict__ acc, int stage) {
+  const T* P = PrepView<T>::get(c_prep[slot]);
+  const int64_t ncell = int64_t(g.H) * g.W;
+  for (int64_t cell = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; cell < ncell;
+       cell += int64_t(gridDim.x) * blockDim.x) {
+    const CellOffsets<2> o = cell_offsets<2>(g, cell);
+    Cross<T, 2> U = gather<T, 2>(h, o);
+    Cross<T, 2> V = gather<T, 2>(h + g.field, o);
+    const T u0 = U.c, v0 = V.c;
+    if (kprev != nullptr) {   // y = h + k * dt / 2  (BUR3:186-187; a = dt / 2 or dt)
+      const Cross<T, 2> KU = gather<T, 2>(kprev, o);
+      const Cross<T, 2> KV = gather<T, 2>(kprev + g.field, o);
+      U.c = u0 + KU.c * a;
+      V.c = v0 + KV.c * a;
+#pragma unroll
+      for (int ax = 0; ax < 2; ++ax)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          U.n[ax][k] = U.n[ax][k] + KU.n[ax][k] * a;
+          V.n[ax][k] = V.n[ax][k] + KV.n[ax][k] * a;
+        }
+    }
+    T fu, fv;
+    if (CELL == 1) burgers_rhs<T>(U, V, P, fu, fv);
+    else lo_rhs<T>(U.c, V.c, lap_apply<T, 2>(U, P), lap_apply<T, 2>(V, P), P, fu, fv);
+    if (stage == 0) {
+      kout[o.c] = fu;
+      kout[g.field + o.c] = fv;
+      acc[o.c] = fu;
+      acc[g.field + o.c] = fv;
+    } else if (stage < 3) {
+      kout[o.c] = fu;
+      kout[g.field + o.c] = fv;
+      acc[o.c] = acc[o.c] + T(2) * fu;
+      acc[g.field + o.c] = acc[g.field + o.c] + T(2) * fv;
+    } else {   // u0 + dt * (k1 + 2 k2 + 2 k3 + k4) / 6  (BUR3:201-202)
+      const T dt = P[P_DT];
+      acc[o.c] = u0 + dt * (acc[o.c] + fu) / T(6);
+      acc[g.field + o.c] = v0 + dt * (acc[g.field + o.c] + fv) / T(6);
+    }
+  }
+}
+
 }  // namespace percnn
 
 // =====================================================================================================

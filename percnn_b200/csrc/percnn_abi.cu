@@ -492,6 +492,38 @@ int percnn_step_fwd(percnn_plan_t* p, const void* h_in, void* h_out, void* strea
   return step_fwd_any(p, h_in, h_out, static_cast<cudaStream_t>(stream));
 }
 
+// One classical RK4 step of a Stage-3 physics cell (RCNNCell.forward_rk4, BUR3:159-206): four launches of the fused
+// right-hand side.  `ws` provides the two scratch states.
+int percnn_step_rk4(percnn_plan_t* p, const void* h_in, void* h_out, void* ws, void* stream) {
+  if (!p || !h_in || !h_out || !ws) return fail(PERCNN_ERR_INVALID, "null argument");
+  if (h_in == h_out) return fail(PERCNN_ERR_INVALID, "step_rk4 cannot run in place");
+  if (p->desc.cell != PERCNN_CELL_BURGERS && p->desc.cell != PERCNN_CELL_LO)
+    return fail(PERCNN_ERR_UNSUPPORTED, "forward_rk4 exists for the Stage-3 physics cells only (BUR3:159, LO3:153)");
+  if (p->desc.slab_ghost) return fail(PERCNN_ERR_UNSUPPORTED, "no slab-mode RK4");
+  DeviceGuard guard(p->desc.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t sb = (state_bytes(p) + 255) / 256 * 256;
+  char* k[2] = {static_cast<char*>(ws) + ws_states_off(p), static_cast<char*>(ws) + ws_states_off(p) + sb};
+  const int grid = generic_grid(p);
+  const double dt = p->desc.dt;
+  const double a_of[4] = {0.0, dt / 2.0, dt / 2.0, dt};
+  for (int stage = 0; stage < 4; ++stage) {
+    const void* kprev = stage == 0 ? nullptr : k[(stage - 1) & 1];
+    void* kout = k[stage & 1];
+    const bool burgers = p->desc.cell == PERCNN_CELL_BURGERS;
+    if (p->elt == 8) {
+      if (burgers) k_rk4_stage<double, 1><<<grid, kGenericThreads, 0, st>>>(p->g, p->slot, static_cast<const double*>(h_in), static_cast<const double*>(kprev), a_of[stage], static_cast<double*>(kout), static_cast<double*>(h_out), stage);
+      else k_rk4_stage<double, 2><<<grid, kGenericThreads, 0, st>>>(p->g, p->slot, static_cast<const double*>(h_in), static_cast<const double*>(kprev), a_of[stage], static_cast<double*>(kout), static_cast<double*>(h_out), stage);
+    } else {
+      if (burgers) k_rk4_stage<float, 1><<<grid, kGenericThreads, 0, st>>>(p->g, p->slot, static_cast<const float*>(h_in), static_cast<const float*>(kprev), float(a_of[stage]), static_cast<float*>(kout), static_cast<float*>(h_out), stage);
+      else k_rk4_stage<float, 2><<<grid, kGenericThreads, 0, st>>>(p->g, p->slot, static_cast<const float*>(h_in), static_cast<const float*>(kprev), float(a_of[stage]), static_cast<float*>(kout), static_cast<float*>(h_out), stage);
+    }
+    PERCNN_CUDA(cudaGetLastError());
+    p->launches++;
+  }
+  return PERCNN_OK;
+}
+
 // Forward step restricted to interior planes [z_lo, z_hi) of a 3-D TMA plan (slab mode overlap: the
 // planes that need ghosts are launched after the halo exchange, the rest before).  Not part of the
 // reference surface; used by percnn_b200.halo.

@@ -144,6 +144,16 @@ __device__ __forceinline__ void burgers_fwd(const Cross<T, 2>& U, const Cross<T,
   ov = fma_t(P[P_DT], fv, V.c);
 }
 
+// The right-hand side alone (f_rhs, BUR3:154-157): the RK4 cell evaluates it four times per step.
+template <typename T>
+__device__ __forceinline__ void burgers_rhs(const Cross<T, 2>& U, const Cross<T, 2>& V, const T* __restrict__ P, T& fu, T& fv) {
+  const T* C = P + P_PHYS;
+  const T* tx = C + 4;
+  const T* ty = C + 8;
+  fu = fma_t(C[1] * V.c, der_apply(ty, U.n[1]), fma_t(C[0] * U.c, der_apply(tx, U.n[0]), P[P_ALPHA + 0] * lap_apply<T, 2>(U, P)));
+  fv = fma_t(C[3] * V.c, der_apply(ty, V.n[1]), fma_t(C[2] * U.c, der_apply(tx, V.n[0]), P[P_ALPHA + 1] * lap_apply<T, 2>(V, P)));
+}
+
 // Adjoint ("Adjoint for a4").  With D^T the mirrored-tap stencil (= -D for the antisymmetric
 // reference taps):
 //   g_u = Gu + dt[nu_u L^T Gu + C1_u Dx(u) Gu + Dx^T(C1_u u Gu) + Dy^T(C2_u v Gu) + C1_v Dx(v) Gv]
@@ -214,6 +224,28 @@ __device__ __forceinline__ void lo_fwd(T u, T v, T Lu, T Lv, const T* __restrict
   fv = fma_t(Cv[5], u, fv);  // C6_v (0 when the cell has no such term)
   ou = fma_t(P[P_DT], fu, u);
   ov = fma_t(P[P_DT], fv, v);
+}
+
+// f_rhs of the lambda-omega cell (LO3:148-151).
+template <typename T>
+__device__ __forceinline__ void lo_rhs(T u, T v, T Lu, T Lv, const T* __restrict__ P, T& fu, T& fv) {
+  const T* Cu = P + P_PHYS;
+  const T* Cv = Cu + 5;
+  const T uu = u * u, vv = v * v;
+  const T u3 = uu * u, u2v = uu * v, uv2 = u * vv, v3 = vv * v;
+  fu = P[P_ALPHA + 0] * Lu;
+  fu = fma_t(Cu[0], u, fu);
+  fu = fma_t(Cu[1], u3, fu);
+  fu = fma_t(Cu[2], u2v, fu);
+  fu = fma_t(Cu[3], uv2, fu);
+  fu = fma_t(Cu[4], v3, fu);
+  fv = P[P_ALPHA + 1] * Lv;
+  fv = fma_t(Cv[0], v, fv);
+  fv = fma_t(Cv[1], u3, fv);
+  fv = fma_t(Cv[2], u2v, fv);
+  fv = fma_t(Cv[3], uv2, fv);
+  fv = fma_t(Cv[4], v3, fv);
+  fv = fma_t(Cv[5], u, fv);  // C6_v (0 when the cell has no such term)
 }
 
 template <typename T>

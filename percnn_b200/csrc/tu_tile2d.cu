@@ -82,7 +82,9 @@ int tile2d_setup(percnn_plan* p) {
   if (getenv("PERCNN_TILE2D_VERBOSE"))
     fprintf(stderr, "tile2d: %dx%d elt %d -> K=%d tile %dx%d (%dx%d tiles) halo %d/%d smem %d model %.2f us/step\n", H, W, p->elt,
             p->t2_K, p->t2_TH, p->t2_TW, p->t2_nty, p->t2_ntx, p->t2_hy, p->t2_hx, p->t2_smem, best);
-  if (cudaFuncSetAttribute(kernel_of(p), cudaFuncAttributeMaxDynamicSharedMemorySize, p->t2_smem) != cudaSuccess) {
+  // (the attribute belongs to the FUNCTION, which every plan of this cell/dtype shares: always ask for the cap, or a
+  // later plan with a smaller region would take the shared memory away from an earlier one)
+  if (cudaFuncSetAttribute(kernel_of(p), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cap)) != cudaSuccess) {
     cudaGetLastError();
     return PERCNN_OK;
   }

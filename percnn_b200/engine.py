@@ -153,6 +153,12 @@ class Plan:
         self._check_state(h_out, "h_out")
         check(self._L.percnn_step_fwd(self._h, h_in.data_ptr(), h_out.data_ptr(), _stream_ptr(self.device)))
 
+    def step_rk4(self, h_in: torch.Tensor, h_out: torch.Tensor) -> None:
+        self._check_state(h_in, "h_in")
+        self._check_state(h_out, "h_out")
+        check(self._L.percnn_step_rk4(self._h, h_in.data_ptr(), h_out.data_ptr(), self.workspace().data_ptr(),
+                                      _stream_ptr(self.device)))
+
     def step_fwd_range(self, h_in: torch.Tensor, h_out: torch.Tensor, z_lo: int, z_hi: int) -> None:
         check(self._L.percnn_step_fwd_range(self._h, h_in.data_ptr(), h_out.data_ptr(), int(z_lo), int(z_hi),
                                             _stream_ptr(self.device)))

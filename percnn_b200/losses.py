@@ -148,8 +148,7 @@ def physics_residuals(frames: torch.Tensor, spec: PhysicsSpec):
 
 class LossGenerator(torch.nn.Module):
     """Drop-in for the scripts' `loss_generator(dt, dx)` (FWD:265-286, GS2D:241-262, GS3D:264-283): holds the
-    constants; the arithmetic is in the fused kernels.  `get_phy_Loss` of the reference takes the PADDED trajectory
-    and is only ever called from `loss_gen` / `loss_func`; use those (or `physics_residuals`) instead."""
+    constants; the arithmetic is in the fused kernels."""
 
     def __init__(self, spec: PhysicsSpec):
         super().__init__()
@@ -159,5 +158,24 @@ class LossGenerator(torch.nn.Module):
         return physics_loss(output, self.spec)
 
     def get_phy_Loss(self, output):
-        raise NotImplementedError("the fused loss works on the un-padded trajectory: call loss_gen(output, loss_func) "
-                                  "(or percnn_b200.losses.physics_residuals for f_u, f_v)")
+        """(f_u, f_v) like the reference's method (GS2D:270-329, FWD:288-342, GS3D:286-327): `output` is the trajectory
+        PADDED periodically by 2 cells before and 3 after every spatial axis (what `loss_gen` builds, GS2D:343-346);
+        each residual field has extent + 1 points per axis, the last being the periodic image of the first.  Computed by
+        the fused residual kernel on the un-padded grid (no gradient: the differentiable path is `loss_gen`)."""
+        nsp = output.dim() - 2
+        core = (slice(None), slice(None)) + (slice(2, -3),) * nsp
+        frames = output[core].contiguous()
+        for ax in range(nsp):   # the padding must be the periodic one, or the un-padded grid does not describe `output`
+            lead = [slice(None)] * output.dim()
+            lead[2 + ax] = slice(0, 2)
+            src = [slice(None)] * output.dim()
+            src[2 + ax] = slice(-5, -3)
+            if not torch.allclose(output[tuple(lead)], output[tuple(src)]):
+                raise ValueError("get_phy_Loss expects the periodic (2, 3) padding of loss_gen (GS2D:343-346)")
+        f_u, f_v = physics_residuals(frames, self.spec)
+        for ax in range(nsp):
+            first = [slice(None)] * f_u.dim()
+            first[2 + ax] = slice(0, 1)
+            f_u = torch.cat((f_u, f_u[tuple(first)]), dim=2 + ax)
+            f_v = torch.cat((f_v, f_v[tuple(first)]), dim=2 + ax)
+        return f_u, f_v

@@ -260,6 +260,37 @@ def make_phys_cases():
     make_phys_case("gs3d", (6, 7, 9), 4, 33)
 
 
+def make_rk4_cases():
+    """`RCNNCell.forward_rk4` of the Stage-3 scripts (BUR3:159-206; defined, never called by the scripts) driven for
+    three steps, with autograd gradients of a weighted sum w.r.t. the initial state and every coefficient."""
+    for alias, seed, amp in (("bur3", 41, (-0.5, 0.5)), ("lo3", 42, (-0.8, 0.8)), ("lo3n", 43, (-0.8, 0.8))):
+        mod = load_reference_module(alias)
+        cell = build_cell(alias, mod)
+        g = torch.Generator().manual_seed(seed + 100)
+        with torch.no_grad():
+            for n, prm in cell.named_parameters():
+                if prm.requires_grad:
+                    prm.add_(0.05 * (torch.rand((), generator=g, dtype=torch.float64) - 0.5))
+        h0 = smooth_state((20, 24), seed, torch.float64, *amp).requires_grad_(True)
+        h, traj = h0, [h0]
+        for _ in range(3):
+            h, _ = cell.forward_rk4(h)
+            traj.append(h)
+        traj = torch.cat(traj, 0)
+        w = torch.randn(traj.shape, generator=torch.Generator().manual_seed(seed + 7), dtype=torch.float64)
+        loss = (traj * w).sum()
+        loss.backward()
+        rec = {"h0": h0.detach().numpy(), "traj": traj.detach().numpy(), "loss_weights": w.numpy(),
+               "loss": np.array(loss.item()), "g_h0": h0.grad.numpy()}
+        for k, v in cell.state_dict().items():
+            rec["param/" + k] = v.detach().numpy()
+        for n, prm in cell.named_parameters():
+            if prm.requires_grad:
+                rec["grad/" + n] = prm.grad.numpy()
+        np.savez_compressed(os.path.join(OUT, f"rk4_{alias}.npz"), **rec)
+        print(f"rk4_{alias}.npz", tuple(traj.shape), loss.item())
+
+
 def make_weights():
     """Cell weights of the shipped checkpoints at full size (bench + full-size property tests)."""
     for alias in CHECKPOINTS:
@@ -298,6 +329,9 @@ if __name__ == "__main__":
     if "--phys-only" in sys.argv:
         make_phys_cases()
         sys.exit(0)
+    if "--rk4-only" in sys.argv:
+        make_rk4_cases()
+        sys.exit(0)
     make_case("fwd", (20, 24), 6, 11, amp=(-0.8, 0.8))
     make_case("gs2d", (20, 24), 6, 12)
     make_case("gs3d", (6, 8, 12), 5, 13)
@@ -308,6 +342,7 @@ if __name__ == "__main__":
     make_case("lo3", (20, 24), 6, 18, amp=(-0.8, 0.8))
     make_case("lo3n", (20, 24), 6, 19, amp=(-0.8, 0.8))
     make_weights()
-    make_rcnn_case()
+    # (rcnn_*.npz, train_*.npz and the Stage-3 checkpoint fixture come from make_golden_modules.py)
     make_data_loss_cases()
     make_phys_cases()
+    make_rk4_cases()

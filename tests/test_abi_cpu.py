@@ -188,3 +188,24 @@ def test_fused_losses_fail_loudly_without_cuda():
     cell = gs2d.RCNNCell(input_channels=2, hidden_channels=8, input_kernel_size=5)
     with pytest.raises(RuntimeError, match="(?i)cuda"):
         cell.rollout_data_loss(torch.zeros(1, 2, 16, 16), 3, torch.zeros(1, 2, 8, 8), [True, False, False, False], 2)
+
+
+def test_stage3_burgers_checkpoint_with_stale_keys_loads():
+    """The shipped Stage-3 Burgers checkpoint carries C3_*/C4_* coefficients of an older script version (SURVEY 8c);
+    the drop-in drops them with a warning and still insists on every key it does have."""
+    import warnings
+    from percnn_b200.variants import burgers_stage3
+    z = np.load(os.path.join(ROOT, "tests", "golden", "ckpt_bur3_stage3.npz"))
+    sd = {k: torch.from_numpy(z[k]) for k in z.files}
+    assert "crnn_cell.C3_u" in sd
+    model = burgers_stage3.RCNN(input_channels=2, hidden_channels=4, output_channels=2, init_state_low=torch.zeros(1, 2, 5, 5, dtype=torch.float64),
+                                input_kernel_size=5, input_stride=1, input_padding=2, step=2, effective_step=[0, 1])
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        model.load_state_dict(sd)          # strict
+    assert any("stale" in str(x.message) for x in w)
+    assert float(model.crnn_cell.nu_u) == float(z["crnn_cell.nu_u"])
+    assert torch.equal(model.UpconvBlock.up0.weight.detach(), sd["UpconvBlock.up0.weight"])
+    del sd["crnn_cell.C1_u"]
+    with pytest.raises(RuntimeError):
+        model.load_state_dict(sd)

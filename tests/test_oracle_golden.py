@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import percnn_oracle as po
-from tests.helpers import DLOSS_CASES, GOLDEN_CASES, load_dloss, load_golden, rel_l2, rel_linf
+from tests.helpers import DLOSS_CASES, GOLDEN, GOLDEN_CASES, load_dloss, load_golden, rel_l2, rel_linf
 
 
 @pytest.mark.parametrize("tag", list(GOLDEN_CASES))
@@ -161,3 +161,15 @@ def test_fwd_checkpoint_known_answer():
     fv = float(p["DB"]) * lap(v) - A * u + (1 - A) * v
     want = np.stack((u + 0.0125 * fu, v + 0.0125 * fv))[None]
     assert np.abs(got - want).max() < 1e-6
+
+
+@pytest.mark.parametrize("tag,variant", [("bur3", "bur3"), ("lo3", "lo3"), ("lo3n", "lo3")])
+def test_oracle_rk4_matches_reference_forward_rk4(tag, variant):
+    """tests/golden/rk4_*.npz: the reference's own `forward_rk4` (BUR3:159-206) for three steps."""
+    import os
+    z = np.load(os.path.join(GOLDEN, f"rk4_{tag}.npz"))
+    p = {k[len("param/"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("param/")}
+    h = torch.from_numpy(z["h0"])
+    for t in range(3):
+        h = po.rk4_step_torch(h, p, variant)
+        assert rel_l2(h.numpy(), z["traj"][t + 1:t + 2]) <= 1e-13, t

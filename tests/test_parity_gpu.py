@@ -347,3 +347,31 @@ def test_persistent_adjoint_equals_per_step_adjoint(tag, monkeypatch):
     assert np.array_equal(res[0][0], res[1][0])
     for k in res[1][1]:
         assert rel_l2(res[0][1][k], res[1][1][k]) <= (1e-12 if z["h0"].dtype == np.float64 else 2e-6), k
+
+
+@pytest.mark.parametrize("tag", ["bur3", "lo3", "lo3n"])
+def test_fused_rk4_matches_reference_forward_rk4(tag):
+    """`forward_rk4` (BUR3:159-206; four launches of the fused right-hand side) against the reference's own method:
+    states, and the gradients of a weighted sum w.r.t. the initial state and every coefficient."""
+    import os
+    from tests.helpers import GOLDEN
+    z = np.load(os.path.join(GOLDEN, f"rk4_{tag}.npz"))
+    params = {k[len("param/"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("param/")}
+    cell = _cell(tag, params)
+    h0 = torch.from_numpy(z["h0"]).to(DEV).requires_grad_(True)
+    launches0 = cell._plan(h0).launch_count
+    h, traj = h0, [h0]
+    for _ in range(3):
+        h, o = cell.forward_rk4(h)
+        assert o is h
+        traj.append(h)
+    assert cell._plan(h0).launch_count - launches0 >= 12, "forward_rk4 must run the fused stage kernels"
+    traj = torch.cat(traj, 0)
+    assert rel_l2(traj.detach().cpu().numpy(), z["traj"]) <= 1e-12
+    loss = (traj * torch.from_numpy(z["loss_weights"]).to(DEV)).sum()
+    loss.backward()
+    assert abs(loss.item() - float(z["loss"])) <= 1e-11 * abs(float(z["loss"]))
+    assert rel_l2(h0.grad.cpu().numpy(), z["g_h0"]) <= 1e-10
+    named = dict(cell.named_parameters())
+    for k in [k for k in z.files if k.startswith("grad/")]:
+        assert rel_l2(named[k[len("grad/"):]].grad.cpu().numpy(), z[k]) <= 1e-10, k

@@ -115,6 +115,6 @@ def test_physics_loss_no_grad_and_errors():
         losses.physics_loss(out[:2], spec)                        # needs >= 3 frames
     with pytest.raises(ValueError):
         losses.physics_loss(out[:, :1], spec)                     # 2 fields
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):                 # get_phy_Loss wants the periodically PADDED trajectory (FWD:344-350)
         from percnn_b200.variants import lambda_omega_fwd
         lambda_omega_fwd.loss_generator().get_phy_Loss(out)
