@@ -278,6 +278,71 @@ int percnn_phys_loss_fwd(const percnn_phys_loss_t* pl, const void* frames, void*
 int percnn_phys_loss_bwd(const percnn_phys_loss_t* pl, const void* frames, const void* resid, const void* gscale,
                          void* g_frames, void* stream);
 
+/* ---- initial-state generator ("upscaler") + IC loss ------------------------ */
+/* `model.UpconvBlock(model.init_state_low)` of the training scripts (GS2D:26-41,164; GS3D:41-56,186; BUR1:38-52 =
+ * LO1:38-52 = BUR3:38-52) and the autograd backward of it (the sink of dL/dh0, GS2D:407):
+ *   layers = 2:  ConvTranspose(2->C, k5, s2, p2, op1) -> act -> ConvTranspose(C->C, k5, stride2, p2, op stride2-1) -> Conv1x1(C->2)
+ *   layers = 1:  ConvTranspose2d(2->C, k5, s2, p2, op1) -> act -> Conv1x1(C->2)
+ * `params`: the module's state_dict tensors concatenated in state_dict order (W1 [2][C][K], b1 [C], (W2 [C][C][K],
+ * b2 [C],) W3 [2][C], b3 [2]; K = 5^ndim).  `low`: [2][Dl][Hl][Wl] (always the WHOLE low-resolution input).
+ * `mid`: caller-owned tape of the activations, percnn_upscaler_sizes().mid_elems elements, written by _fwd and read by
+ * _bwd.  h0 / g_h0: [2] fields of [out_nz][Ho][Wo], `out_field_stride` elements apart (0 = dense).
+ * Slab mode (3-D): out_z0 / out_nz select the output planes this call produces, so every rank generates its own slab
+ * of h0; in _bwd, g_h0 must then be addressable 2 planes beyond both ends of the range (the ghost planes of the slab
+ * layout, holding the neighbours' dL/dh0; planes outside the global grid are never read), and the parameter gradients
+ * are this slab's partial sums (all-reduce them).  Stand-alone: no plan needed; stream-ordered, deterministic. */
+typedef struct percnn_upscaler {
+  int32_t ndim;              /* 2 | 3 */
+  int32_t dtype;             /* percnn_dtype_t */
+  int32_t channels;          /* C: 8 (GS2D:31, GS3D:46) | 16 (BUR1:44) */
+  int32_t act;               /* 0 = sigmoid (GS2D:34) | 1 = tanh (BUR1:46) */
+  int32_t layers;            /* 1 | 2 */
+  int32_t stride2;           /* stride of the second transposed conv: 2 (GS2D:36) | 1 (GS3D:51); ignored for layers = 1 */
+  int32_t device;
+  int32_t reserved;
+  int64_t low_extent[3];     /* Dl, Hl, Wl (2-D: Dl = 1) */
+  int64_t out_z0, out_nz;    /* output plane range; out_nz = 0: the whole grid */
+  int64_t out_field_stride;  /* 0 = out_nz * Ho * Wo */
+} percnn_upscaler_t;
+/* Any output pointer may be NULL.  out_extent[3] = Do, Ho, Wo of the whole output grid. */
+int percnn_upscaler_sizes(const percnn_upscaler_t* up, int64_t* nparams, int64_t* mid_elems, int64_t* out_extent,
+                          size_t* ws_bytes);
+int percnn_upscaler_fwd(const percnn_upscaler_t* up, const void* params, const void* low, void* mid, void* h0, void* ws,
+                        void* stream);
+/* g_params (same packing as `params`) = dL/dparams for the upstream gradient g_h0; accumulate != 0 adds to it. */
+int percnn_upscaler_bwd(const percnn_upscaler_t* up, const void* params, const void* low, const void* mid,
+                        const void* g_h0, void* g_params, int accumulate, void* ws, void* stream);
+/* `get_ic_loss` (GS2D:331-338, GS3D:325-333, BUR1:462-471): loss_out = mean((a - b)^2) over n elements (fp64
+ * partial sums, fixed order); _bwd: g = gscale * 2/n * (a - b)  (gscale: device scalar, NULL = 1; accumulate != 0 adds). */
+size_t percnn_mse_workspace_bytes(void);
+int percnn_mse_fwd(int dtype, int device, const void* a, const void* b, int64_t n, void* loss_out, void* ws, void* stream);
+int percnn_mse_bwd(int dtype, int device, const void* a, const void* b, int64_t n, const void* gscale, void* g,
+                   int accumulate, void* stream);
+
+/* ---- Stage-2 library of candidate terms ------------------------------------- */
+/* `Loss_generator.get_phy_residual` / `get_library` (2D_Burgers_eqn/Stage-2/derivatives.py:129-199, lambda-omega
+ * stage-2/derivatives.py:128-199) on the periodically padded trajectory that `get_residual_mse` builds
+ * (derivatives.py:207-208), and the 70-column matrix of PDE_FIND_u.py:185-193,246-259.
+ * frames: [nframes][2][H][W].  terms: [12][nframes-2][H+1][W+1] in the order
+ *     f_u f_v u v u_t v_t u_x u_y v_x v_y lap_u lap_v
+ * ('ones' is implicit); point (i, j) of the (H+1) x (W+1) grid is cell (i mod H, j mod W) -- the reference's padding
+ * makes the last row/column the periodic image of the first.  u_x differentiates along tensor dim 2, u_y along dim 3. */
+typedef struct percnn_library {
+  int32_t dtype;     /* percnn_dtype_t (the scripts run in fp32, derivatives.py:8) */
+  int32_t kind;      /* residual: 0 = Burgers, nu = 1/200 (derivatives.py:189-192) | 1 = lambda-omega (stage-2/derivatives.py:188-192) */
+  int64_t H, W;
+  int32_t nframes;   /* >= 3 */
+  int32_t device;
+  double dt, dx;     /* derivatives.py:87: dy = dx */
+} percnn_library_t;
+int64_t percnn_library_points(const percnn_library_t* lib);   /* (nframes-2)(H+1)(W+1), -1 on a bad descriptor */
+int percnn_library_terms(const percnn_library_t* lib, const void* frames, void* terms, void* stream);
+/* theta[r][a*7+b] = A_a * B_b at flattened point idx[r] (fp64, from the stored terms: `to_numpy_float64` then the
+ * eval'd products), A = ones u v u^2 uv v^2 u^3 u^2v uv^2 v^3, B = ones u_x u_y v_x v_y lap_u lap_v;
+ * rhs[r] = (u_t, v_t).  idx: n device int64 indices into [0, points). */
+int percnn_library_theta(const percnn_library_t* lib, const void* terms, const int64_t* idx, int64_t n, double* theta,
+                         double* rhs, void* stream);
+
 /* ---- host-buffer convenience (end-to-end path) ------------------------------------------------ */
 /* Same as params_load + rollout_fwd but with HOST pointers: copies params and h0 to the device, runs the
  * rollout, copies the emitted frames (and h_final if non-NULL) back, blocks until done.  Scratch is

@@ -610,6 +610,130 @@ def phys_loss_np(output, variant: str):
 
 
 # --------------------------------------------------------------------------------------
+# Stage-2 library of candidate terms
+# --------------------------------------------------------------------------------------
+
+STAGE2_LIST_A = ["ones", "u", "v", "u**2", "u*v", "v**2", "u**3", "u**2*v", "u*v**2", "v**3"]   # PDE_FIND_u.py:187
+STAGE2_LIST_B = ["ones", "u_x", "u_y", "v_x", "v_y", "lap_u", "lap_v"]                           # PDE_FIND_u.py:188
+
+
+def stage2_library_torch(output: torch.Tensor, kind: str, dt: float, dx: float) -> Dict[str, torch.Tensor]:
+    """`Loss_generator.get_phy_residual` (BUR2d:129-199; lambda-omega: `get_library`) on the periodic (2, 3) padding
+    `get_residual_mse` builds (BUR2d:207-208), as the same op sequence: three fixed 5x5 valid convs per field divided
+    by their resolution, forward time difference, residual.  `output`: un-padded [T, 2, H, W]."""
+    dtype = output.dtype
+    pad = torch.cat((output[:, :, :, -2:], output, output[:, :, :, 0:3]), dim=3)
+    pad = torch.cat((pad[:, :, -2:, :], pad, pad[:, :, 0:3, :]), dim=2)
+    w_dx = torch.tensor(dx_stencil_2d(), dtype=torch.float32).to(dtype).reshape(1, 1, 5, 5)
+    w_dy = torch.tensor(dy_stencil_2d(), dtype=torch.float32).to(dtype).reshape(1, 1, 5, 5)
+    w_lap = torch.tensor(laplace_stencil(2), dtype=torch.float32).to(dtype).reshape(1, 1, 5, 5)
+    u_in, v_in = pad[0:-2, 0:1], pad[0:-2, 1:2]
+    lap_u, lap_v = F.conv2d(u_in, w_lap) / dx ** 2, F.conv2d(v_in, w_lap) / dx ** 2
+    u_x, u_y = F.conv2d(u_in, w_dx) / dx, F.conv2d(u_in, w_dy) / dx
+    v_x, v_y = F.conv2d(v_in, w_dx) / dx, F.conv2d(v_in, w_dy) / dx
+    q = pad[:, :, 2:-2, 2:-2]
+    q_t = (q[1:-1] - q[:-2]) / dt
+    u, v, u_t, v_t = q[0:-2, 0:1], q[0:-2, 1:2], q_t[:, 0:1], q_t[:, 1:2]
+    if kind == "burgers":
+        nu = 1 / 200
+        f_u = u_t - nu * lap_u + u * u_x + v * u_y
+        f_v = v_t - nu * lap_v + u * v_x + v * v_y
+    else:
+        f_u = u_t - (0.1 * lap_u + (1 - u ** 2 - v ** 2) * u + 1.0 * (u ** 2 + v ** 2) * v)
+        f_v = v_t - (0.1 * lap_v + (1 - u ** 2 - v ** 2) * v - 1.0 * (u ** 2 + v ** 2) * u)
+    return {"f_u": f_u, "f_v": f_v, "ones": torch.ones_like(u), "u": u, "v": v, "u_t": u_t, "v_t": v_t, "u_x": u_x,
+            "u_y": u_y, "v_x": v_x, "v_y": v_y, "lap_u": lap_u, "lap_v": lap_v}
+
+
+def stage2_theta_np(library: Dict[str, torch.Tensor], idx) -> Tuple[np.ndarray, np.ndarray]:
+    """PDE_FIND_u.py:228-259: terms -> flattened fp64 columns, the 70 products A*B at the sampled rows, rhs (u_t, v_t)."""
+    col = {k: v.detach().double().numpy().reshape(-1)[np.asarray(idx)] for k, v in library.items()}
+    u, v = col["u"], col["v"]
+    A = {"ones": np.ones_like(u), "u": u, "v": v, "u**2": u ** 2, "u*v": u * v, "v**2": v ** 2, "u**3": u ** 3,
+         "u**2*v": u ** 2 * v, "u*v**2": u * v ** 2, "v**3": v ** 3}
+    lhs = np.stack([A[a] * col[b] for a in STAGE2_LIST_A for b in STAGE2_LIST_B], axis=1)
+    return lhs, np.stack((col["u_t"], col["v_t"]), axis=1)
+
+
+# --------------------------------------------------------------------------------------
+# Initial-state generator ("upscaler") and IC loss (SURVEY.md 8f rank 3)
+# --------------------------------------------------------------------------------------
+
+#: per script family: (ndim, channels, activation, layers, stride of the 2nd transposed conv, state_dict key prefixes)
+UPSCALERS = {
+    "gs2d": dict(ndim=2, C=8, act="sigmoid", layers=2, stride2=2, keys=("convnet.0", "convnet.2", "convnet.3")),   # GS2D:26-41
+    "gs3d": dict(ndim=3, C=8, act="sigmoid", layers=2, stride2=1, keys=("convnet.0", "convnet.2", "convnet.3")),   # GS3D:41-56
+    "stage": dict(ndim=2, C=16, act="tanh", layers=1, stride2=1, keys=("up0", "out")),                            # BUR1:38-52
+}
+
+
+def upscaler_torch(low: torch.Tensor, sd: Dict[str, torch.Tensor], kind: str) -> torch.Tensor:
+    """`upscaler.forward` as the ATen op sequence `nn.Sequential` issues (GS2D:40-41): conv_transpose (k5, s2, p2,
+    op1), sigmoid | tanh, [conv_transpose (k5, s, p2, op s-1)], 1x1 conv.  Differentiable (CPU autograd gives the
+    parameter gradients the fused adjoint is checked against)."""
+    u = UPSCALERS[kind]
+    ct = F.conv_transpose2d if u["ndim"] == 2 else F.conv_transpose3d
+    cv = F.conv2d if u["ndim"] == 2 else F.conv3d
+    k = u["keys"]
+    x = ct(low, sd[k[0] + ".weight"], sd[k[0] + ".bias"], stride=2, padding=2, output_padding=1)
+    x = torch.sigmoid(x) if u["act"] == "sigmoid" else torch.tanh(x)
+    if u["layers"] == 2:
+        s2 = u["stride2"]
+        x = ct(x, sd[k[1] + ".weight"], sd[k[1] + ".bias"], stride=s2, padding=2, output_padding=s2 - 1)
+    return cv(x, sd[k[-1] + ".weight"], sd[k[-1] + ".bias"])
+
+
+def _conv_transpose_np(x: np.ndarray, w: np.ndarray, b: np.ndarray, stride: int) -> np.ndarray:
+    """Transposed conv (kernel 5, padding 2, output_padding stride-1) from its definition, scatter form:
+    out[co, s*i - 2 + k] += x[ci, i] * w[ci, co, k] per axis; x [Cin, *sp], w [Cin, Cout, 5, ...]."""
+    nd = x.ndim - 1
+    sp = x.shape[1:]
+    full = tuple(stride * (n - 1) + 5 for n in sp)               # un-cropped scatter target
+    out = np.zeros((w.shape[1],) + full, dtype=np.float64)
+    for k in np.ndindex(*(5,) * nd):
+        contrib = np.tensordot(w[(slice(None), slice(None)) + k].T.astype(np.float64), x.astype(np.float64), axes=(1, 0))
+        sl = tuple(slice(kk, kk + stride * (n - 1) + 1, stride) for kk, n in zip(k, sp))
+        out[(slice(None),) + sl] += contrib
+    crop = tuple(slice(2, 2 + stride * n) for n in sp)           # padding 2 in front; extent stride*n (op = stride-1)
+    res = np.zeros((w.shape[1],) + tuple(stride * n for n in sp), dtype=np.float64)
+    src = out[(slice(None),) + crop]
+    res[(slice(None),) + tuple(slice(0, m) for m in src.shape[1:])] = src
+    return res + b.astype(np.float64).reshape((-1,) + (1,) * nd)
+
+
+def upscaler_np(low, sd, kind: str) -> np.ndarray:
+    """Independent fp64 numpy restatement of the upscaler (scatter-form transposed convs); low [1, 2, *sp]."""
+    u = UPSCALERS[kind]
+    k = u["keys"]
+    g = lambda name: _np(sd[name])
+    x = _conv_transpose_np(_np(low)[0], g(k[0] + ".weight"), g(k[0] + ".bias"), 2)
+    x = 1.0 / (1.0 + np.exp(-x)) if u["act"] == "sigmoid" else np.tanh(x)
+    if u["layers"] == 2:
+        x = _conv_transpose_np(x, g(k[1] + ".weight"), g(k[1] + ".bias"), u["stride2"])
+    w3 = g(k[-1] + ".weight").reshape(2, -1)
+    out = np.tensordot(w3, x, axes=(1, 0)) + g(k[-1] + ".bias").reshape((2,) + (1,) * (x.ndim - 1))
+    return out[None]
+
+
+def ic_target_torch(low: torch.Tensor, kind: str, size) -> torch.Tensor:
+    """The interpolated low-resolution state `get_ic_loss` compares the upscaler with: GS2D:334 bicubic to `size`;
+    GS3D:328 trilinear; BUR1:465-470 periodic extension by one row/column, bicubic with align_corners, last
+    row/column dropped."""
+    if kind == "gs2d":
+        return F.interpolate(low, tuple(size), mode="bicubic")
+    if kind == "gs3d":
+        return F.interpolate(low, tuple(size), mode="trilinear")
+    ext = torch.cat((low, low[:, :, :, 0:1]), dim=3)
+    ext = torch.cat((ext, ext[:, :, 0:1, :]), dim=2)
+    return F.interpolate(ext, tuple(n + 1 for n in size), mode="bicubic", align_corners=True)[:, :, :-1, :-1]
+
+
+def ic_loss_torch(low: torch.Tensor, sd: Dict[str, torch.Tensor], kind: str, size) -> torch.Tensor:
+    """`get_ic_loss(model)` (GS2D:331-338): mse(upscaler(low), interpolated low)."""
+    return F.mse_loss(upscaler_torch(low, sd, kind), ic_target_torch(low, kind, size))
+
+
+# --------------------------------------------------------------------------------------
 # Synthetic initial states of SURVEY 8d (seeded, periodic-safe) -- shared by tests and bench.
 # --------------------------------------------------------------------------------------
 

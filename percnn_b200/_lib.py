@@ -30,6 +30,8 @@ EXPORTS = (
     "percnn_rollout_fwd_host", "percnn_data_loss_fwd", "percnn_step_bwd_loss", "percnn_rollout_bwd_loss",
     "percnn_phys_loss_workspace_bytes", "percnn_phys_loss_fwd", "percnn_phys_loss_bwd",
     "percnn_slab_rollout_fwd", "percnn_slab_rollout_tape", "percnn_slab_rollout_bwd", "percnn_plan_slab_persistent", "percnn_plan_uses_tile2d", "percnn_step_rk4",
+    "percnn_upscaler_sizes", "percnn_upscaler_fwd", "percnn_upscaler_bwd", "percnn_mse_workspace_bytes", "percnn_mse_fwd",
+    "percnn_mse_bwd", "percnn_library_points", "percnn_library_terms", "percnn_library_theta",
 )
 
 
@@ -72,6 +74,23 @@ class PhysLoss(ctypes.Structure):
     _fields_ = [
         ("ndim", c_int32), ("dtype", c_int32), ("extent", c_int64 * 3), ("nframes", c_int32), ("device", c_int32),
         ("diff", c_double * 2), ("poly", (c_double * 10) * 2), ("dt", c_double), ("dx", c_double),
+    ]
+
+
+class Upscaler(ctypes.Structure):
+    """percnn_upscaler_t"""
+    _fields_ = [
+        ("ndim", c_int32), ("dtype", c_int32), ("channels", c_int32), ("act", c_int32), ("layers", c_int32),
+        ("stride2", c_int32), ("device", c_int32), ("reserved", c_int32), ("low_extent", c_int64 * 3),
+        ("out_z0", c_int64), ("out_nz", c_int64), ("out_field_stride", c_int64),
+    ]
+
+
+class Library(ctypes.Structure):
+    """percnn_library_t"""
+    _fields_ = [
+        ("dtype", c_int32), ("kind", c_int32), ("H", c_int64), ("W", c_int64), ("nframes", c_int32), ("device", c_int32),
+        ("dt", c_double), ("dx", c_double),
     ]
 
 
@@ -129,6 +148,16 @@ def lib() -> ctypes.CDLL:
     L.percnn_phys_loss_workspace_bytes.restype = c_size_t
     L.percnn_phys_loss_fwd.argtypes = [POINTER(PhysLoss), vp, vp, vp, vp, vp]
     L.percnn_phys_loss_bwd.argtypes = [POINTER(PhysLoss), vp, vp, vp, vp, vp]
+    L.percnn_upscaler_sizes.argtypes = [POINTER(Upscaler), POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), POINTER(c_size_t)]
+    L.percnn_upscaler_fwd.argtypes = [POINTER(Upscaler), vp, vp, vp, vp, vp, vp]
+    L.percnn_upscaler_bwd.argtypes = [POINTER(Upscaler), vp, vp, vp, vp, vp, c_int, vp, vp]
+    L.percnn_mse_workspace_bytes.restype = c_size_t
+    L.percnn_mse_fwd.argtypes = [c_int, c_int, vp, vp, c_int64, vp, vp, vp]
+    L.percnn_mse_bwd.argtypes = [c_int, c_int, vp, vp, c_int64, vp, vp, c_int, vp]
+    L.percnn_library_points.restype = c_int64
+    L.percnn_library_points.argtypes = [POINTER(Library)]
+    L.percnn_library_terms.argtypes = [POINTER(Library), vp, vp, vp]
+    L.percnn_library_theta.argtypes = [POINTER(Library), vp, vp, c_int64, vp, vp, vp]
     if L.percnn_abi_version() != ABI_VERSION:
         raise ImportError(f"{LIB_PATH}: ABI version {L.percnn_abi_version()} != {ABI_VERSION}; rebuild the library")
     _lib = L

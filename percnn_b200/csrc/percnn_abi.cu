@@ -21,17 +21,6 @@ constexpr int kMaxDevices = 64;
 std::mutex g_slot_mutex;
 bool g_slot_used[kMaxDevices][kPrepSlots] = {};
 
-// Makes the plan's device current for the duration of an entry point and restores the caller's device.
-struct DeviceGuard {
-  int prev = -1;
-  bool changed = false;
-  explicit DeviceGuard(int dev) {
-    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) changed = cudaSetDevice(dev) == cudaSuccess;
-  }
-  ~DeviceGuard() {
-    if (changed) cudaSetDevice(prev);
-  }
-};
 }  // namespace
 
 namespace percnn {

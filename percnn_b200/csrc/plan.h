@@ -97,6 +97,18 @@ namespace percnn {
 
 int fail(int code, const std::string& msg);   // sets the thread-local error message, returns `code`
 
+// Makes a device current for the duration of an entry point and restores the caller's device.
+struct DeviceGuard {
+  int prev = -1;
+  bool changed = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) changed = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (changed) cudaSetDevice(prev);
+  }
+};
+
 #define PERCNN_CUDA(call)                                                                                   \
   do {                                                                                                      \
     cudaError_t e__ = (call);                                                                               \

@@ -176,6 +176,38 @@ class SlabRollout:
     def interior(self) -> torch.Tensor:
         return self.bufs[self.cur][:, 2:self.nz + 2]
 
+    # -- sharded initial-state generator ------------------------------------------
+    def set_state_from_upscaler(self, upscaler, init_state_low: torch.Tensor) -> None:
+        """h0 = upscaler(init_state_low) (GS3D:186), every rank producing only its own planes, straight into the slab
+        buffer (no full-resolution tensor exists anywhere); `init_state_low` is the whole low-resolution input,
+        replicated (1/8 of the cells).  Keeps what `upscaler_backward` needs."""
+        from . import upscaler as up
+        H, W = self.plan.spatial[1:]
+        low = init_state_low.detach().to(self.device, torch.float32).contiguous()
+        geo = upscaler.geometry(tuple(low.shape[2:]), torch.float32, self.device, out_z0=self.z0, out_nz=self.nz,
+                                out_field_stride=(self.nz + 4) * H * W)
+        if tuple(geo.out_shape) != (self.nz * self.world, H, W):
+            raise ValueError(f"upscaler output {geo.out_shape} does not match the global grid {(self.nz * self.world, H, W)}")
+        flat = up._pack(upscaler.up_parameters(), torch.float32)
+        b = self.bufs[self.cur]
+        _, mid = up.upscaler_fwd(geo, flat, low, out=b[:, 2:])
+        self._up = (upscaler, geo, flat, low, mid)
+        self.set_state(b[:, 2:self.nz + 2])
+
+    def upscaler_backward(self, g_h0: torch.Tensor) -> torch.Tensor:
+        """Parameter gradient of the upscaler for dL/dh0 = `g_h0` (this rank's [2][nz][H][W] planes, as `backward`
+        returns them): ghost planes of the gradient are exchanged once, every rank reduces the sums of its own planes,
+        one all-reduce adds them.  Returns the flat gradient (packing order), identical on every rank."""
+        from . import upscaler as up
+        upscaler, geo, flat, low, mid = self._up
+        gb = self.bufs[self.cur ^ 1]
+        gb[:, 2:self.nz + 2].copy_(g_h0)
+        self._exchange_blocking(self.cur ^ 1)
+        gp = up.upscaler_bwd(geo, flat, low, mid, gb[:, 2:].data_ptr())
+        if self.world > 1:
+            dist.all_reduce(gp, op=dist.ReduceOp.SUM, group=self.group)
+        return gp
+
     @property
     def launch_count(self) -> int:
         return self.plan.launch_count + self._extra_launches

@@ -5,11 +5,14 @@ import torch.nn as nn
 
 from .. import _lib
 from ..cells import FusedRCNN, PiCell
+from ..upscaler import FusedUpscaler, ic_loss
 
 
-class upscaler(nn.Module):
+class upscaler(FusedUpscaler):
     """BUR1:38-52 / LO1:38-52: one stride-2 transposed conv, tanh, 1x1 conv.  The layers are registered both
-    by name and inside `convnet`, which is why the shipped checkpoints carry aliased keys."""
+    by name and inside `convnet`, which is why the shipped checkpoints carry aliased keys; they hold
+    the parameters, the arithmetic runs in the fused kernels."""
+    up_ndim, up_channels, up_act, up_stride2 = 2, 16, "tanh", 1
 
     def __init__(self):
         super().__init__()
@@ -19,8 +22,14 @@ class upscaler(nn.Module):
         self.out = nn.Conv2d(16, 2, 1, 1, padding=0, bias=True)
         self.convnet = nn.Sequential(self.up0, self.tanh, self.out)
 
-    def forward(self, h):
-        return self.convnet(h)
+    def _up_modules(self):
+        return [self.up0, self.out]
+
+
+def get_ic_loss(model):
+    """BUR1:462-471 (= LO1:450-459, BUR3:487-496): mse(UpconvBlock(init_state_low), bicubic align_corners interpolation
+    of the periodically extended init_state_low, last row/column dropped), fused."""
+    return ic_loss(model, "bicubic_periodic")
 
 
 class Stage1Cell(PiCell):

@@ -5,7 +5,7 @@ import torch.nn as nn
 from .. import _lib
 from ..cells import Conv2dDerivative, FusedRCNN, PhysicsCell, derivative_table, laplace_table
 from ..engine import CellSpec
-from ._stage1 import upscaler  # noqa: F401  (BUR3:38-52 is the same upscaler)
+from ._stage1 import get_ic_loss, upscaler  # noqa: F401  (BUR3:38-52, 487-496: the same upscaler and IC loss)
 
 
 class Stage3RCNN(FusedRCNN):

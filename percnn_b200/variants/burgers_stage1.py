@@ -1,5 +1,5 @@
 """Drop-in for Stage-1 Burgers (BUR1:38-303): 5x5 Pi convs on the manually padded state."""
-from ._stage1 import Stage1Cell, Stage1RCNN, upscaler  # noqa: F401
+from ._stage1 import Stage1Cell, Stage1RCNN, get_ic_loss, upscaler  # noqa: F401
 
 
 class RCNNCell(Stage1Cell):

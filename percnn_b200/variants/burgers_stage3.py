@@ -4,7 +4,7 @@ import torch
 from .. import _lib
 from ..cells import Conv2dDerivative, PhysicsCell, derivative_table, laplace_table
 from ..engine import CellSpec
-from ._stage3 import Stage3RCNN, _scalar, upscaler  # noqa: F401
+from ._stage3 import Stage3RCNN, _scalar, get_ic_loss, upscaler  # noqa: F401
 
 
 class RCNNCell(PhysicsCell):

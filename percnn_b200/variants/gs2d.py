@@ -5,14 +5,17 @@ import torch.nn as nn
 
 from .. import _lib, losses
 from ..cells import FusedRCNN, PiCell
+from ..upscaler import FusedUpscaler, ic_loss
 
 
-class upscaler(nn.Module):
-    """Low-res -> full-res initial-state generator (GS2D:26-41): two stride-2 transposed convs.
+class upscaler(FusedUpscaler):
+    """Low-res -> full-res initial-state generator (GS2D:26-41): two stride-2 transposed convs and a 1x1 conv.
 
-    Runs once per rollout and is outside the fused hot path: stock PyTorch modules,
-    registered so that the state_dict keys are `convnet.{0,2,3}.*` like the reference's.
+    The layers are the reference's (same construction order, so the same initial values under a given seed, and the
+    same state_dict keys `convnet.{0,2,3}.*`); they only hold the parameters.  `forward` runs the fused kernels
+    (percnn_upscaler_fwd / _bwd).
     """
+    up_ndim, up_channels, up_act, up_stride2 = 2, 8, "sigmoid", 2
 
     def __init__(self):
         super().__init__()
@@ -24,8 +27,8 @@ class upscaler(nn.Module):
         ]
         self.convnet = nn.Sequential(*self.layers)
 
-    def forward(self, h):
-        return self.convnet(h)
+    def _up_modules(self):
+        return [self.convnet[0], self.convnet[2], self.convnet[3]]
 
 
 class RCNNCell(PiCell):
@@ -63,6 +66,12 @@ class loss_generator(losses.LossGenerator):
 
     def __init__(self, dt=(1.0 / 2), dx=(1.0 / 100)):
         super().__init__(losses.gray_scott_spec(2e-5, 2e-5 / 4, 1 / 25, 3 / 50, dt, dx))
+
+
+def get_ic_loss(model):
+    """GS2D:331-338: mse(UpconvBlock(init_state_low), bicubic interpolation of init_state_low to the output size
+    ((100, 100) for the script's 25 x 25 data)), fused (percnn_mse_fwd / _bwd + the upscaler kernels)."""
+    return ic_loss(model, "bicubic")
 
 
 def loss_gen(output, loss_func):

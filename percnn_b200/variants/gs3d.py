@@ -5,10 +5,13 @@ import torch.nn as nn
 
 from .. import _lib, losses
 from ..cells import FusedRCNN, PiCell
+from ..upscaler import FusedUpscaler, ic_loss
 
 
-class upscaler(nn.Module):
-    """GS3D:41-56 (stock modules, off the hot path): stride-2 then stride-1 transposed conv, 1x1x1 conv."""
+class upscaler(FusedUpscaler):
+    """GS3D:41-56: stride-2 then stride-1 transposed conv, 1x1x1 conv; the registered layers hold the parameters
+    (state_dict keys `convnet.{0,2,3}.*`), the arithmetic runs in the fused kernels."""
+    up_ndim, up_channels, up_act, up_stride2 = 3, 8, "sigmoid", 1
 
     def __init__(self):
         super().__init__()
@@ -20,8 +23,8 @@ class upscaler(nn.Module):
         ]
         self.convnet = nn.Sequential(*self.layers)
 
-    def forward(self, h):
-        return self.convnet(h)
+    def _up_modules(self):
+        return [self.convnet[0], self.convnet[2], self.convnet[3]]
 
 
 class RCNNCell(PiCell):
@@ -61,6 +64,12 @@ class loss_generator(losses.LossGenerator):
 
     def __init__(self, dt=0.5, dx=(100 / 48)):
         super().__init__(losses.gray_scott_spec(0.2, 0.1, 0.025, 0.055, dt, dx))
+
+
+def get_ic_loss(model):
+    """GS3D:325-333: mse(UpconvBlock(init_state_low), trilinear interpolation of init_state_low to the output size
+    ((48, 48, 48) for the script's 24^3 data)), fused."""
+    return ic_loss(model, "trilinear")
 
 
 def loss_func(output, loss_generator):

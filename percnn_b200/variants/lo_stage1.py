@@ -1,6 +1,6 @@
 """Drop-in for Stage-1 lambda-omega (LO1:38-296): same cell with conv-internal circular padding, which is
 the same arithmetic as BUR1's manual padding."""
-from ._stage1 import Stage1Cell, Stage1RCNN, upscaler  # noqa: F401
+from ._stage1 import Stage1Cell, Stage1RCNN, get_ic_loss, upscaler  # noqa: F401
 
 
 class RCNNCell(Stage1Cell):

@@ -4,7 +4,7 @@ import torch
 from .. import _lib
 from ..cells import Conv2dDerivative, PhysicsCell, laplace_table
 from ..engine import CellSpec
-from ._stage3 import Stage3RCNN, _scalar, upscaler  # noqa: F401
+from ._stage3 import Stage3RCNN, _scalar, get_ic_loss, upscaler  # noqa: F401
 
 _INIT = (("nu_u", 0.09465), ("nu_v", 0.09455), ("C1_u", 1.0081), ("C2_u", -1.0167), ("C3_u", 0.9973),
          ("C4_u", -1.0176), ("C5_u", 0.9981), ("C1_v", 0.9873), ("C2_v", -0.9987), ("C3_v", -0.9945),

@@ -190,6 +190,29 @@ def test_fused_losses_fail_loudly_without_cuda():
         cell.rollout_data_loss(torch.zeros(1, 2, 16, 16), 3, torch.zeros(1, 2, 8, 8), [True, False, False, False], 2)
 
 
+def test_fused_upscaler_fails_loudly_without_cuda_and_keeps_the_reference_keys():
+    """The drop-in upscalers hold the reference's layers as parameter containers (same state_dict keys, same initial
+    values under a seed as the stock modules constructed in the same order) and have no CPU path."""
+    import pytest
+    import torch
+    from percnn_b200 import upscaler as up
+    from percnn_b200.variants import burgers_stage1, gs2d, gs3d
+    assert list(gs2d.upscaler().state_dict().keys()) == [f"convnet.{i}.{w}" for i in (0, 2, 3) for w in ("weight", "bias")]
+    assert list(gs3d.upscaler().state_dict().keys()) == [f"convnet.{i}.{w}" for i in (0, 2, 3) for w in ("weight", "bias")]
+    assert list(burgers_stage1.upscaler().state_dict().keys()) == [
+        "up0.weight", "up0.bias", "out.weight", "out.bias", "convnet.0.weight", "convnet.0.bias", "convnet.2.weight", "convnet.2.bias"]
+    torch.manual_seed(7)
+    a = gs2d.upscaler()
+    torch.manual_seed(7)
+    ref0 = torch.nn.ConvTranspose2d(2, 8, kernel_size=5, padding=2, stride=2, output_padding=1, bias=True)
+    assert torch.equal(a.convnet[0].weight, ref0.weight)
+    assert [tuple(p.shape) for p in a.up_parameters()] == [(2, 8, 5, 5), (8,), (8, 8, 5, 5), (8,), (2, 8, 1, 1), (2,)]
+    with pytest.raises(RuntimeError, match="(?i)cuda"):
+        a(torch.zeros(1, 2, 5, 5))
+    with pytest.raises(RuntimeError, match="(?i)cuda"):
+        up.mse(torch.zeros(4), torch.zeros(4))
+
+
 def test_stage3_burgers_checkpoint_with_stale_keys_loads():
     """The shipped Stage-3 Burgers checkpoint carries C3_*/C4_* coefficients of an older script version (SURVEY 8c);
     the drop-in drops them with a warning and still insists on every key it does have."""

@@ -83,3 +83,28 @@ def test_self_ring_training_step_matches_periodic_adjoint(shape):
     g_ref, gp_ref = plan1.rollout_bwd(flat, tape1, w[:, :, 2:nz + 2].contiguous(), [True] * (T + 1), T)
     assert torch.equal(g_h0d, g_ref)
     assert float((gradsd.double() - gp_ref.double()).norm() / gp_ref.double().norm()) <= 1e-6
+
+
+def test_self_ring_initial_state_from_the_sharded_upscaler():
+    """GS3D:186 on a slab: the rank generates its planes of h0 straight into the slab buffer (periodic ghosts come from
+    the exchange, although the transposed convs themselves pad with zeros) and reduces the upscaler's parameter
+    gradient from dL/dh0 with exchanged ghost planes."""
+    from percnn_b200 import upscaler as up
+    from percnn_b200.variants import gs3d
+    torch.manual_seed(8)
+    cell = _cell()
+    ups = gs3d.upscaler().to(DEV)
+    low = torch.rand((1, 2, 8, 8, 64), device=DEV) * 0.8 + 0.1
+    shape = (16, 16, 128)
+    want = ups(low)
+    g = torch.rand((2, *shape), device=DEV) - 0.5
+    ups.zero_grad()
+    (want[0] * g).sum().backward()
+    ref = torch.cat([p.grad.reshape(-1) for p in ups.up_parameters()])
+    slab = halo.SlabRollout(cell, shape, DEV, 0, 1, transport="fused")
+    slab.set_state_from_upscaler(ups, low)
+    assert torch.equal(slab.interior(), want[0].detach())
+    b = slab.bufs[slab.cur]
+    assert torch.equal(b[:, 0:2], b[:, 16:18]) and torch.equal(b[:, 18:20], b[:, 2:4])     # periodic ghosts of the state
+    gp = slab.upscaler_backward(g)
+    assert float((gp - ref).abs().max()) <= 1e-6 * float(ref.abs().max())
