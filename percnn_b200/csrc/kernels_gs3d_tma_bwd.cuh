@@ -17,6 +17,10 @@
 namespace percnn {
 namespace tma3d {
 
+#ifndef PERCNN_BWD_STATIC_STAGE
+#define PERCNN_BWD_STATIC_STAGE 0
+#endif
+static_assert(STAGES == 8, "the static-stage switch of the adjoint enumerates 8 ring stages");
 constexpr int BWD_FLUSH = 32;
 // The adjoint holds 22 running sums and the state on top of the 5-plane window: 15 consumer warps + 1 producer
 // warp = 512 threads = 128 registers per thread (a 17th warp would round the allocation down to 96).
@@ -50,7 +54,10 @@ __device__ __forceinline__ float4 ldg128(const float* p) { return __ldg(reinterp
 // `valid`: this warp's row is not a duplicate of the previous tile's rows (last tile of a column is shifted
 // back), so it contributes to the reductions.
 // `DOWN`: the item is marched towards decreasing z (slab kernel, odd steps); `zstep` = +-plane accordingly.
-template <bool FUSED, bool DOWN>
+// `SS`: the ring stage of the arriving plane as a compile-time constant (PERCNN_BWD_STATIC_STAGE: the caller switches
+// over c.s, so every ring / mbarrier address below is `base + immediate` instead of ~30 integer instructions per
+// plane); SS < 0: use c.s at run time.
+template <bool FUSED, bool DOWN, int SS = -1>
 __device__ __forceinline__ void adjoint_plane(Consumer& c, const float* __restrict__ TP, bool prefetch_seam,
                                               const float* seam_ptr, int64_t field, int64_t zstep, int64_t off,
                                               float* __restrict__ dst, float* mirror, const float* __restrict__ hbase,
@@ -58,7 +65,8 @@ __device__ __forceinline__ void adjoint_plane(Consumer& c, const float* __restri
                                               float2 (&seam_next)[2], float (&aacc)[2], float2* __restrict__ macc,
                                               const Inject<float>& inj, int64_t inj_row, int xq) {
   const float* P = c.P;
-  mbar_wait(&c.full[c.s], c.parity);   // plane k has landed; planes k-4 .. k-1 are still resident
+  const uint32_t cs = SS >= 0 ? uint32_t(SS) : c.s;
+  mbar_wait(&c.full[cs], c.parity);   // plane k has landed; planes k-4 .. k-1 are still resident
   const float2 seam_u = seam_next[0], seam_v = seam_next[1];
   if (prefetch_seam) {
     ldg_f2_if(c.is_seam, seam_ptr, seam_next[0]);
@@ -83,8 +91,8 @@ __device__ __forceinline__ void adjoint_plane(Consumer& c, const float* __restri
     float4 win[5];
 #pragma unroll
     for (int j = 0; j < 5; ++j)   // local plane k-4+j sits in stage (s + STAGES - 4 + j) % STAGES; win[] is ascending in z
-      win[j] = lds128(c.ring + ((c.s + STAGES - (DOWN ? j : 4 - j)) & (STAGES - 1)) * STAGE_FLOATS + f * ROWS * TX + lane_off);
-    const float* sp = c.ring + ((c.s + STAGES - 2) & (STAGES - 1)) * STAGE_FLOATS + f * ROWS * TX + c.row * TX + 4 * c.lane;
+      win[j] = lds128(c.ring + ((cs + STAGES - (DOWN ? j : 4 - j)) & (STAGES - 1)) * STAGE_FLOATS + f * ROWS * TX + lane_off);
+    const float* sp = c.ring + ((cs + STAGES - 2) & (STAGES - 1)) * STAGE_FLOATS + f * ROWS * TX + c.row * TX + 4 * c.lane;
     const float4 y[4] = {lds128(sp), lds128(sp + TX), lds128(sp + 3 * TX), lds128(sp + 4 * TX)};
     const float4 ctr = win[2];
     float Lz = __shfl_up_sync(0xffffffffu, ctr.z, 1), Lw = __shfl_up_sync(0xffffffffu, ctr.w, 1);
@@ -103,7 +111,7 @@ __device__ __forceinline__ void adjoint_plane(Consumer& c, const float* __restri
   // plane k-4 is no longer needed by this warp (release only once the loads have completed, see mbar_arrive_after)
   __syncwarp();
   // (the release must NOT wait for the long-latency global loads of h)
-  if (c.lane == 0) mbar_arrive_after(&c.empty[(c.s + STAGES - 4) & (STAGES - 1)], Lu_lo.x + Lv_lo.x);
+  if (c.lane == 0) mbar_arrive_after(&c.empty[(cs + STAGES - 4) & (STAGES - 1)], Lu_lo.x + Lv_lo.x);
   float4 au4 = make_float4(0.f, 0.f, 0.f, 0.f), av4 = au4;
   if (gadd != nullptr) {
     au4 = ldg128(gadd + off);
@@ -339,8 +347,21 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
         seam_ptr += zstep;
         int64_t inj_row = -1;
         if (inj_ly >= 0 && zi % x.inj.s == 0) inj_row = (int64_t(zi / x.inj.s) * x.inj.lh + inj_ly) * x.inj.lw;
+#if PERCNN_BWD_STATIC_STAGE
+#define PERCNN_BWD_CASE(S)                                                                                              \
+  case S:                                                                                                               \
+    adjoint_plane<false, DOWN, S>(c, TP, k <= ic.nz + 2, seam_ptr, field, zstep, off, p.dst, nullptr, x.h, x.gadd,      \
+                                  k + 1 < nk, valid, seam_next, aacc, macc, x.inj, inj_row, ic.x0 + 4 * lane);          \
+    break;
+        switch (c.s) {
+          PERCNN_BWD_CASE(0) PERCNN_BWD_CASE(1) PERCNN_BWD_CASE(2) PERCNN_BWD_CASE(3)
+          PERCNN_BWD_CASE(4) PERCNN_BWD_CASE(5) PERCNN_BWD_CASE(6) PERCNN_BWD_CASE(7)
+        }
+#undef PERCNN_BWD_CASE
+#else
         adjoint_plane<false, DOWN>(c, TP, k <= ic.nz + 2, seam_ptr, field, zstep, off, p.dst, nullptr, x.h, x.gadd,
                                    k + 1 < nk, valid, seam_next, aacc, macc, x.inj, inj_row, ic.x0 + 4 * lane);
+#endif
         off += zstep;
         if (FUSED && k == 5) slab_consumer_signal<DOWN, 1>(p, item);   // first boundary pair stored: over to the helper
         zi += DOWN ? -1 : 1;

@@ -28,6 +28,8 @@ int up_geom(const percnn_upscaler_t* d, UpGeom* u) {
   if (d->act != 0 && d->act != 1) return fail(PERCNN_ERR_INVALID, "act must be 0 (sigmoid) or 1 (tanh)");
   if (d->layers != 1 && d->layers != 2) return fail(PERCNN_ERR_INVALID, "layers must be 1 or 2");
   if (d->layers == 2 && d->stride2 != 1 && d->stride2 != 2) return fail(PERCNN_ERR_INVALID, "stride2 must be 1 or 2");
+  if (d->layers == 2 && d->ndim == 3 && d->channels == 16)   // (the correlation kernel's thread map: 16 x 25 > 256)
+    return fail(PERCNN_ERR_UNSUPPORTED, "two-layer 3-D upscalers are built for 8 channels (GS3D:46)");
   for (int i = 0; i < 3; ++i)
     if (d->low_extent[i] < 1 || d->low_extent[i] > (1 << 14)) return fail(PERCNN_ERR_INVALID, "bad low-resolution extents");
   if (d->ndim == 2 && d->low_extent[0] != 1) return fail(PERCNN_ERR_INVALID, "2-D needs low_extent[0] == 1");
@@ -83,7 +85,7 @@ int up_geom(const percnn_upscaler_t* d, UpGeom* u) {
   u->off_sums2 = o;
   o += align256(size_t(u->n2) * 8);
   u->off_partials = o;
-  o += align256(size_t(kMaxCorrBlocks) * size_t(u->n1 > u->n2 ? u->n1 : u->n2) * 8);
+  o += align256(size_t(kCorrMaxVB) * size_t(u->n1 > u->n2 ? u->n1 : u->n2) * 8);
   u->off_gmid = o;
   o += align256(size_t(u->own_elems) * elt);
   u->ws_bytes = o;
@@ -138,11 +140,20 @@ int fwd_t(const UpGeom& u, const T* raw, const T* low, T* mid, T* out, char* ws,
 template <typename T>
 int corr(const Grid& ga, const Grid& gb, int ndim, int S, int CA, int CB, int single, const T* A, const T* B, int n, double* partials,
          double* sums, cudaStream_t st) {
-  int64_t nrows = int64_t(ga.nz) * ga.H;
-  const int nb = int(nrows < kMaxCorrBlocks ? (nrows < 1 ? 1 : nrows) : kMaxCorrBlocks);
-  k_up_corr<T><<<nb, kThreads, 0, st>>>(ga, gb, ndim, S, CA, CB, single, A, B, partials);
+  const int64_t nrows = int64_t(ga.nz) * ga.H;
+  int nvb = int(nrows / 4 + 1 < kCorrMaxVB ? nrows / 4 + 1 : kCorrMaxVB);
+  if (nvb > nrows) nvb = int(nrows < 1 ? 1 : nrows);
+  const int cat = CA >= 4 ? 4 : 2;                                   // CA is 2, 8 or 16
+  const int ktaps = single ? 1 : (ndim == 3 ? 25 : 5);               // (kz, ky) pairs
+  const int nth = (CA / cat) * CB * ktaps;
+  const int groups = kThreads / nth;                                 // nth <= 200 for every supported net
+  const int nb = (nvb + groups - 1) / groups;
+  if (cat == 4)
+    k_up_corr<T, 4><<<nb, kThreads, 0, st>>>(ga, gb, ndim, S, CA, CB, single, nvb, A, B, partials);
+  else
+    k_up_corr<T, 2><<<nb, kThreads, 0, st>>>(ga, gb, ndim, S, CA, CB, single, nvb, A, B, partials);
   PERCNN_CUDA(cudaGetLastError());
-  k_up_fold<<<(n + 255) / 256, 256, 0, st>>>(partials, nb, n, sums);
+  k_up_fold<<<(n + 255) / 256, 256, 0, st>>>(partials, nvb, n, sums);
   PERCNN_CUDA(cudaGetLastError());
   return PERCNN_OK;
 }
