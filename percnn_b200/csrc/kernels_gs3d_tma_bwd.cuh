@@ -17,6 +17,9 @@
 namespace percnn {
 namespace tma3d {
 
+#ifndef PERCNN_BWD_REG_MONO
+#define PERCNN_BWD_REG_MONO 0      // 1: the 20 per-lane monomial sums live in registers instead of shared memory
+#endif
 #ifndef PERCNN_BWD_STATIC_STAGE
 #define PERCNN_BWD_STATIC_STAGE 0
 #endif
@@ -41,6 +44,14 @@ struct BwdExtra {
   Inject<float> inj;     // fused data-loss gradient of this step's state (target == nullptr: none)
 };
 
+#if PERCNN_BWD_REG_MONO
+typedef float2 (&MonoAcc)[10];
+#define PERCNN_MACC(M) macc[M]
+#else
+typedef float2* __restrict__ MonoAcc;
+#define PERCNN_MACC(M) macc[(M) * BWD_THREADS]
+#endif
+
 __device__ __forceinline__ float2 quad2(const float* __restrict__ d, float2 u, float2 v) {
   float2 a0 = fma2(u, fma2(u, d[3], d[1]), d[0]);
   float2 a1 = fma2(u, d[4], d[2]);
@@ -62,7 +73,7 @@ __device__ __forceinline__ void adjoint_plane(Consumer& c, const float* __restri
                                               const float* seam_ptr, int64_t field, int64_t zstep, int64_t off,
                                               float* __restrict__ dst, float* mirror, const float* __restrict__ hbase,
                                               const float* __restrict__ gadd, bool prefetch_next, bool valid,
-                                              float2 (&seam_next)[2], float (&aacc)[2], float2* __restrict__ macc,
+                                              float2 (&seam_next)[2], float (&aacc)[2], MonoAcc macc,
                                               const Inject<float>& inj, int64_t inj_row, int xq) {
   const float* P = c.P;
   const uint32_t cs = SS >= 0 ? uint32_t(SS) : c.s;
@@ -155,11 +166,11 @@ __device__ __forceinline__ void adjoint_plane(Consumer& c, const float* __restri
     const float2 el = EL, eh = EH;                                                                  \
     const float2 tu = fma2(guh, eh, __fmul2_rn(gul, el));                                           \
     const float2 tv = fma2(gvh, eh, __fmul2_rn(gvl, el));                                           \
-    macc[M * BWD_THREADS] = __fadd2_rn(macc[M * BWD_THREADS], make_float2(tu.x + tu.y, tv.x + tv.y)); \
+    PERCNN_MACC(M) = __fadd2_rn(PERCNN_MACC(M), make_float2(tu.x + tu.y, tv.x + tv.y));             \
   }
     {
       const float2 tu = __fadd2_rn(gul, guh), tv = __fadd2_rn(gvl, gvh);
-      macc[0] = __fadd2_rn(macc[0], make_float2(tu.x + tu.y, tv.x + tv.y));
+      PERCNN_MACC(0) = __fadd2_rn(PERCNN_MACC(0), make_float2(tu.x + tu.y, tv.x + tv.y));
     }
     PERCNN_MONO(1, ul, uh)
     PERCNN_MONO(2, vl, vh)
@@ -293,7 +304,13 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
   float2 seam_next[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
   float aacc[2] = {0.f, 0.f};
   int since_flush = 0;
+#if PERCNN_BWD_REG_MONO
+  float2 macc[10];
+#pragma unroll
+  for (int m = 0; m < 10; ++m) macc[m] = make_float2(0.f, 0.f);
+#else
   float2* macc = macc_all + threadIdx.x;
+#endif
   auto flush = [&]() {   // per-lane fp32 partial sums -> per-warp fp64 accumulators (every BWD_FLUSH planes)
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -304,9 +321,10 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
       aacc[i] = 0.f;
     }
     const float dt = c.P[P_DT];
+#pragma unroll
     for (int m = 0; m < 10; ++m) {
-      float2 t = macc[m * BWD_THREADS];
-      macc[m * BWD_THREADS] = make_float2(0.f, 0.f);
+      float2 t = PERCNN_MACC(m);
+      PERCNN_MACC(m) = make_float2(0.f, 0.f);
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) {
         t.x += __shfl_down_sync(0xffffffffu, t.x, off);

@@ -14,31 +14,40 @@ namespace percnn {
 namespace k5 {
 
 constexpr int CELLS = 4;
+#ifndef K5_FWD_MIN_BLOCKS
+#define K5_FWD_MIN_BLOCKS 4
+#endif
 constexpr int BX = 8, BY = 16;
 constexpr int THREADS = BX * BY;
 constexpr int TILE_X = BX * CELLS, TILE_Y = BY;
 constexpr int SM_W = TILE_X + 8;   // 4 halo columns each side (2 used) keeps rows float4-aligned
 constexpr int SM_H = TILE_Y + 4;
 
-__host__ __device__ inline size_t smem_bytes(int hc) { return size_t(2 * SM_H * SM_W + k5_total_floats(hc)) * 4; }
+__host__ __device__ inline size_t smem_bytes(int hc) { return size_t(2 * SM_H * SM_W + k5_total_floats(hc) - k5_weight_floats(hc) / 2) * 4; }
 
 __device__ __forceinline__ float2 ffma2_bs(float s, float2 w, float2 acc) { return __ffma2_rn(make_float2(s, s), w, acc); }
 
-__global__ void __launch_bounds__(THREADS) k_pi_k5_fwd(Geom g, int slot, int hc, const float* __restrict__ src,
+// One block = one 32 x 16 tile of ONE output field q = blockIdx.z: the two output fields share nothing but the input
+// tile, and 2 x 512 half-size blocks spread over the 148 SMs far more evenly than 512 full ones (0.86 waves of 4
+// resident blocks left a quarter of the SMs idle for a quarter of the kernel); a block also stages only its field's
+// half of the weights.
+__global__ void __launch_bounds__(THREADS, K5_FWD_MIN_BLOCKS) k_pi_k5_fwd(Geom g, int slot, int hc, const float* __restrict__ src,
                                                        float* __restrict__ dst, const float* __restrict__ k5w) {
   extern __shared__ __align__(16) float smem[];
   float* tile = smem;                       // [2][SM_H][SM_W]
-  float* wsm = smem + 2 * SM_H * SM_W;      // repacked weights
+  float* wsm = smem + 2 * SM_H * SM_W;      // this field's conv weights, then bias | w4 | b4 of both fields
   const float* P = c_prep[slot].f;
   const int ncp = hc / 2;
   const int x0 = blockIdx.x * TILE_X, y0 = blockIdx.y * TILE_Y;
+  const int q = blockIdx.z;
+  const int wq = k5_weight_floats(hc) / 2;  // conv weights of one field
 
-  {  // weights: straight float4 copy
-    const int n4 = k5_total_floats(hc) / 4;
-    const float4* s4 = reinterpret_cast<const float4*>(k5w);
+  {  // weights: straight float4 copies (both regions are 16-byte aligned: wq and k5_weight_floats are multiples of 32)
+    const float4* s4 = reinterpret_cast<const float4*>(k5w + q * wq);
     float4* d4 = reinterpret_cast<float4*>(wsm);
-    for (int i = threadIdx.x; i < n4; i += THREADS) d4[i] = __ldg(s4 + i);
-    for (int i = n4 * 4 + threadIdx.x; i < k5_total_floats(hc); i += THREADS) wsm[i] = __ldg(k5w + i);
+    for (int i = threadIdx.x; i < wq / 4; i += THREADS) d4[i] = __ldg(s4 + i);
+    const int ntail = k5_total_floats(hc) - k5_weight_floats(hc);
+    for (int i = threadIdx.x; i < ntail; i += THREADS) wsm[wq + i] = __ldg(k5w + k5_weight_floats(hc) + i);
   }
   // state tile with periodic halo (rows: ghost-aware in slab mode)
   for (int e = threadIdx.x; e < 2 * SM_H * SM_W; e += THREADS) {
@@ -61,76 +70,69 @@ __global__ void __launch_bounds__(THREADS) k_pi_k5_fwd(Geom g, int slot, int hc,
   __syncthreads();
 
   const int tx = threadIdx.x % BX, ty = threadIdx.x / BX;
-  const float* bias = wsm + k5_weight_floats(hc);
+  const float* bias = wsm + wq;
   const float* w4 = bias + 2 * 3 * hc;
-  float R[2][CELLS];
+  float R[CELLS];
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
+  for (int j = 0; j < CELLS; ++j) R[j] = w4[2 * hc + q];
+  for (int cp = 0; cp < ncp; ++cp) {
+    float2 acc[3][CELLS];
 #pragma unroll
-    for (int j = 0; j < CELLS; ++j) R[q][j] = w4[2 * hc + q];
-    for (int cp = 0; cp < ncp; ++cp) {
-      float2 acc[3][CELLS];
+    for (int i = 0; i < 3; ++i) {
+      const float2 b = *reinterpret_cast<const float2*>(bias + (q * 3 + i) * hc + 2 * cp);
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const float2 b = *reinterpret_cast<const float2*>(bias + (q * 3 + i) * hc + 2 * cp);
+      for (int j = 0; j < CELLS; ++j) acc[i][j] = b;
+    }
 #pragma unroll
-        for (int j = 0; j < CELLS; ++j) acc[i][j] = b;
-      }
+    for (int f = 0; f < 2; ++f) {
 #pragma unroll
-      for (int f = 0; f < 2; ++f) {
+      for (int dy = 0; dy < 5; ++dy) {
+        const float4* trow = reinterpret_cast<const float4*>(tile + (f * SM_H + ty + dy) * SM_W + 4 * tx);
+        const float4 d0 = trow[0], d1 = trow[1], d2 = trow[2];
+        const float d[12] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w, d2.x, d2.y, d2.z, d2.w};
+        const float4* wrow = reinterpret_cast<const float4*>(wsm + (((cp * 2 + f) * 5 + dy) * kK5RowFloats));
+        float wr[32];
 #pragma unroll
-        for (int dy = 0; dy < 5; ++dy) {
-          const float4* trow = reinterpret_cast<const float4*>(tile + (f * SM_H + ty + dy) * SM_W + 4 * tx);
-          const float4 d0 = trow[0], d1 = trow[1], d2 = trow[2];
-          const float d[12] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w, d2.x, d2.y, d2.z, d2.w};
-          const float4* wrow =
-              reinterpret_cast<const float4*>(wsm + ((((q * ncp + cp) * 2 + f) * 5 + dy) * kK5RowFloats));
-          float wr[32];
-#pragma unroll
-          for (int v = 0; v < 8; ++v) {
-            const float4 t = wrow[v];
-            wr[4 * v + 0] = t.x; wr[4 * v + 1] = t.y; wr[4 * v + 2] = t.z; wr[4 * v + 3] = t.w;
-          }
-#pragma unroll
-          for (int dx = 0; dx < 5; ++dx)
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-              const float2 wp = make_float2(wr[(dx * 3 + i) * 2], wr[(dx * 3 + i) * 2 + 1]);
-#pragma unroll
-              for (int j = 0; j < CELLS; ++j) acc[i][j] = ffma2_bs(d[2 + dx + j], wp, acc[i][j]);
-            }
+        for (int v = 0; v < 8; ++v) {
+          const float4 t = wrow[v];
+          wr[4 * v + 0] = t.x; wr[4 * v + 1] = t.y; wr[4 * v + 2] = t.z; wr[4 * v + 3] = t.w;
         }
-      }
-      const float2 w4p = *reinterpret_cast<const float2*>(w4 + q * hc + 2 * cp);
 #pragma unroll
-      for (int j = 0; j < CELLS; ++j) {
-        const float2 pr = __fmul2_rn(__fmul2_rn(acc[0][j], acc[1][j]), acc[2][j]);
-        R[q][j] = fmaf(w4p.y, pr.y, fmaf(w4p.x, pr.x, R[q][j]));
+        for (int dx = 0; dx < 5; ++dx)
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const float2 wp = make_float2(wr[(dx * 3 + i) * 2], wr[(dx * 3 + i) * 2 + 1]);
+#pragma unroll
+            for (int j = 0; j < CELLS; ++j) acc[i][j] = ffma2_bs(d[2 + dx + j], wp, acc[i][j]);
+          }
       }
+    }
+    const float2 w4p = *reinterpret_cast<const float2*>(w4 + q * hc + 2 * cp);
+#pragma unroll
+    for (int j = 0; j < CELLS; ++j) {
+      const float2 pr = __fmul2_rn(__fmul2_rn(acc[0][j], acc[1][j]), acc[2][j]);
+      R[j] = fmaf(w4p.y, pr.y, fmaf(w4p.x, pr.x, R[j]));
     }
   }
   const int y = y0 + ty;
   if (y >= g.H) return;
+  const float* t = tile + (q * SM_H + ty + 2) * SM_W + 4 * tx + 4;
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const float* t = tile + (q * SM_H + ty + 2) * SM_W + 4 * tx + 4;
-#pragma unroll
-    for (int j = 0; j < CELLS; ++j) {
-      const int x = x0 + 4 * tx + j;
-      if (x >= g.W) continue;
-      const float* c = t + j;
-      float L = P[P_LAP_C0] * c[0];
-      L = fmaf(P[P_LAP_AX + 0], c[-2 * SM_W], L);
-      L = fmaf(P[P_LAP_AX + 1], c[-1 * SM_W], L);
-      L = fmaf(P[P_LAP_AX + 2], c[1 * SM_W], L);
-      L = fmaf(P[P_LAP_AX + 3], c[2 * SM_W], L);
-      L = fmaf(P[P_LAP_AX + 4], c[-2], L);
-      L = fmaf(P[P_LAP_AX + 5], c[-1], L);
-      L = fmaf(P[P_LAP_AX + 6], c[1], L);
-      L = fmaf(P[P_LAP_AX + 7], c[2], L);
-      const float res = fmaf(P[P_ALPHA + q], L, R[q][j]);
-      dst[q * g.field + int64_t(y + g.ghost) * g.W + x] = fmaf(res, P[P_DT], c[0]);
-    }
+  for (int j = 0; j < CELLS; ++j) {
+    const int x = x0 + 4 * tx + j;
+    if (x >= g.W) continue;
+    const float* c = t + j;
+    float L = P[P_LAP_C0] * c[0];
+    L = fmaf(P[P_LAP_AX + 0], c[-2 * SM_W], L);
+    L = fmaf(P[P_LAP_AX + 1], c[-1 * SM_W], L);
+    L = fmaf(P[P_LAP_AX + 2], c[1 * SM_W], L);
+    L = fmaf(P[P_LAP_AX + 3], c[2 * SM_W], L);
+    L = fmaf(P[P_LAP_AX + 4], c[-2], L);
+    L = fmaf(P[P_LAP_AX + 5], c[-1], L);
+    L = fmaf(P[P_LAP_AX + 6], c[1], L);
+    L = fmaf(P[P_LAP_AX + 7], c[2], L);
+    const float res = fmaf(P[P_ALPHA + q], L, R[j]);
+    dst[q * g.field + int64_t(y + g.ghost) * g.W + x] = fmaf(res, P[P_DT], c[0]);
   }
 }
 
@@ -161,7 +163,9 @@ constexpr int R2_CELLS = R2_W * R2_H;
 constexpr int SLICE_FLOATS = 2 * 5 * 5 * 3 * 2;   // (f, dy, dx, i, channel of the pair) = 300
 
 __host__ __device__ inline size_t bwd_smem_floats(int hc, int nparams) {
-  return size_t(2 * R4_H * R4_W + 2 * R2_H * R2_W + 3 * R2_CELLS * 2 + k5_total_floats(hc) + BT_Y * SLICE_FLOATS + nparams + 64);
+  (void)nparams;   // every parameter sum is produced by exactly one (q, cp) stage, so the block writes it straight to its
+                   // global partial vector: no block-wide accumulator array (it cost 19.7 KB and the 4th resident block)
+  return size_t(2 * R4_H * R4_W + 2 * R2_H * R2_W + 3 * R2_CELLS * 2 + k5_total_floats(hc) + BT_Y * SLICE_FLOATS + 64);
 }
 
 __global__ void __launch_bounds__(BTHREADS) k_pi_k5_bwd(Geom g, int slot, int hc, int nparams, const float* __restrict__ h,
@@ -174,8 +178,9 @@ __global__ void __launch_bounds__(BTHREADS) k_pi_k5_bwd(Geom g, int slot, int hc
   float2* sgbar = reinterpret_cast<float2*>(sg + 2 * R2_H * R2_W);   // [3][R2_CELLS]
   float* wsm = reinterpret_cast<float*>(sgbar + 3 * R2_CELLS);
   float* sslice = wsm + k5_total_floats(hc);          // [BT_Y][SLICE_FLOATS]
-  float* sacc = sslice + BT_Y * SLICE_FLOATS;         // [nparams] block accumulators, raw packing
-  float* sred = sacc + nparams;                       // [64] scratch for small reductions
+  float* sred = sslice + BT_Y * SLICE_FLOATS;         // [64] scratch for small reductions
+  // this block's partial parameter sums, raw packing; each entry is written exactly once (by the stage that owns it)
+  float* out = partials + size_t(blockIdx.y * gridDim.x + blockIdx.x) * nparams;
   const float* P = c_prep[slot].f;
   const PiPacking pk(2, 5, hc);
   const int ncp = hc / 2;
@@ -183,7 +188,7 @@ __global__ void __launch_bounds__(BTHREADS) k_pi_k5_bwd(Geom g, int slot, int hc
   const int x0 = blockIdx.x * BT_X, y0 = blockIdx.y * BT_Y;
   const float dt = P[P_DT];
 
-  for (int i = tid; i < nparams; i += BTHREADS) sacc[i] = 0.f;
+  for (int i = 2 + tid; i < 2 + 25; i += BTHREADS) out[i] = 0.f;   // the frozen Laplacian table gets no gradient
   {
     const int n4 = k5_total_floats(hc) / 4;
     const float4* s4 = reinterpret_cast<const float4*>(k5w);
@@ -308,7 +313,7 @@ __global__ void __launch_bounds__(BTHREADS) k_pi_k5_bwd(Geom g, int slot, int hc
         const int c = 2 * cp + (tid & 1);
         const int which = tid >> 1;   // 0: W4, 1..3: bias of conv which-1
         const int idx = which == 0 ? pk.w4(q) + c : pk.b(q, which - 1) + c;
-        sacc[idx] += v;
+        out[idx] = v;
       }
       // ================= phase 2: transposed conv into gacc (field f2) =================
       {
@@ -385,7 +390,7 @@ __global__ void __launch_bounds__(BTHREADS) k_pi_k5_bwd(Geom g, int slot, int hc
         for (int r = 0; r < BT_Y; ++r) v += sslice[r * SLICE_FLOATS + e];
         const int ch = e & 1, i = (e >> 1) % 3, dx = (e / 6) % 5, dy = (e / 30) % 5, f = e / 150;
         const int c = 2 * cp + ch;
-        sacc[pk.w(q, i) + ((c * 2 + f) * 5 + dy) * 5 + dx] += v;
+        out[pk.w(q, i) + ((c * 2 + f) * 5 + dy) * 5 + dx] = v;
       }
       __syncthreads();
     }
@@ -429,12 +434,9 @@ __global__ void __launch_bounds__(BTHREADS) k_pi_k5_bwd(Geom g, int slot, int hc
   }
   __syncthreads();
   if (tid < 2) {   // warps 0,1 hold field 0; warps 2,3 field 1
-    sacc[tid] += sred[32 + (2 * tid) * 2] + sred[32 + (2 * tid + 1) * 2];                    // alpha_f
-    sacc[pk.w4(tid) + hc] += sred[32 + (2 * tid) * 2 + 1] + sred[32 + (2 * tid + 1) * 2 + 1];  // b4_f
+    out[tid] = sred[32 + (2 * tid) * 2] + sred[32 + (2 * tid + 1) * 2];                    // alpha_f
+    out[pk.w4(tid) + hc] = sred[32 + (2 * tid) * 2 + 1] + sred[32 + (2 * tid + 1) * 2 + 1];  // b4_f
   }
-  __syncthreads();
-  float* out = partials + size_t(blockIdx.y * gridDim.x + blockIdx.x) * nparams;
-  for (int i = tid; i < nparams; i += BTHREADS) out[i] = sacc[i];
 }
 
 // acc[i] += sum over blocks (fixed order, fp64) of partials[b][i]

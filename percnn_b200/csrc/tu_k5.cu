@@ -25,7 +25,7 @@ int k5_setup(percnn_plan* p) {
 }
 
 int k5_step_fwd(percnn_plan* p, const float* src, float* dst, cudaStream_t st) {
-  dim3 grid((p->g.W + k5::TILE_X - 1) / k5::TILE_X, (p->g.H + k5::TILE_Y - 1) / k5::TILE_Y);
+  dim3 grid((p->g.W + k5::TILE_X - 1) / k5::TILE_X, (p->g.H + k5::TILE_Y - 1) / k5::TILE_Y, 2);   // z = output field
   k5::k_pi_k5_fwd<<<grid, k5::THREADS, k5::smem_bytes(p->desc.hidden), st>>>(p->g, p->slot, p->desc.hidden, src, dst,
                                                                               p->d_k5w);
   PERCNN_CUDA(cudaGetLastError());

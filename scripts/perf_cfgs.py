@@ -110,17 +110,25 @@ def train_phys_case(name, tag, alias, shape, nsteps, lo, hi):
     print(f"{name:34s} f+b  {nsteps:5d} steps: {ms:9.3f} ms  {ms/nsteps*1e3:8.2f} us/step  (rollout + fused physics loss + adjoint)", flush=True)
 
 
-fwd_case("cfg1 lambda-omega 128^2 fp64", "fwd", "fwd", (128, 128), 200, -0.8, 0.8)
-train_phys_case("cfg1 lambda-omega 128^2 fp64 epoch", "fwd", "fwd", (128, 128), 200, -0.8, 0.8)
-fwd_case("cfg2 GS 256^2 fp32", "gs2d", "gs2d", (256, 256), 1000)
-fwd_case("cfg3i Burgers k5 512^2 fp32", "bur1", "bur1", (512, 512), 40, -0.5, 0.5)
-train_case("cfg3i Burgers k5 512^2 fp32", "bur1", "bur1", (512, 512), 40, -0.5, 0.5)
-fwd_case("cfg3ii Burgers phys 512^2 fp64", "bur3", None, (512, 512), 40, -0.5, 0.5)
-train_case("cfg3ii Burgers phys 512^2 fp64", "bur3", None, (512, 512), 40, -0.5, 0.5)
-fwd_case("cfg4 GS3D 128^3 fp32", "gs3d", "gs3d", (128, 128, 128), 500)
-train_case("GS3D 128^3 fp32 (TMA adjoint)", "gs3d", "gs3d", (128, 128, 128), 20)
-train_case("GS3D 256^3 fp32 (TMA adjoint)", "gs3d", "gs3d", (256, 256, 256), 20)
-train_fused_loss_case("GS3D 256^3 fp32 (TMA adjoint)", "gs3d", "gs3d", (256, 256, 256), 20)
-train_case("GS2D 256^2 fp32", "gs2d", "gs2d", (256, 256), 200)
-fwd_case("ref-size GS3D 48^3", "gs3d", "gs3d", (48, 48, 48), 300)
-fwd_case("ref-size GS2D 100^2", "gs2d", "gs2d", (100, 100), 400)
+ONLY = os.environ.get("PERF_ONLY", "")     # e.g. PERF_ONLY=cfg3i: run only the cases whose name contains the string
+
+
+def _run(fn, name, *a):
+    if ONLY in name:
+        fn(name, *a)
+
+
+_run(fwd_case, "cfg1 lambda-omega 128^2 fp64", "fwd", "fwd", (128, 128), 200, -0.8, 0.8)
+_run(train_phys_case, "cfg1 lambda-omega 128^2 fp64 epoch", "fwd", "fwd", (128, 128), 200, -0.8, 0.8)
+_run(fwd_case, "cfg2 GS 256^2 fp32", "gs2d", "gs2d", (256, 256), 1000)
+_run(fwd_case, "cfg3i Burgers k5 512^2 fp32", "bur1", "bur1", (512, 512), 40, -0.5, 0.5)
+_run(train_case, "cfg3i Burgers k5 512^2 fp32", "bur1", "bur1", (512, 512), 40, -0.5, 0.5)
+_run(fwd_case, "cfg3ii Burgers phys 512^2 fp64", "bur3", None, (512, 512), 40, -0.5, 0.5)
+_run(train_case, "cfg3ii Burgers phys 512^2 fp64", "bur3", None, (512, 512), 40, -0.5, 0.5)
+_run(fwd_case, "cfg4 GS3D 128^3 fp32", "gs3d", "gs3d", (128, 128, 128), 500)
+_run(train_case, "GS3D 128^3 fp32 (TMA adjoint)", "gs3d", "gs3d", (128, 128, 128), 20)
+_run(train_case, "GS3D 256^3 fp32 (TMA adjoint)", "gs3d", "gs3d", (256, 256, 256), 20)
+_run(train_fused_loss_case, "GS3D 256^3 fp32 (TMA adjoint)", "gs3d", "gs3d", (256, 256, 256), 20)
+_run(train_case, "GS2D 256^2 fp32", "gs2d", "gs2d", (256, 256), 200)
+_run(fwd_case, "ref-size GS3D 48^3", "gs3d", "gs3d", (48, 48, 48), 300)
+_run(fwd_case, "ref-size GS2D 100^2", "gs2d", "gs2d", (100, 100), 400)
