@@ -18,7 +18,7 @@ namespace percnn {
 namespace tma3d {
 
 #ifndef PERCNN_BWD_REG_MONO
-#define PERCNN_BWD_REG_MONO 0      // 1: the 20 per-lane monomial sums live in registers instead of shared memory
+#define PERCNN_BWD_REG_MONO 1      // 1: the 20 per-lane monomial sums live in registers (0: shared memory, round 1)
 #endif
 #ifndef PERCNN_BWD_STATIC_STAGE
 #define PERCNN_BWD_STATIC_STAGE 0
@@ -151,8 +151,10 @@ __device__ __forceinline__ void adjoint_plane(Consumer& c, const float* __restri
   PERCNN_BWD_PAIR(hi(hu), hi(hv), hi(Gu), hi(Gv), Lu_hi, Lv_hi, ou.z, ou.w, ov.z, ov.w, au4.z, au4.w, av4.z, av4.w)
 #undef PERCNN_BWD_PAIR
   if (valid) {
-    // 20 monomial sums  sum G_f u^a v^b  for this lane's 4 cells, added to per-lane accumulators in shared memory
-    // (keeping them in registers next to the stencil state spilled).  Everything stays in the NATURAL register pairs
+    // 20 monomial sums  sum G_f u^a v^b  for this lane's 4 cells, added to per-lane accumulators: 10 float2 registers
+    // (round 1 kept them in shared memory because the windowed kernel spilled with them; the windowless one holds them
+    // at exactly 128 registers, no spills, and sheds 10 LDS.64 + 10 STS.64 per plane: 813 -> 760 us per 512^3 step,
+    // profiles/r02_adjoint_variants.txt).  Everything stays in the NATURAL register pairs
     // of the 128-bit loads -- (cell0, cell1) and (cell2, cell3) -- so that no operand has to be re-packed: monomials
     // by FMUL2, products by FMUL2/FFMA2, then one FADD per field folds the pair and (sum_u, sum_v) is the float2
     // that is accumulated.  (Packing (G_u, G_v) per cell instead cost ~80 MOVs per plane: ncu r01b_ncu_bwd_512.)
@@ -234,7 +236,11 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
   }
   float2* macc_all = reinterpret_cast<float2*>(wacc + 16 * kRedPiK1);   // [10][BWD_THREADS] per-lane monomial sums
   for (int i = threadIdx.x; i < TY * kRedPiK1; i += BWD_THREADS) wacc[i] = 0.0;
+#if !PERCNN_BWD_REG_MONO
   for (int m = 0; m < 10; ++m) macc_all[m * BWD_THREADS + threadIdx.x] = make_float2(0.f, 0.f);
+#else
+  (void)macc_all;
+#endif
   __syncthreads();
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // see the forward kernel
   if (FUSED && warp == BWD_WARPS && lane == 0)   // the ghost pair this march starts from: overlaps the previous kernel's tail

@@ -333,60 +333,35 @@ __global__ void __launch_bounds__(kThreads) k_up_gmid2(Grid gmid, Grid gout, int
 // R[ca][cb][k] = sum_o A[ca, o] B[cb, (o + 2 - k) / S]  over the valid taps (the weight gradient of a transposed conv
 // whose input is B and whose output gradient is A), followed by CA plain sums  R[CA CB K + ca] = sum_o A[ca, o].
 // `single_tap`: K = 1, the centre tap only (B on the same grid as A): the 1x1 conv's weight gradient.
-// Thread = (chunk of CAT channels of A, cb, kz, ky): it walks its rows along x with the CAT x 5 sums of the five kx taps
-// in registers (row sums in T, added to fp64 totals after every row), so one B value feeds CAT multiply-adds and the A
-// values are shared by the five taps.  A "virtual block" (one thread group) owns a contiguous range of A rows and
-// writes one fp64 partial vector; k_up_fold adds the vectors in fixed order (deterministic).
+// A block owns a contiguous range of A rows (one fp64 partial vector per block, added up by k_up_fold in fixed order:
+// deterministic).  Inside it a WARP takes one (chunk of CAT channels of A, cb, kz, ky) combination at a time and its
+// lanes stride along x, so the loads of A and of the five kx-shifted B values are coalesced; every lane keeps the
+// CAT x 5 sums of the five kx taps in registers and a shuffle tree folds the lanes once per combination.
+// (A first version gave every THREAD its own combination: 32 different rows per load instruction, bound by L1
+// sector traffic at 1 % of the FP32 pipe.)
 constexpr int kCorrMaxVB = 1184;
 template <typename T, int CAT>
-__global__ void __launch_bounds__(kThreads) k_up_corr(Grid ga, Grid gb, int ndim, int S, int CA, int CB, int single_tap, int nvb,
+__global__ void __launch_bounds__(kThreads) k_up_corr(Grid ga, Grid gb, int ndim, int S, int CA, int CB, int single_tap,
                                                       const T* __restrict__ A, const T* __restrict__ B,
                                                       double* __restrict__ partials) {
   const int KZ = single_tap ? 1 : (ndim == 3 ? 5 : 1);
   const int KY = single_tap ? 1 : 5;
-  const int KX = KY;
-  const int K = KZ * KY * KX;
+  const int K = KZ * KY * KY;
   const int NS = CA * CB * K;
-  const int nchunk = CA / CAT;
-  const int nth = nchunk * CB * KZ * KY;            // threads of one group
-  const int groups = blockDim.x / nth;
-  const int grp = threadIdx.x / nth, t = threadIdx.x - grp * nth;
-  const int vb = blockIdx.x * groups + grp;
-  if (grp >= groups || vb >= nvb) return;
-  const int kyi = t % KY, kzi = (t / KY) % KZ;      // tap indices (0 when the axis has a single tap)
-  const int ky = single_tap ? 2 : kyi;
-  const int kz = KZ == 1 ? 2 : kzi;                 // (no z axis / single tap: the centre, offset 0)
-  const int cb = (t / (KY * KZ)) % CB;
-  const int chunk = t / (KY * KZ * CB);
-  const bool sums_too = cb == 0 && kyi == 0 && kzi == 0;   // one thread per chunk also adds up A itself
+  const int ncombo = (CA / CAT) * CB * KZ * KY;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int64_t nrows = int64_t(ga.nz) * ga.H;
-  const int64_t r0 = nrows * vb / nvb, r1 = nrows * (vb + 1) / nvb;
-  double tot[CAT][5], stot[CAT];
-#pragma unroll
-  for (int c = 0; c < CAT; ++c) {
-    stot[c] = 0;
-#pragma unroll
-    for (int k = 0; k < 5; ++k) tot[c][k] = 0;
-  }
-  const T* a0 = A + int64_t(chunk * CAT) * ga.cstride;
-  const T* b0 = B + int64_t(cb) * gb.cstride;
-  for (int64_t r = r0; r < r1; ++r) {
-    const int y = int(r % ga.H), z = ga.z0 + int(r / ga.H);
-    bool row_ok = true;
-    int iz = gb.z0, iy = 0;
-    if (ndim == 3) {
-      const int nz = z + 2 - kz;
-      row_ok = nz >= 0 && (nz % S) == 0 && nz / S < gb.D;
-      iz = nz / S;
-    }
-    {
-      const int ny = y + 2 - ky;
-      row_ok = row_ok && ny >= 0 && (ny % S) == 0 && ny / S < gb.H;
-      iy = ny / S;
-    }
-    if (!row_ok && !sums_too) continue;
-    const T* arow = a0 + r * ga.W;
-    const T* brow = b0 + (row_ok ? at(gb, iz, iy, 0) : 0);
+  const int64_t r0 = nrows * blockIdx.x / gridDim.x, r1 = nrows * (blockIdx.x + 1) / gridDim.x;
+  double* out = partials + size_t(blockIdx.x) * (NS + CA);
+  for (int combo = warp; combo < ncombo; combo += nwarps) {
+    const int kyi = combo % KY, kzi = (combo / KY) % KZ;      // tap indices (0 when the axis has a single tap)
+    const int ky = single_tap ? 2 : kyi;
+    const int kz = KZ == 1 ? 2 : kzi;                         // (no z axis / single tap: the centre, offset 0)
+    const int cb = (combo / (KY * KZ)) % CB;
+    const int chunk = combo / (KY * KZ * CB);
+    const bool sums_too = cb == 0 && kyi == 0 && kzi == 0;    // one combination per chunk also adds up A itself
+    const T* a0 = A + int64_t(chunk * CAT) * ga.cstride;
+    const T* b0 = B + int64_t(cb) * gb.cstride;
     T acc[CAT][5], sacc[CAT];
 #pragma unroll
     for (int c = 0; c < CAT; ++c) {
@@ -394,44 +369,68 @@ __global__ void __launch_bounds__(kThreads) k_up_corr(Grid ga, Grid gb, int ndim
 #pragma unroll
       for (int k = 0; k < 5; ++k) acc[c][k] = T(0);
     }
-    for (int x = 0; x < ga.W; ++x) {
-      T a[CAT];
-#pragma unroll
-      for (int c = 0; c < CAT; ++c) {
-        a[c] = __ldg(arow + int64_t(c) * ga.cstride + x);
-        sacc[c] += a[c];
+    for (int64_t r = r0; r < r1; ++r) {
+      const int y = int(r % ga.H), z = ga.z0 + int(r / ga.H);
+      bool row_ok = true;
+      int iz = gb.z0, iy = 0;
+      if (ndim == 3) {
+        const int nz = z + 2 - kz;
+        row_ok = nz >= 0 && (nz % S) == 0 && nz / S < gb.D;
+        iz = nz / S;
       }
-      if (!row_ok) continue;
+      {
+        const int ny = y + 2 - ky;
+        row_ok = row_ok && ny >= 0 && (ny % S) == 0 && ny / S < gb.H;
+        iy = ny / S;
+      }
+      if (!row_ok && !sums_too) continue;
+      const T* arow = a0 + r * ga.W;
+      const T* brow = b0 + (row_ok ? at(gb, iz, iy, 0) : 0);
+      for (int x = lane; x < ga.W; x += 32) {
+        T a[CAT];
+#pragma unroll
+        for (int c = 0; c < CAT; ++c) {
+          a[c] = __ldg(arow + int64_t(c) * ga.cstride + x);
+          sacc[c] += a[c];
+        }
+        if (!row_ok) continue;
+#pragma unroll
+        for (int kx = 0; kx < 5; ++kx) {
+          if (single_tap && kx != 2) continue;
+          const int nx = x + 2 - kx;
+          if (nx < 0 || (nx % S) != 0) continue;
+          const int ix = nx / S;
+          if (ix >= gb.W) continue;
+          const T bv = __ldg(brow + ix);
+#pragma unroll
+          for (int c = 0; c < CAT; ++c) acc[c][kx] = fma_t(a[c], bv, acc[c][kx]);
+        }
+      }
+    }
+    // fold the lanes (fixed shuffle tree), lane 0 stores
+#pragma unroll
+    for (int c = 0; c < CAT; ++c) {
+      const int ca = chunk * CAT + c;
 #pragma unroll
       for (int kx = 0; kx < 5; ++kx) {
         if (single_tap && kx != 2) continue;
-        const int nx = x + 2 - kx;
-        if (nx < 0 || (nx % S) != 0) continue;
-        const int ix = nx / S;
-        if (ix >= gb.W) continue;
-        const T bv = __ldg(brow + ix);
+        double v = double(acc[c][kx]);
 #pragma unroll
-        for (int c = 0; c < CAT; ++c) acc[c][kx] = fma_t(a[c], bv, acc[c][kx]);
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        if (lane == 0) {
+          if (single_tap)
+            out[ca * CB + cb] = v;
+          else
+            out[(ca * CB + cb) * K + (kzi * 5 + kyi) * 5 + kx] = v;
+        }
+      }
+      if (sums_too) {
+        double v = double(sacc[c]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        if (lane == 0) out[NS + ca] = v;
       }
     }
-#pragma unroll
-    for (int c = 0; c < CAT; ++c) {
-      stot[c] += double(sacc[c]);
-#pragma unroll
-      for (int k = 0; k < 5; ++k) tot[c][k] += double(acc[c][k]);
-    }
-  }
-  double* out = partials + size_t(vb) * (NS + CA);
-#pragma unroll
-  for (int c = 0; c < CAT; ++c) {
-    const int ca = chunk * CAT + c;
-    if (single_tap) {
-      out[ca * CB + cb] = tot[c][2];
-    } else {
-#pragma unroll
-      for (int kx = 0; kx < 5; ++kx) out[(ca * CB + cb) * K + (kzi * 5 + kyi) * 5 + kx] = tot[c][kx];
-    }
-    if (sums_too) out[NS + ca] = stot[c];
   }
 }
 __global__ void k_up_fold(const double* __restrict__ partials, int nblocks, int n, double* __restrict__ sums) {

@@ -28,8 +28,6 @@ int up_geom(const percnn_upscaler_t* d, UpGeom* u) {
   if (d->act != 0 && d->act != 1) return fail(PERCNN_ERR_INVALID, "act must be 0 (sigmoid) or 1 (tanh)");
   if (d->layers != 1 && d->layers != 2) return fail(PERCNN_ERR_INVALID, "layers must be 1 or 2");
   if (d->layers == 2 && d->stride2 != 1 && d->stride2 != 2) return fail(PERCNN_ERR_INVALID, "stride2 must be 1 or 2");
-  if (d->layers == 2 && d->ndim == 3 && d->channels == 16)   // (the correlation kernel's thread map: 16 x 25 > 256)
-    return fail(PERCNN_ERR_UNSUPPORTED, "two-layer 3-D upscalers are built for 8 channels (GS3D:46)");
   for (int i = 0; i < 3; ++i)
     if (d->low_extent[i] < 1 || d->low_extent[i] > (1 << 14)) return fail(PERCNN_ERR_INVALID, "bad low-resolution extents");
   if (d->ndim == 2 && d->low_extent[0] != 1) return fail(PERCNN_ERR_INVALID, "2-D needs low_extent[0] == 1");
@@ -141,19 +139,16 @@ template <typename T>
 int corr(const Grid& ga, const Grid& gb, int ndim, int S, int CA, int CB, int single, const T* A, const T* B, int n, double* partials,
          double* sums, cudaStream_t st) {
   const int64_t nrows = int64_t(ga.nz) * ga.H;
-  int nvb = int(nrows / 4 + 1 < kCorrMaxVB ? nrows / 4 + 1 : kCorrMaxVB);
-  if (nvb > nrows) nvb = int(nrows < 1 ? 1 : nrows);
-  const int cat = CA >= 4 ? 4 : 2;                                   // CA is 2, 8 or 16
-  const int ktaps = single ? 1 : (ndim == 3 ? 25 : 5);               // (kz, ky) pairs
-  const int nth = (CA / cat) * CB * ktaps;
-  const int groups = kThreads / nth;                                 // nth <= 200 for every supported net
-  const int nb = (nvb + groups - 1) / groups;
-  if (cat == 4)
-    k_up_corr<T, 4><<<nb, kThreads, 0, st>>>(ga, gb, ndim, S, CA, CB, single, nvb, A, B, partials);
+  int64_t nvb = nrows / 8;                       // ~8 rows per block amortise the per-combination lane fold
+  if (nvb < 148) nvb = nrows < 148 ? nrows : 148;
+  if (nvb > kCorrMaxVB) nvb = kCorrMaxVB;
+  if (nvb < 1) nvb = 1;
+  if (CA >= 4)
+    k_up_corr<T, 4><<<int(nvb), kThreads, 0, st>>>(ga, gb, ndim, S, CA, CB, single, A, B, partials);
   else
-    k_up_corr<T, 2><<<nb, kThreads, 0, st>>>(ga, gb, ndim, S, CA, CB, single, nvb, A, B, partials);
+    k_up_corr<T, 2><<<int(nvb), kThreads, 0, st>>>(ga, gb, ndim, S, CA, CB, single, A, B, partials);
   PERCNN_CUDA(cudaGetLastError());
-  k_up_fold<<<(n + 255) / 256, 256, 0, st>>>(partials, nvb, n, sums);
+  k_up_fold<<<(n + 255) / 256, 256, 0, st>>>(partials, int(nvb), n, sums);
   PERCNN_CUDA(cudaGetLastError());
   return PERCNN_OK;
 }
