@@ -178,6 +178,20 @@ typedef struct percnn_slab_ring {
  * buf[cur ^ (s & 1)], writes the other buffer and uses epoch + s.  The state ends in buf[cur ^ (nsteps & 1)]. */
 int percnn_slab_rollout_fwd(percnn_plan_t* plan, const percnn_slab_ring_t* ring, int cur, int nsteps, uint32_t epoch,
                             void* stream);
+/* Communication-avoiding variant for SMALL slabs (percnn_plan_slab_persistent(plan) != 0; cfg4-class grids): the whole
+ * rollout is one persistent kernel that exchanges 2k ghost planes every k time steps instead of 2 planes every step
+ * (the per-step hand-shake over NVLink costs more than such a slab's arithmetic).  `wide`: four scratch buffers
+ * [2][D + 4k][H][W] of this rank (contents irrelevant) and the neighbours' mappings of theirs; 2k <= D.  Same
+ * contract as percnn_slab_rollout_fwd otherwise (ring buffers in/out, flags, epochs): the two are interchangeable. */
+typedef struct percnn_slab_wide {
+  void* buf[4];
+  void* peer_lo_buf[4];
+  void* peer_hi_buf[4];
+  int32_t k;
+  int32_t reserved;
+} percnn_slab_wide_t;
+int percnn_slab_rollout_fwd_blocked(percnn_plan_t* plan, const percnn_slab_ring_t* ring, const percnn_slab_wide_t* wide,
+                                    int cur, int nsteps, uint32_t epoch, void* stream);
 /* Same, keeping every state: step t reads tape slot t and writes slot t+1, mirroring the boundary planes into the
  * neighbours' slot t+1 (`peer_*_tape` are the peer mappings of their tapes; slots are percnn_state_elems apart). */
 int percnn_slab_rollout_tape(percnn_plan_t* plan, void* tape, void* peer_lo_tape, void* peer_hi_tape,

@@ -31,7 +31,7 @@ EXPORTS = (
     "percnn_phys_loss_workspace_bytes", "percnn_phys_loss_fwd", "percnn_phys_loss_bwd",
     "percnn_slab_rollout_fwd", "percnn_slab_rollout_tape", "percnn_slab_rollout_bwd", "percnn_plan_slab_persistent", "percnn_plan_uses_tile2d", "percnn_step_rk4",
     "percnn_upscaler_sizes", "percnn_upscaler_fwd", "percnn_upscaler_bwd", "percnn_mse_workspace_bytes", "percnn_mse_fwd",
-    "percnn_mse_bwd", "percnn_library_points", "percnn_library_terms", "percnn_library_theta",
+    "percnn_mse_bwd", "percnn_slab_rollout_fwd_blocked", "percnn_library_points", "percnn_library_terms", "percnn_library_theta",
 )
 
 
@@ -59,6 +59,12 @@ class SlabRing(ctypes.Structure):
         ("buf", c_void_p * 2), ("peer_lo_buf", c_void_p * 2), ("peer_hi_buf", c_void_p * 2), ("my_flags", c_void_p),
         ("peer_lo_flags", c_void_p), ("peer_hi_flags", c_void_p), ("scratch", c_void_p),
     ]
+
+
+class SlabWide(ctypes.Structure):
+    """percnn_slab_wide_t"""
+    _fields_ = [("buf", c_void_p * 4), ("peer_lo_buf", c_void_p * 4), ("peer_hi_buf", c_void_p * 4), ("k", c_int32),
+                ("reserved", c_int32)]
 
 
 class DataLoss(ctypes.Structure):
@@ -143,6 +149,7 @@ def lib() -> ctypes.CDLL:
     L.percnn_step_bwd_loss.argtypes = [vp, vp, vp, vp, vp, c_int, c_int64, vp, vp, vp, POINTER(SlabLink), vp]
     L.percnn_rollout_bwd_loss.argtypes = [vp, vp, vp, vp, POINTER(c_uint8), POINTER(DataLoss), c_int, vp, vp, vp, vp]
     L.percnn_slab_rollout_fwd.argtypes = [vp, POINTER(SlabRing), c_int, c_int, ctypes.c_uint32, vp]
+    L.percnn_slab_rollout_fwd_blocked.argtypes = [vp, POINTER(SlabRing), POINTER(SlabWide), c_int, c_int, ctypes.c_uint32, vp]
     L.percnn_slab_rollout_tape.argtypes = [vp, vp, vp, vp, POINTER(SlabRing), c_int, ctypes.c_uint32, vp]
     L.percnn_slab_rollout_bwd.argtypes = [vp, vp, vp, POINTER(DataLoss), POINTER(SlabRing), c_int, ctypes.c_uint32, vp, vp]
     L.percnn_phys_loss_workspace_bytes.restype = c_size_t

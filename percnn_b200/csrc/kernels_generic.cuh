@@ -545,6 +545,174 @@ static __global__ void __launch_bounds__(kMultiThreads) k_multi_step_slab(Geom g
 }  // namespace percnn
 
 // =====================================================================================================
+// The same, COMMUNICATION-AVOIDING: neighbours exchange 2K ghost planes every K steps instead of 2 planes every step.
+// The per-step hand-shake of k_multi_step_slab (system-scope fences behind the peer stores, flag round trip over
+// NVLink, grid barrier) costs ~10 us whatever the slab holds -- more than the 8.8 us ONE GPU needs for a whole 128^3
+// step, which is why cfg4 got slower on more GPUs.  Here a block of K steps runs between two hand-shakes:
+//   * the state lives in "wide" buffers [2][D + 4K][H][W] (2K ghost planes per side);
+//   * sub-step j of a block computes the planes [-e, D + e), e = 2 (K - 1 - j), from the previous sub-step's output:
+//     the planes that can still be valid shrink by 2 per sub-step and end at the interior (redundant work: at D = 16,
+//     K = 4 it is +37 % planes for a quarter of the hand-shakes); only a plain grid barrier separates sub-steps;
+//   * the LAST sub-step stores the interior and mirrors its first / last 2K planes into the neighbours' ghost planes
+//     of the buffer the NEXT block starts from.  Blocks alternate between two buffer PAIRS, so a fast neighbour never
+//     writes ghost planes that a slow rank still reads (it can be at most one block ahead: it needs this rank's
+//     planes of the previous block, published after this rank's last read of that block).
+// The first step reads the caller's standard buffer (2 ghost planes: a block of one step) and the last block writes
+// the standard buffer and the neighbours' standard ghost planes, with the same flags and epochs as the per-step
+// kernels, so the three slab paths stay interchangeable between rollout calls.  Per-cell arithmetic is the gather
+// kernel's: results are bit-identical to the single-GPU rollout.
+// =====================================================================================================
+namespace percnn {
+
+struct SlabBlockedArgs {
+  float* buf[2];              // standard ping-pong buffers [2][D+4][H][W] and the neighbours' mappings of theirs
+  float* peer_lo[2];
+  float* peer_hi[2];
+  float* w[4];                // wide buffers [2][D+4K][H][W]: pairs (0,1) and (2,3)
+  float* wlo[4];
+  float* whi[4];
+  const uint32_t* my_flags;
+  uint32_t* post_lo_flag;
+  uint32_t* post_hi_flag;
+  uint32_t* err;
+  uint32_t epoch0;
+  uint32_t spin_limit;
+  int nsteps;
+  int cur;
+  int K;
+};
+
+static __global__ void __launch_bounds__(kMultiThreads) k_multi_step_slab_tb(Geom g, int slot, SlabBlockedArgs a, unsigned* counter) {
+  const float* P = PrepView<float>::get(c_prep[slot]);
+  unsigned* go = counter + 1;
+  const int G = 2 * a.K;
+  const int64_t wfield = int64_t(g.D + 2 * G) * g.plane;
+  unsigned nbar = 0;            // barriers passed so far (both kinds count on the same words)
+  int done = 0, blk = 0;
+  while (done < a.nsteps) {
+    const bool first = done == 0;
+    const int Kb = first ? 1 : min(a.K, a.nsteps - done);
+    const bool last = done + Kb == a.nsteps;
+    const int p = blk & 1;      // wide pair this block works in (blocks >= 1)
+    for (int j = 0; j < Kb; ++j) {
+      const int e = 2 * (Kb - 1 - j);
+      const bool fin = j == Kb - 1;
+      // ---- source: planes [-e-2, D+e+2) must be valid ----
+      Geom gs = g;
+      const float* src;
+      if (first) {
+        src = a.buf[a.cur];
+      } else {
+        src = a.w[2 * p + (j & 1)];
+        gs.D = g.D + 2 * e;
+        gs.ghost = G - e;
+        gs.field = wfield;
+      }
+      // ---- destination ----
+      float* dst;
+      float* plo = nullptr;
+      float* phi = nullptr;
+      int64_t dfield;
+      int dghost, send = 0;
+      if (!fin) {
+        dst = a.w[2 * p + ((j & 1) ^ 1)];
+        dfield = wfield;
+        dghost = G;
+      } else if (last) {
+        const int di = a.cur ^ (a.nsteps & 1);
+        dst = a.buf[di];
+        plo = a.peer_lo[di];
+        phi = a.peer_hi[di];
+        dfield = g.field;
+        dghost = g.ghost;
+        send = 2;
+      } else {
+        const int nw = 2 * ((blk + 1) & 1);     // the next block's first buffer (the other pair)
+        dst = a.w[nw];
+        plo = a.wlo[nw];
+        phi = a.whi[nw];
+        dfield = wfield;
+        dghost = G;
+        send = G;
+      }
+      const int64_t ncell = int64_t(gs.D) * g.plane;
+      bool wrote_peer = false;
+      for (int64_t cell = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; cell < ncell; cell += int64_t(gridDim.x) * blockDim.x) {
+        const CellOffsets<3> o = cell_offsets<3>(gs, cell);
+        const Cross<float, 3> U = gather_cg<float, 3>(src, o);
+        const Cross<float, 3> V = gather_cg<float, 3>(src + gs.field, o);
+        float ou, ov;
+        pi_k1_fwd_poly<float>(U.c, V.c, lap_apply<float, 3>(U, P), lap_apply<float, 3>(V, P), P, ou, ov);
+        const int zl = int(cell / g.plane);                 // plane inside the computed range
+        const int z = zl - e;                               // interior index
+        const int64_t od = int64_t(z + dghost) * g.plane + (cell - int64_t(zl) * g.plane);
+        dst[od] = ou;
+        dst[dfield + od] = ov;
+        if (send) {
+          if (z < send) {                    // -> the lower neighbour's upper ghost planes D .. D + send - 1
+            const int64_t m = od + int64_t(g.D) * g.plane;
+            plo[m] = ou;
+            plo[dfield + m] = ov;
+            wrote_peer = true;
+          }
+          if (z >= g.D - send) {             // -> the upper neighbour's lower ghost planes -send .. -1
+            const int64_t m = od - int64_t(g.D) * g.plane;
+            phi[m] = ou;
+            phi[dfield + m] = ov;
+            wrote_peer = true;
+          }
+        }
+      }
+      ++nbar;
+      if (!fin) {
+        grid_barrier(counter, nbar * gridDim.x);
+        continue;
+      }
+      // ---- grid barrier + halo hand-shake (as in k_multi_step_slab) ----
+      if (wrote_peer) __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        if (blockIdx.x == 0) {
+          unsigned v;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+          } while (v < nbar * gridDim.x);
+          asm volatile("fence.acq_rel.sys;" ::: "memory");
+          const uint32_t ep = a.epoch0 + uint32_t(done + Kb);
+          asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.post_lo_flag), "r"(ep) : "memory");
+          asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.post_hi_flag), "r"(ep) : "memory");
+          for (uint32_t spins = 0;; ++spins) {
+            uint32_t w0, w1;
+            asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(w0) : "l"(a.my_flags + 0) : "memory");
+            asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(w1) : "l"(a.my_flags + 1) : "memory");
+            if (int32_t(w0 - ep) >= 0 && int32_t(w1 - ep) >= 0) break;
+            if (spins >= a.spin_limit) {
+              atomicExch(a.err, 1u);
+              __threadfence_system();
+              __trap();
+            }
+          }
+          asm volatile("fence.acq_rel.sys;" ::: "memory");
+          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(go), "r"(nbar) : "memory");
+        } else {
+          unsigned v;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(go) : "memory");
+          } while (v < nbar);
+        }
+      }
+      __syncthreads();
+    }
+    done += Kb;
+    ++blk;
+  }
+}
+
+}  // namespace percnn
+
+// =====================================================================================================
 // Persistent multi-step ADJOINT for small grids: the backward twin of k_multi_step.  A training step on the 2-D
 // configs (and the reference's own 100^2 / 48^3 grids) is bound by one launch + one 22-value grid reduction per
 // time step (measured: 11 us per step at 128^2 fp64, of which the stencil is ~2 us).  Here ONE cooperative launch

@@ -20,6 +20,9 @@ namespace tma3d {
 #ifndef PERCNN_BWD_REG_MONO
 #define PERCNN_BWD_REG_MONO 1      // 1: the 20 per-lane monomial sums live in registers (0: shared memory, round 1)
 #endif
+#ifndef PERCNN_BWD_ALIGNED_ENTRY
+#define PERCNN_BWD_ALIGNED_ENTRY 1
+#endif
 #ifndef PERCNN_BWD_STATIC_STAGE
 #define PERCNN_BWD_STATIC_STAGE 0
 #endif
@@ -291,6 +294,15 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
     return;
   }
   if (warp >= p.ty) return;
+#if PERCNN_BWD_ALIGNED_ENTRY
+  // An ALIGNED barrier among the consumer warps: every thread of a warp executes it together, which tells the compiler
+  // that the warps are converged from here on.  Without it ptxas treats the whole consumer loop as potentially
+  // divergent (the role split above branches on threadIdx): loop state lives in vector registers, every LDG / STG
+  // re-materialises its memory descriptor with two R2UR (34 per plane), the shuffles sit behind BRA.DIV -- 89 R2UR and
+  // 24 BRA.DIV in the kernel without it, 15 and 0 with it, 5 registers fewer, 783 -> 743 us per 512^3 adjoint step
+  // (profiles/r02_adjoint_variants.txt).  The forward kernel gets the same guarantee from setmaxnreg.sync.aligned.
+  asm volatile("bar.sync 4, %0;" ::"r"(p.ty * 32) : "memory");
+#endif
   Consumer c;
   c.P = c_prep[SLOT].f;
   c.ring = ring;

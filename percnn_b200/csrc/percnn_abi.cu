@@ -602,6 +602,53 @@ int percnn_slab_rollout_fwd(percnn_plan_t* p, const percnn_slab_ring_t* ring, in
   return PERCNN_OK;
 }
 
+// The persistent small-slab rollout with K time steps per halo exchange (k_multi_step_slab_tb): `wide` holds four
+// buffers [2][D + 4K][H][W] of this rank and the neighbours' mappings of theirs.
+int percnn_slab_rollout_fwd_blocked(percnn_plan_t* p, const percnn_slab_ring_t* ring, const percnn_slab_wide_t* wide, int cur,
+                                    int nsteps, uint32_t epoch, void* stream) {
+  if (!p || !ring || !wide) return fail(PERCNN_ERR_INVALID, "null argument");
+  if (nsteps < 1 || (cur != 0 && cur != 1)) return fail(PERCNN_ERR_INVALID, "bad nsteps / cur");
+  if (!percnn_plan_slab_persistent(p)) return fail(PERCNN_ERR_UNSUPPORTED, "plan has no persistent slab kernel (slab too large, or not a slab plan)");
+  if (wide->k < 1 || 2 * wide->k > p->g.D) return fail(PERCNN_ERR_INVALID, "need 1 <= k and 2 k <= planes per rank");
+  if (!ring->buf[0] || !ring->buf[1] || !ring->peer_lo_buf[0] || !ring->peer_lo_buf[1] || !ring->peer_hi_buf[0] ||
+      !ring->peer_hi_buf[1] || !ring->my_flags || !ring->peer_lo_flags || !ring->peer_hi_flags || !ring->scratch)
+    return fail(PERCNN_ERR_INVALID, "incomplete slab ring");
+  SlabBlockedArgs a;
+  for (int i = 0; i < 2; ++i) {
+    a.buf[i] = static_cast<float*>(ring->buf[i]);
+    a.peer_lo[i] = static_cast<float*>(ring->peer_lo_buf[i]);
+    a.peer_hi[i] = static_cast<float*>(ring->peer_hi_buf[i]);
+  }
+  for (int i = 0; i < 4; ++i) {
+    if (!wide->buf[i] || !wide->peer_lo_buf[i] || !wide->peer_hi_buf[i]) return fail(PERCNN_ERR_INVALID, "incomplete wide buffers");
+    a.w[i] = static_cast<float*>(wide->buf[i]);
+    a.wlo[i] = static_cast<float*>(wide->peer_lo_buf[i]);
+    a.whi[i] = static_cast<float*>(wide->peer_hi_buf[i]);
+  }
+  a.my_flags = ring->my_flags;
+  a.post_lo_flag = ring->peer_lo_flags + 1;
+  a.post_hi_flag = ring->peer_hi_flags + 0;
+  a.err = ring->scratch + 1;
+  a.epoch0 = epoch;
+  a.spin_limit = p->flag_spin_limit;
+  a.nsteps = nsteps;
+  a.cur = cur;
+  a.K = wide->k;
+  DeviceGuard guard(p->desc.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PERCNN_CUDA(cudaMemsetAsync(p->d_sync, 0, 8, st));
+  Geom g = p->g;
+  int slot = p->slot;
+  unsigned* counter = p->d_sync;
+  void* args[] = {&g, &slot, &a, &counter};
+  const int64_t ncell = int64_t(g.D) * g.H * g.W;
+  int grid = int((ncell + kMultiThreads - 1) / kMultiThreads);
+  if (grid > p->multi_slab_grid) grid = p->multi_slab_grid;
+  PERCNN_CUDA(cudaLaunchCooperativeKernel((const void*)k_multi_step_slab_tb, dim3(grid), dim3(kMultiThreads), args, 0, st));
+  p->launches++;
+  return PERCNN_OK;
+}
+
 // Taped slab rollout: step t reads tape slot t and writes slot t+1 (and the boundary planes of the peers' slot t+1).
 int percnn_slab_rollout_tape(percnn_plan_t* p, void* tape, void* peer_lo_tape, void* peer_hi_tape,
                              const percnn_slab_ring_t* ring, int nsteps, uint32_t epoch, void* stream) {

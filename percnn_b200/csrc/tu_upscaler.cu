@@ -148,7 +148,7 @@ int corr(const Grid& ga, const Grid& gb, int ndim, int S, int CA, int CB, int si
   else
     k_up_corr<T, 2><<<int(nvb), kThreads, 0, st>>>(ga, gb, ndim, S, CA, CB, single, A, B, partials);
   PERCNN_CUDA(cudaGetLastError());
-  k_up_fold<<<(n + 255) / 256, 256, 0, st>>>(partials, int(nvb), n, sums);
+  k_up_fold<<<(n + 31) / 32, 256, 0, st>>>(partials, int(nvb), n, sums);
   PERCNN_CUDA(cudaGetLastError());
   return PERCNN_OK;
 }

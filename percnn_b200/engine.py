@@ -176,6 +176,10 @@ class Plan:
         check(self._L.percnn_slab_rollout_fwd(self._h, ctypes.byref(ring), int(cur), int(nsteps), int(epoch) & 0xFFFFFFFF,
                                               _stream_ptr(self.device)))
 
+    def slab_rollout_fwd_blocked(self, ring, wide, cur: int, nsteps: int, epoch: int) -> None:
+        check(self._L.percnn_slab_rollout_fwd_blocked(self._h, ctypes.byref(ring), ctypes.byref(wide), int(cur), int(nsteps),
+                                                      int(epoch) & 0xFFFFFFFF, _stream_ptr(self.device)))
+
     def slab_rollout_tape(self, tape, peer_lo_tape, peer_hi_tape, ring, nsteps: int, epoch: int) -> None:
         self._check_state(tape, "tape", nsteps + 1)
         check(self._L.percnn_slab_rollout_tape(self._h, tape.data_ptr(), peer_lo_tape.data_ptr(), peer_hi_tape.data_ptr(),

@@ -29,6 +29,8 @@ from __future__ import annotations
 
 from typing import List, Optional
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -152,6 +154,26 @@ class SlabRollout:
             self.transport = "nccl" if world > 1 else "local"
             self.bufs = [torch.zeros(shape, dtype=torch.float32, device=self.device) for _ in range(2)]
         self.cur = 0
+        # Small slabs (cfg4-class): the persistent rollout kernel exchanges 2K ghost planes every K time steps; it works
+        # in four "wide" buffers [2][nz + 4K][H][W] (peer-mapped like the state buffers).  PERCNN_SLAB_TB_K=1 keeps
+        # the per-step hand-shake of round 2's first persistent kernel.
+        self._wide = None
+        if self.transport == "fused" and self.plan.slab_persistent:
+            k = max(1, min(int(os.environ.get("PERCNN_SLAB_TB_K", "4")), self.nz // 2))
+            if k >= 2:
+                wshape = (4, 2, self.nz + 4 * k, H, W)
+                if self.symm == "self":
+                    wide = torch.zeros(wshape, dtype=torch.float32, device=self.device)
+                    wlo = whi = wide
+                else:
+                    import torch.distributed._symmetric_memory as symm_mem
+                    wide = symm_mem.empty(wshape, dtype=torch.float32, device=self.device)
+                    whdl = symm_mem.rendezvous(wide, group=group if group is not None else dist.group.WORLD)
+                    wide.zero_()
+                    wlo = whdl.get_buffer((rank - 1) % world, wshape, torch.float32)
+                    whi = whdl.get_buffer((rank + 1) % world, wshape, torch.float32)
+                    self._wide_hdl = whdl
+                self._wide = (wide, wlo, whi, k)
         self.comm_stream = torch.cuda.Stream(self.device)
         self.ev_boundary = torch.cuda.Event()
         self.ev_ghosts = torch.cuda.Event()
@@ -222,8 +244,14 @@ class SlabRollout:
             "nccl": "boundary kernels first, grouped ncclSend/ncclRecv on a second stream under the interior kernel",
             "local": "single rank: ghost planes are a local wrap copy",
         }[self.transport]
-        return {"transport": self.transport, "planes_per_rank": self.nz, "ghost_bytes_per_side_per_step": 2 * 2 * H * W * 4,
-                "cuda_graph": bool(self.use_graph), "overlap": overlap}
+        d = {"transport": self.transport, "planes_per_rank": self.nz, "ghost_bytes_per_side_per_step": 2 * 2 * H * W * 4,
+             "cuda_graph": bool(self.use_graph), "overlap": overlap}
+        if self._wide is not None:
+            k = self._wide[3]
+            d["time_blocking"] = {"steps_per_exchange": k, "ghost_planes_per_side": 2 * k,
+                                  "note": "persistent small-slab kernel: 2K ghost planes exchanged every K steps, K sub-steps on "
+                                          "shrinking plane ranges between hand-shakes (one cooperative launch per rollout)"}
+        return d
 
     # -- exchange -------------------------------------------------------------------------------
     def _exchange_blocking(self, b: int) -> None:
@@ -300,6 +328,17 @@ class SlabRollout:
         r.peer_hi_flags = self._peer_hi_words.data_ptr()
         r.scratch = self._words.data_ptr() + 8
         return r
+
+    def _wide_struct(self):
+        from ._lib import SlabWide
+        wide, wlo, whi, k = self._wide
+        w = SlabWide()
+        for i in range(4):
+            w.buf[i] = wide[i].data_ptr()
+            w.peer_lo_buf[i] = wlo[i].data_ptr()
+            w.peer_hi_buf[i] = whi[i].data_ptr()
+        w.k = k
+        return w
 
     def refresh_params(self) -> None:
         """Re-read the cell's parameters (call after an optimiser step)."""
@@ -409,7 +448,10 @@ class SlabRollout:
         """Advance the slab by nsteps time steps.  Invariant on entry and exit: the ghosts of the current
         buffer are valid and every exchange signal has been consumed (set_state() establishes it)."""
         if self.transport == "fused":
-            self.plan.slab_rollout_fwd(self._ring(), self.cur, nsteps, self.epoch)
+            if self._wide is not None and nsteps >= 2:
+                self.plan.slab_rollout_fwd_blocked(self._ring(), self._wide_struct(), self.cur, nsteps, self.epoch)
+            else:
+                self.plan.slab_rollout_fwd(self._ring(), self.cur, nsteps, self.epoch)
             self.epoch += nsteps
             self.cur ^= nsteps & 1
             return

@@ -108,3 +108,33 @@ def test_self_ring_initial_state_from_the_sharded_upscaler():
     assert torch.equal(b[:, 0:2], b[:, 16:18]) and torch.equal(b[:, 18:20], b[:, 2:4])     # periodic ghosts of the state
     gp = slab.upscaler_backward(g)
     assert float((gp - ref).abs().max()) <= 1e-6 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("shape,k,steps", [((16, 16, 128), 4, 11), ((16, 16, 128), 3, 2), ((8, 32, 128), 4, 9), ((9, 16, 128), 2, 6),
+                                           ((128, 128, 128), 4, 10), ((16, 128, 128), 8, 18)])
+def test_time_blocked_slab_rollout_is_bitwise_equal(shape, k, steps, monkeypatch):
+    """Communication-avoiding persistent rollout (2K ghost planes every K steps) against the single-GPU gather kernel,
+    for K that divides / does not divide the step count, K = D/2, and back-to-back calls (odd and even lengths) that
+    hand the standard buffers, flags and epochs over to each other and to the per-step path."""
+    monkeypatch.setenv("PERCNN_SLAB_TB_K", str(k))
+    cell = _cell()
+    h0 = _state(shape, 6)
+    slab = halo.SlabRollout(cell, shape, DEV, 0, 1, transport="fused")
+    assert slab.plan.slab_persistent and slab._wide is not None and slab._wide[3] == min(k, shape[0] // 2)
+    assert slab.describe()["time_blocking"]["steps_per_exchange"] == min(k, shape[0] // 2)
+    with torch.no_grad():
+        cell._flags = _lib.FLAG_NO_TMA
+        ref = cell.rollout(h0[None], 2 * steps + 1)
+        cell._flags = 0
+    slab.set_state(h0)
+    slab.run(steps)
+    assert torch.equal(slab.interior(), ref[steps]), float((slab.interior() - ref[steps]).abs().max())
+    slab.run(steps)                  # back to back: the standard buffers, flags and epochs were handed over intact
+    assert torch.equal(slab.interior(), ref[2 * steps])
+    b = slab.bufs[slab.cur]
+    nz = shape[0]
+    assert torch.equal(b[:, 0:2], b[:, nz:nz + 2]) and torch.equal(b[:, nz + 2:nz + 4], b[:, 2:4])   # ghosts valid afterwards
+    slab.run(1)                      # a single step takes the per-step TMA kernel (same arithmetic up to rounding)
+    err = float((slab.interior() - ref[2 * steps + 1]).abs().max() / ref[2 * steps + 1].abs().max())
+    assert err <= 2e-6, err
+    assert slab.error_word() == 0
