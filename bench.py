@@ -562,9 +562,25 @@ def run_ours(args):
                 e1.record()
                 barrier()
                 ms4 = max_over_ranks(e0.elapsed_time(e1)) / 5
+                # correctness of THIS path inside the artefact: the full 500-step slab rollout against a single-GPU
+                # recompute of the same global field on every rank (the persistent slab kernel shares the gather
+                # kernel's per-cell arithmetic: bitwise; the TMA z-march differs from it by rounding only)
+                from percnn_b200 import _lib as _plib
+                full4 = synthetic_state(s4, 0, s4[0], dev, torch.float32)
+                slab4.set_state(full4[:, slab4.z0:slab4.z0 + slab4.nz])
+                slab4.run(ROLLOUT_STEPS)
+                ref_flags = _plib.FLAG_NO_TMA if slab4.plan.slab_persistent else 0
+                import dataclasses as _dc
+                plan4 = engine.get_plan(_dc.replace(cell._spec(), flags=ref_flags), s4, dev)
+                plan4.params_load(flat)
+                ref4 = torch.empty_like(full4)
+                plan4.rollout_fwd(full4, ROLLOUT_STEPS, h_final=ref4)
+                same = torch.tensor([int(torch.equal(slab4.interior(), ref4[:, slab4.z0:slab4.z0 + slab4.nz]))], device=dev)
+                dist.all_reduce(same, op=dist.ReduceOp.MIN)
                 extra["cfg4_gs3d_128"] = {"workload": "3-D Gray-Scott 128^3, fp32, hc=2, 500-step forward rollout, slab-decomposed",
                                           "n_gpus": world, "timesteps_per_s": ROLLOUT_STEPS / (ms4 * 1e-3), "us_per_timestep": 1e3 * ms4 / ROLLOUT_STEPS,
-                                          "ms_per_rollout": ms4, "halo": slab4.describe(), "finite": bool(torch.isfinite(slab4.interior()).all())}
+                                          "ms_per_rollout": ms4, "halo": slab4.describe(), "finite": bool(torch.isfinite(slab4.interior()).all()),
+                                          "vs_single_gpu_500_steps": "bitwise" if int(same.item()) else "MISMATCH"}
             except Exception as e:
                 extra["cfg4_gs3d_128"] = {"error": str(e)[:300]}
 

@@ -635,30 +635,74 @@ static __global__ void __launch_bounds__(kMultiThreads) k_multi_step_slab_tb(Geo
         dghost = G;
         send = G;
       }
-      const int64_t ncell = int64_t(gs.D) * g.plane;
+      // One thread = four x-adjacent cells: 11 x 128-bit L2 loads per field (centre, the two neighbouring quads, four
+      // y rows, four z planes) instead of 52 scalar ones, and one round of loads per sub-step for most threads -- the
+      // sub-step is bound by L2 latency, not by arithmetic.  The per-cell arithmetic is the gather kernel's own
+      // (Cross -> lap_apply -> pi_k1_fwd_poly), so the results stay bit-identical to it.
+      const int W4 = g.W >> 2;
+      const int64_t nquad = int64_t(gs.D) * g.H * W4;
       bool wrote_peer = false;
-      for (int64_t cell = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; cell < ncell; cell += int64_t(gridDim.x) * blockDim.x) {
-        const CellOffsets<3> o = cell_offsets<3>(gs, cell);
-        const Cross<float, 3> U = gather_cg<float, 3>(src, o);
-        const Cross<float, 3> V = gather_cg<float, 3>(src + gs.field, o);
-        float ou, ov;
-        pi_k1_fwd_poly<float>(U.c, V.c, lap_apply<float, 3>(U, P), lap_apply<float, 3>(V, P), P, ou, ov);
-        const int zl = int(cell / g.plane);                 // plane inside the computed range
+      for (int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; q < nquad; q += int64_t(gridDim.x) * blockDim.x) {
+        const int xq = int(q % W4) << 2;
+        const int64_t r = q / W4;
+        const int y = int(r % g.H), zl = int(r / g.H);
+        const int64_t pl = int64_t(zl + gs.ghost) * g.plane;
+        const int64_t row = pl + int64_t(y) * g.W;
+        const int xl = xq == 0 ? g.W - 4 : xq - 4, xr = xq + 4 == g.W ? 0 : xq + 4;
+        int64_t yo[4];
+        {
+          const int offs[4] = {-2, -1, 1, 2};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) yo[k] = pl + int64_t(wrap_idx(y + offs[k], g.H)) * g.W + xq;
+        }
+        float lapv[2][4], ctr[2][4];
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+          const float* sf = src + f * gs.field;
+          auto ld4 = [&](int64_t off) { return __ldcg(reinterpret_cast<const float4*>(sf + off)); };
+          const float4 c4 = ld4(row + xq), l4 = ld4(row + xl), r4 = ld4(row + xr);
+          const float4 y0 = ld4(yo[0]), y1 = ld4(yo[1]), y2 = ld4(yo[2]), y3 = ld4(yo[3]);
+          const float4 z0 = ld4(row + xq - 2 * g.plane), z1 = ld4(row + xq - g.plane), z2 = ld4(row + xq + g.plane),
+                       z3 = ld4(row + xq + 2 * g.plane);
+          const float line[12] = {l4.x, l4.y, l4.z, l4.w, c4.x, c4.y, c4.z, c4.w, r4.x, r4.y, r4.z, r4.w};
+          const float ya[4][4] = {{y0.x, y0.y, y0.z, y0.w}, {y1.x, y1.y, y1.z, y1.w}, {y2.x, y2.y, y2.z, y2.w}, {y3.x, y3.y, y3.z, y3.w}};
+          const float za[4][4] = {{z0.x, z0.y, z0.z, z0.w}, {z1.x, z1.y, z1.z, z1.w}, {z2.x, z2.y, z2.z, z2.w}, {z3.x, z3.y, z3.z, z3.w}};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            Cross<float, 3> Q;
+            Q.c = line[4 + j];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              Q.n[0][k] = za[k][j];
+              Q.n[1][k] = ya[k][j];
+            }
+            Q.n[2][0] = line[2 + j];
+            Q.n[2][1] = line[3 + j];
+            Q.n[2][2] = line[5 + j];
+            Q.n[2][3] = line[6 + j];
+            lapv[f][j] = lap_apply<float, 3>(Q, P);
+            ctr[f][j] = Q.c;
+          }
+        }
+        float ou[4], ov[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pi_k1_fwd_poly<float>(ctr[0][j], ctr[1][j], lapv[0][j], lapv[1][j], P, ou[j], ov[j]);
+        const float4 o_u = make_float4(ou[0], ou[1], ou[2], ou[3]), o_v = make_float4(ov[0], ov[1], ov[2], ov[3]);
         const int z = zl - e;                               // interior index
-        const int64_t od = int64_t(z + dghost) * g.plane + (cell - int64_t(zl) * g.plane);
-        dst[od] = ou;
-        dst[dfield + od] = ov;
+        const int64_t od = int64_t(z + dghost) * g.plane + int64_t(y) * g.W + xq;
+        *reinterpret_cast<float4*>(dst + od) = o_u;
+        *reinterpret_cast<float4*>(dst + dfield + od) = o_v;
         if (send) {
           if (z < send) {                    // -> the lower neighbour's upper ghost planes D .. D + send - 1
             const int64_t m = od + int64_t(g.D) * g.plane;
-            plo[m] = ou;
-            plo[dfield + m] = ov;
+            *reinterpret_cast<float4*>(plo + m) = o_u;
+            *reinterpret_cast<float4*>(plo + dfield + m) = o_v;
             wrote_peer = true;
           }
           if (z >= g.D - send) {             // -> the upper neighbour's lower ghost planes -send .. -1
             const int64_t m = od - int64_t(g.D) * g.plane;
-            phi[m] = ou;
-            phi[dfield + m] = ov;
+            *reinterpret_cast<float4*>(phi + m) = o_u;
+            *reinterpret_cast<float4*>(phi + dfield + m) = o_v;
             wrote_peer = true;
           }
         }

@@ -369,19 +369,25 @@ __global__ void __launch_bounds__(kThreads) k_up_corr(Grid ga, Grid gb, int ndim
 #pragma unroll
       for (int k = 0; k < 5; ++k) acc[c][k] = T(0);
     }
-    for (int64_t r = r0; r < r1; ++r) {
-      const int y = int(r % ga.H), z = ga.z0 + int(r / ga.H);
+    int y = int(r0 % ga.H), z = ga.z0 + int(r0 / ga.H);     // walked along with r (no 64-bit division per row)
+    for (int64_t r = r0; r < r1; ++r, ++y) {
+      if (y == ga.H) {
+        y = 0;
+        ++z;
+      }
       bool row_ok = true;
       int iz = gb.z0, iy = 0;
       if (ndim == 3) {
         const int nz = z + 2 - kz;
-        row_ok = nz >= 0 && (nz % S) == 0 && nz / S < gb.D;
-        iz = nz / S;
+        row_ok = nz >= 0 && (S == 1 || (nz & 1) == 0);
+        iz = S == 1 ? nz : nz >> 1;
+        row_ok = row_ok && iz < gb.D;
       }
       {
         const int ny = y + 2 - ky;
-        row_ok = row_ok && ny >= 0 && (ny % S) == 0 && ny / S < gb.H;
-        iy = ny / S;
+        row_ok = row_ok && ny >= 0 && (S == 1 || (ny & 1) == 0);
+        iy = S == 1 ? ny : ny >> 1;
+        row_ok = row_ok && iy < gb.H;
       }
       if (!row_ok && !sums_too) continue;
       const T* arow = a0 + r * ga.W;
@@ -398,8 +404,8 @@ __global__ void __launch_bounds__(kThreads) k_up_corr(Grid ga, Grid gb, int ndim
         for (int kx = 0; kx < 5; ++kx) {
           if (single_tap && kx != 2) continue;
           const int nx = x + 2 - kx;
-          if (nx < 0 || (nx % S) != 0) continue;
-          const int ix = nx / S;
+          if (nx < 0 || (S == 2 && (nx & 1))) continue;
+          const int ix = S == 1 ? nx : nx >> 1;
           if (ix >= gb.W) continue;
           const T bv = __ldg(brow + ix);
 #pragma unroll
@@ -481,17 +487,38 @@ __global__ void k_up_finish(const T* __restrict__ raw, const double* __restrict_
       put(r.W2 + i, double(raw[r.W3 + co]) * C2[(0 * C + ci) * K + k] + double(raw[r.W3 + C + co]) * C2[(1 * C + ci) * K + k]);
     }
     for (int co = tid; co < C; co += nth) put(r.b2 + co, double(raw[r.W3 + co]) * Sg[0] + double(raw[r.W3 + C + co]) * Sg[1]);
-    for (int i = tid; i < 2 * C; i += nth) {         // dW3[f][co] = b2[co] sum g[f] + sum_{ci,k} W2[ci][co][k] C2[f][ci][k]
-      const int co = i % C, f = i / C;
-      double s = double(raw[r.b2 + co]) * Sg[f];
-      for (int ci = 0; ci < C; ++ci)
-        for (int k = 0; k < K; ++k) s += double(raw[r.W2 + (ci * C + co) * K + k]) * C2[(f * C + ci) * K + k];
-      put(r.W3 + i, s);
-    }
+    // (dW3 is a C*K-term contraction per entry: k_up_finish_w3, one block per entry)
     for (int f = tid; f < 2; f += nth) put(r.b3 + f, Sg[f]);
   } else {
     for (int i = tid; i < 2 * C; i += nth) put(r.W3 + i, sums2[i]);
     for (int f = tid; f < 2; f += nth) put(r.b3 + f, sums2[2 * C + f]);
+  }
+}
+
+// dW3[f][co] = b2[co] sum g[f] + sum_{ci,k} W2[ci][co][k] C2[f][ci][k]: one block per entry, 128 threads stride over the
+// C*K terms, fixed-order tree in shared memory (deterministic).
+template <typename T>
+__global__ void __launch_bounds__(128) k_up_finish_w3(const T* __restrict__ raw, const double* __restrict__ sums2, int C, int K,
+                                                      T* __restrict__ gp, int accumulate) {
+  __shared__ double sm[128];
+  const RawOff r = raw_off(C, K, 2);
+  const double* C2 = sums2;
+  const double* Sg = sums2 + 2 * C * K;
+  const int i = blockIdx.x, co = i % C, f = i / C;
+  double s = 0;
+  for (int t = threadIdx.x; t < C * K; t += 128) {
+    const int ci = t / K, k = t - ci * K;
+    s += double(raw[r.W2 + (ci * C + co) * K + k]) * C2[(f * C + ci) * K + k];
+  }
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int off = 64; off > 0; off >>= 1) {
+    if (threadIdx.x < off) sm[threadIdx.x] += sm[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double v = sm[0] + double(raw[r.b2 + co]) * Sg[f];
+    gp[r.W3 + i] = accumulate ? T(double(gp[r.W3 + i]) + v) : T(v);
   }
 }
 

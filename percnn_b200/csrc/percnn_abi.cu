@@ -95,7 +95,7 @@ const void* multi_step_kernel(const percnn_plan* p) {
 // set stays in L2 and a per-step launch would be latency-bound.  Larger non-TMA plans (fp64 3-D, W % 128 != 0)
 // run one generic kernel per step.
 constexpr size_t kMultiStepMaxStateBytes = size_t(40) << 20;
-constexpr size_t kSmallSlabBytes = size_t(6) << 20;   // per-rank state (incl. ghosts) below which a slab rollout runs persistently
+constexpr size_t kSmallSlabBytes = size_t(12) << 20;   // per-rank state (incl. ghosts) below which a slab rollout runs persistently
 bool multi_step_eligible(const percnn_plan* p) {
   if (p->use_tma || is_k5(p) || p->desc.slab_ghost) return false;
   if (state_bytes(p) > kMultiStepMaxStateBytes) return false;

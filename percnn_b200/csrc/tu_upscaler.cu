@@ -139,9 +139,7 @@ template <typename T>
 int corr(const Grid& ga, const Grid& gb, int ndim, int S, int CA, int CB, int single, const T* A, const T* B, int n, double* partials,
          double* sums, cudaStream_t st) {
   const int64_t nrows = int64_t(ga.nz) * ga.H;
-  int64_t nvb = nrows / 8;                       // ~8 rows per block amortise the per-combination lane fold
-  if (nvb < 148) nvb = nrows < 148 ? nrows : 148;
-  if (nvb > kCorrMaxVB) nvb = kCorrMaxVB;
+  int64_t nvb = nrows < kCorrMaxVB ? nrows : kCorrMaxVB;   // the kernel is latency-bound per warp: as many blocks as rows
   if (nvb < 1) nvb = 1;
   if (CA >= 4)
     k_up_corr<T, 4><<<int(nvb), kThreads, 0, st>>>(ga, gb, ndim, S, CA, CB, single, A, B, partials);
@@ -191,6 +189,10 @@ int bwd_t(const UpGeom& u, const T* raw, const T* low, const T* mid, const T* g,
   if (int rc = corr<T>(u.own, u.low, u.ndim, 2, C, 2, 0, gm, low, u.n1, partials, sums1, st)) return rc;
   k_up_finish<T><<<32, 256, 0, st>>>(raw, sums1, sums2, C, u.K, u.layers, gp, accumulate);
   PERCNN_CUDA(cudaGetLastError());
+  if (u.layers == 2) {
+    k_up_finish_w3<T><<<2 * C, 128, 0, st>>>(raw, sums2, C, u.K, gp, accumulate);
+    PERCNN_CUDA(cudaGetLastError());
+  }
   return PERCNN_OK;
 }
 

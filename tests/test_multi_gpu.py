@@ -40,6 +40,16 @@ def test_fused_halo_stress_full_width_planes():
 
 
 @needs2
+@pytest.mark.parametrize("shape,steps", [(("32", "128", "128"), 23), (("16", "16", "128"), 12), (("128", "128", "128"), 50)])
+def test_time_blocked_small_slab_rollout_over_nvlink(shape, steps):
+    """The communication-avoiding persistent kernel (2K ghost planes every K steps, landing buffers alternating between
+    two pairs) between real peers, repeated so that rank skew gets its chance: 16 / 8 / 64 planes per rank."""
+    rc, out = _torchrun("check_slab.py", ["--shape", *shape, "--steps", str(steps), "--repeat", "25", "--transport", "fused"], 29614)
+    assert "bitwise_equal=True" in out, out[-2000:]
+    assert rc == 0
+
+
+@needs2
 def test_slab_training_step_matches_single_gpu_autograd():
     rc, out = _torchrun("check_slab_bwd.py", ["--shape", "64", "48", "128", "--steps", "6"], 29612)
     assert "ok=True" in out, out[-2000:]
