@@ -20,6 +20,12 @@ namespace tma3d {
 #ifndef PERCNN_BWD_REG_MONO
 #define PERCNN_BWD_REG_MONO 1      // 1: the 20 per-lane monomial sums live in registers (0: shared memory, round 1)
 #endif
+#ifndef PERCNN_BWD_EARLY_H
+#define PERCNN_BWD_EARLY_H 1
+#endif
+#ifndef PERCNN_BWD_PREFETCH
+#define PERCNN_BWD_PREFETCH 1
+#endif
 #ifndef PERCNN_BWD_ALIGNED_ENTRY
 #define PERCNN_BWD_ALIGNED_ENTRY 1
 #endif
@@ -80,16 +86,23 @@ __device__ __forceinline__ void adjoint_plane(Consumer& c, const float* __restri
                                               const Inject<float>& inj, int64_t inj_row, int xq) {
   const float* P = c.P;
   const uint32_t cs = SS >= 0 ? uint32_t(SS) : c.s;
+#if PERCNN_BWD_EARLY_H
+  // stored state of this step: issued BEFORE the wait for the ring (it does not depend on it), L2-prefetched one plane ahead
+  const float4 hu = ldg128(hbase + off);
+  const float4 hv = ldg128(hbase + off + field);
+#endif
   mbar_wait(&c.full[cs], c.parity);   // plane k has landed; planes k-4 .. k-1 are still resident
   const float2 seam_u = seam_next[0], seam_v = seam_next[1];
   if (prefetch_seam) {
     ldg_f2_if(c.is_seam, seam_ptr, seam_next[0]);
     ldg_f2_if(c.is_seam, seam_ptr + field, seam_next[1]);
   }
+#if !PERCNN_BWD_EARLY_H
   // stored state of this step: from global memory, L2-prefetched one plane ahead
   const float4 hu = ldg128(hbase + off);
   const float4 hv = ldg128(hbase + off + field);
-  if (prefetch_next && (c.lane & 7) == 0) {
+#endif
+  if (PERCNN_BWD_PREFETCH && prefetch_next && (c.lane & 7) == 0) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(hbase + off + zstep));
     asm volatile("prefetch.global.L2 [%0];" ::"l"(hbase + off + zstep + field));
     if (gadd != nullptr) {

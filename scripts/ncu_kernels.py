@@ -41,6 +41,31 @@ if which in ("all", "slab"):
     torch.cuda.synchronize()
     del slab
     engine.clear_plans()
+if which in ("all", "slabtrain"):
+    # the cfg5 training step's kernels on the per-rank slab of 8 GPUs: taped slab forward + fused-halo adjoint (ring of one)
+    shape = (64, 512, 512)
+    slab = halo.SlabRollout(cell, shape, dev, 0, 1, transport="fused")
+    slab.set_state(synthetic_state(shape, 0, 64, dev, torch.float32))
+    T = 4
+    tape = slab.rollout_tape(T)
+    sel = (True, False, False, False, False)
+    tgt = torch.rand((1, 2, 32, 256, 256), device=dev)
+    slab.backward(tape, None, loss=(tgt, sel, 2, None))
+    torch.cuda.synchronize()
+    del slab, tape
+    engine.clear_plans()
+    # and the periodic adjoint on the same 64 x 512 x 512 cells, for comparison
+    plan = engine.get_plan(cell._spec(), shape, dev)
+    plan.params_load(flat)
+    a = synthetic_state(shape, 0, 64, dev, torch.float32)
+    tape = torch.empty((T + 1, *plan.buffer_shape), device=dev)
+    plan.rollout_fwd(a, T, tape=tape)
+    spec = engine.DataLossSpec(sel=sel, stride=2)
+    plan.rollout_bwd_loss(flat, tape, T, spec, tgt[0:1].reshape(1, 2, 32, 256, 256))
+    torch.cuda.synchronize()
+    del tape, a, plan
+    engine.clear_plans()
+    torch.cuda.empty_cache()
 if which in ("all", "tile2d"):
     c2 = gs2d.RCNNCell(2, 8, 5)
     c2.load_state_dict(load_weights("gs2d"))
