@@ -227,6 +227,23 @@ def cpu_config_baselines():
     bptt("cfg3i_train", "bur1", load_weights("bur1"), po.ic_fourier_2d(512, seed=1), 10, 40)
     bptt("cfg3ii_train", "bur3", po.make_phys_params("bur3"), po.ic_fourier_2d(512, seed=1, dtype=torch.float64), 10, 40)
     fwd("cfg4", "gs3d", load_gs3d_weights(), po.ic_gs_3d((128, 128, 128), seed=0), 5, 500)
+    try:   # the stock modules of GS3D:41-56 on the host cores, forward + autograd backward
+        torch.manual_seed(0)
+        ct = torch.nn.ConvTranspose3d
+        net = torch.nn.Sequential(ct(2, 8, 5, padding=2, stride=2, output_padding=1), torch.nn.Sigmoid(), ct(8, 8, 5, padding=2, stride=1),
+                                  torch.nn.Conv3d(8, 2, 1))
+        sd = {"convnet.%d.%s" % (i, w): getattr(net[i], w).detach() for i in (0, 2, 3) for w in ("weight", "bias")}
+        low = torch.rand((1, 2, 24, 24, 24))
+        prm = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        po.upscaler_torch(low, prm, "gs3d").sum().backward()       # warm-up
+        t0 = time.perf_counter()
+        for _ in range(3):
+            po.upscaler_torch(low, prm, "gs3d").sum().backward()
+        dt = (time.perf_counter() - t0) / 3
+        out["upscaler_gs3d"] = {"value": dt * 1e6, "unit": "us per forward + autograd backward", "cores": cores, "kind": "port",
+                                "sample": "3 calls, 24^3 -> 48^3, torch.float32"}
+    except Exception as e:  # noqa: BLE001
+        out["upscaler_gs3d"] = {"error": str(e)[:200]}
     return out
 
 
@@ -328,6 +345,25 @@ def gpu_config_blocks(dev, peak):
     h3b = smooth_state_2d(512, dev, torch.float64, 1, -0.5, 0.5)
     guarded(fwd, "cfg3ii_fwd", c3b, h3b, 40, "2-D Burgers 512^2, d/dx d/dy advection stencil cell fp64, 40-step forward")
     guarded(train, "cfg3ii_train", c3b, h3b, 40, "2-D Burgers 512^2, advection stencil cell fp64, back-propagation through 40 steps")
+    def upscale(name, mod, low_shape, desc):
+        torch.manual_seed(0)
+        m = mod.upscaler().to(dev)
+        low = torch.rand((1, 2, *low_shape), device=dev)
+        with torch.no_grad():
+            g = torch.rand_like(m(low))
+
+        def f():
+            with torch.no_grad():
+                m(low)
+
+        def fb():
+            m.zero_grad(set_to_none=True)
+            (m(low) * g).sum().backward()
+
+        out[name] = {"workload": desc, "forward_us": 1e3 * _time_ms(f, 10, dev), "forward_plus_adjoint_us": 1e3 * _time_ms(fb, 10, dev)}
+
+    guarded(upscale, "upscaler_gs3d", gs3d, (24, 24, 24),
+            "initial-state generator of GS3D:41-56 at the script's own size, 24^3 -> 48^3 (fused forward; forward + hand-derived adjoint)")
     c4 = gs3d.RCNNCell(2, 2, 5)
     c4.load_state_dict(load_gs3d_weights())
     guarded(fwd, "cfg4", c4, synthetic_state((128, 128, 128), 0, 128, dev, torch.float32)[None], ROLLOUT_STEPS,

@@ -66,6 +66,15 @@ if which in ("all", "slabtrain"):
     del tape, a, plan
     engine.clear_plans()
     torch.cuda.empty_cache()
+if which in ("all", "slabsmall"):
+    # the communication-avoiding persistent kernel on cfg4's per-rank slab of 8 GPUs (ring of one)
+    shape = (16, 128, 128)
+    slab = halo.SlabRollout(cell, shape, dev, 0, 1, transport="fused")
+    slab.set_state(synthetic_state(shape, 0, 16, dev, torch.float32))
+    slab.run(41)
+    torch.cuda.synchronize()
+    del slab
+    engine.clear_plans()
 if which in ("all", "tile2d"):
     c2 = gs2d.RCNNCell(2, 8, 5)
     c2.load_state_dict(load_weights("gs2d"))
