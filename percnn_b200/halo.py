@@ -159,10 +159,11 @@ class SlabRollout:
         # the per-step hand-shake of round 2's first persistent kernel.
         self._wide = None
         if self.transport == "fused" and self.plan.slab_persistent:
-            # measured on a ring of one (profiles/r02_slab_small_time_blocking.txt): 16 planes of 128^2 want K = 4
-            # (6.3 us/step vs 16.2 with a hand-shake per step), 32 planes K = 2-3 (7.9): the redundant planes of a long
-            # block cost more the deeper the slab
-            k_default = 4 if self.nz <= 16 else (3 if self.nz <= 24 else 2)
+            # measured: 16 planes of 128^2 per rank on 8 GPUs want K = 6 (8.4 us/step; 9.1 at K = 4, 8.5 at K = 8, 19 with
+            # a hand-shake per step -- profiles/r02_cfg4_8gpu_time_blocking.txt); on a ring of one, 32 planes want
+            # K = 2-3 (profiles/r02_slab_small_time_blocking.txt): the redundant planes of a long block cost more the
+            # deeper the slab
+            k_default = 6 if self.nz <= 16 else (3 if self.nz <= 24 else 2)
             k = max(1, min(int(os.environ.get("PERCNN_SLAB_TB_K", str(k_default))), self.nz // 2))
             if k >= 2:
                 wshape = (4, 2, self.nz + 4 * k, H, W)
