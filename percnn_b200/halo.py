@@ -163,7 +163,9 @@ class SlabRollout:
             # a hand-shake per step -- profiles/r02_cfg4_8gpu_time_blocking.txt); on a ring of one, 32 planes want
             # K = 2-3 (profiles/r02_slab_small_time_blocking.txt): the redundant planes of a long block cost more the
             # deeper the slab
-            k_default = 6 if self.nz <= 16 else (3 if self.nz <= 24 else 2)
+            # (over real NVLink the hand-shake is ~2x the ring-of-one's, so deeper slabs also want K = 4: 32 planes per rank on
+            # 4 GPUs 12.0 us/step at K = 2, 64 planes on 2 GPUs 13.4 at K = 2 vs 13.0 at K = 4)
+            k_default = 6 if self.nz <= 16 else 4
             k = max(1, min(int(os.environ.get("PERCNN_SLAB_TB_K", str(k_default))), self.nz // 2))
             if k >= 2:
                 wshape = (4, 2, self.nz + 4 * k, H, W)
