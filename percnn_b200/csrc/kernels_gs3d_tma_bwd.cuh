@@ -68,6 +68,13 @@ __device__ __forceinline__ float2 quad2(const float* __restrict__ d, float2 u, f
 }
 __device__ __forceinline__ float4 ldg128(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
+__device__ __forceinline__ void slab_signal_inline(int which, bool sync_mode, int nbar) {
+  if (sync_mode)
+    asm volatile("bar.sync %0, %1;" ::"r"(which), "r"(nbar) : "memory");
+  else
+    asm volatile("bar.arrive %0, %1;" ::"r"(which), "r"(nbar) : "memory");
+}
+
 // One output plane of the adjoint.  Unlike the forward kernel there is no register window: the five plane
 // centres (z-2..z+2) are all read from the ring (planes k-4..k stay resident), which frees 32 registers for the
 // state, the injected gradient and the pointwise Jacobian -- the windowed version spilled.
@@ -259,13 +266,15 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
 #endif
   __syncthreads();
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // see the forward kernel
-  if (FUSED && warp == BWD_WARPS && lane == 0)   // the ghost pair this march starts from: overlaps the previous kernel's tail
-    wait_flag(p.my_flags + (DOWN ? 1 : 0), p.epoch_wait, p.scratch + 1, p.spin_limit);
-  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int nitems = total_items(p);
 
   if (warp >= BWD_WARPS) {
     if (lane == 0) {
+      // the ghost pair this march starts from: its flag wait overlaps the previous kernel's tail.  (The spin loop lives
+      // inside the producer's branch on purpose: at top level, on every warp's path, it made ptxas treat the consumer
+      // loop as divergent -- 83 R2UR / 27 BRA.DIV in the slab kernels against 15 / 1 in the periodic one.)
+      if (FUSED) wait_flag(p.my_flags + (DOWN ? 1 : 0), p.epoch_wait, p.scratch + 1, p.spin_limit);
+      asm volatile("griddepcontrol.wait;" ::: "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_main)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_halo)) : "memory");
       uint32_t it = 0;
@@ -300,6 +309,7 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
     return;
   }
 
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   // ===== consumer warps =====
   if (FUSED && warp == BWD_WARPS - 1) {   // the helper warp moves the boundary pairs to the neighbours
     slab_helper<DOWN, 1>(p, sm, lane, nitems, reinterpret_cast<uint64_t*>(smem_raw + SLAB_HELPER_OFF),
@@ -370,6 +380,15 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
   };
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
     const ItemCoord ic = decode_item(p, item);
+    // Hand-over to the halo helper (slab_consumer_signal_fn's logic, inline): a real CALL inside this loop made ptxas
+    // treat everything after it as divergent again -- 127 R2UR and 29 BRA.DIV in the slab kernels against 15 and 1 in
+    // the periodic one, +9 % instructions per plane (ncu: 64.5 M vs 59.2 M for 64 planes of 512^2).  `ic` is already
+    // decoded here, so the inline form costs a handful of uniform instructions per item.
+    const bool s_lo = ic.z0 == 0, s_hi = ic.z0 + ic.nz == p.D;
+    const bool own_early = FUSED && !(p.debug & 1) && (DOWN ? s_hi : s_lo);
+    const bool own_late = FUSED && !(p.debug & 1) && !p.defer_late && (DOWN ? s_lo : s_hi);
+    const bool sync_mode = nitems > int(gridDim.x);
+    const int nbar = (p.ty + 1) * 32;
     // rows below the natural start of this tile are duplicates of the previous tile (last tile shifted back)
     const bool valid = (ic.y0 + warp) >= ic.ytile * p.ty;
     // fused data loss: is this warp's row on the sampling lattice, and where does it start in the low-res frame
@@ -412,7 +431,7 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
                                    k + 1 < nk, valid, seam_next, aacc, macc, x.inj, inj_row, ic.x0 + 4 * lane);
 #endif
         off += zstep;
-        if (FUSED && k == 5) slab_consumer_signal<DOWN, 1>(p, item);   // first boundary pair stored: over to the helper
+        if (FUSED && k == 5 && own_early) slab_signal_inline(1, sync_mode, nbar);   // first boundary pair stored: over to the helper
         zi += DOWN ? -1 : 1;
         if (++since_flush >= BWD_FLUSH) flush();
       }
@@ -425,7 +444,7 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
 #pragma unroll
       for (int j = 1; j <= 4; ++j) mbar_arrive(&c.empty[(c.s + STAGES - j) & (STAGES - 1)]);
     }
-    if (FUSED) slab_consumer_signal<DOWN, 2>(p, item);
+    if (FUSED && own_late) slab_signal_inline(2, sync_mode, nbar);
   }
   flush();
   // ---- CTA result -> global partials; the last CTA folds all CTAs in fixed order ----
