@@ -9,36 +9,25 @@
 // from the ring too instead of a register window);
 // the stored state h_t (centre only, no halo) and the injected loss gradient g_add are read with coalesced
 // 128-bit loads one plane ahead.  Algorithmic traffic: 24 B/cell (+8 with g_add).
-// Reductions: per-lane fp32 partial sums, flushed every 32 planes into per-warp fp64 accumulators in shared
-// memory; per-CTA results go to global memory and the last CTA folds them in fixed order (deterministic).
+// Reductions: per-lane fp32 partial sums in registers, flushed every 32 planes into per-warp fp64 accumulators in
+// shared memory; per-CTA results go to global memory and the last CTA folds them in fixed order (deterministic).
+// Round-2 history of this kernel (813 -> 707-714 us per 512^3 step; every step A/B-timed, profiles/
+// r02_adjoint_variants.txt): monomial sums from shared memory into registers, an aligned barrier at the consumers'
+// entry and no CALL / top-level spin loop on their path (keeps the loop on the uniform datapath), state loads
+// before the ring wait, last-CTA fold shared by all warps.  Tried and dropped: compile-time ring stages through a
+// switch (8x the loop body, instruction-cache bound, +36 %), no L2 prefetch (neutral).
 #pragma once
 #include "kernels_gs3d_slab.cuh"
 
 namespace percnn {
 namespace tma3d {
 
-#ifndef PERCNN_BWD_REG_MONO
-#define PERCNN_BWD_REG_MONO 1      // 1: the 20 per-lane monomial sums live in registers (0: shared memory, round 1)
-#endif
-#ifndef PERCNN_BWD_EARLY_H
-#define PERCNN_BWD_EARLY_H 1
-#endif
-#ifndef PERCNN_BWD_PREFETCH
-#define PERCNN_BWD_PREFETCH 1
-#endif
-#ifndef PERCNN_BWD_ALIGNED_ENTRY
-#define PERCNN_BWD_ALIGNED_ENTRY 1
-#endif
-#ifndef PERCNN_BWD_STATIC_STAGE
-#define PERCNN_BWD_STATIC_STAGE 0
-#endif
-static_assert(STAGES == 8, "the static-stage switch of the adjoint enumerates 8 ring stages");
 constexpr int BWD_FLUSH = 32;
 // The adjoint holds 22 running sums and the state on top of the 5-plane window: 15 consumer warps + 1 producer
 // warp = 512 threads = 128 registers per thread (a 17th warp would round the allocation down to 96).
 constexpr int BWD_WARPS = 15;
 constexpr int BWD_THREADS = (BWD_WARPS + 1) * 32;
-constexpr int SMEM_BYTES_BWD = SMEM_BYTES + 16 * kRedPiK1 * 8 + 64 + 10 * BWD_THREADS * 8;
+constexpr int SMEM_BYTES_BWD = SMEM_BYTES + 16 * kRedPiK1 * 8 + 64;
 // slab mode: the halo helper's staging rows come after everything else (half a boundary pair: two chunks per pair)
 constexpr int BWD_STAGE_OFF = (SMEM_BYTES_BWD + 127) / 128 * 128;   // TMA destinations are 128-byte aligned
 constexpr int SMEM_BYTES_BWD_SLAB = BWD_STAGE_OFF + SLAB_FIELD_PAIR_BYTES;
@@ -49,17 +38,11 @@ struct BwdExtra {
   const float* gadd;     // injected gradient for this step (nullable)
   double* partials;      // [gridDim.x][2 or 22]
   unsigned* counter;
-  double* acc;           // [22] running sums over steps ([0..1] from this kernel, [2..21] from k_monomial_sums)
+  double* acc;           // [22] running sums over steps
   Inject<float> inj;     // fused data-loss gradient of this step's state (target == nullptr: none)
 };
 
-#if PERCNN_BWD_REG_MONO
-typedef float2 (&MonoAcc)[10];
-#define PERCNN_MACC(M) macc[M]
-#else
-typedef float2* __restrict__ MonoAcc;
-#define PERCNN_MACC(M) macc[(M) * BWD_THREADS]
-#endif
+typedef float2 (&MonoAcc)[10];   // the 20 per-lane monomial sums: (sum_u, sum_v) per monomial, in registers
 
 __device__ __forceinline__ float2 quad2(const float* __restrict__ d, float2 u, float2 v) {
   float2 a0 = fma2(u, fma2(u, d[3], d[1]), d[0]);
@@ -81,10 +64,7 @@ __device__ __forceinline__ void slab_signal_inline(int which, bool sync_mode, in
 // `valid`: this warp's row is not a duplicate of the previous tile's rows (last tile of a column is shifted
 // back), so it contributes to the reductions.
 // `DOWN`: the item is marched towards decreasing z (slab kernel, odd steps); `zstep` = +-plane accordingly.
-// `SS`: the ring stage of the arriving plane as a compile-time constant (PERCNN_BWD_STATIC_STAGE: the caller switches
-// over c.s, so every ring / mbarrier address below is `base + immediate` instead of ~30 integer instructions per
-// plane); SS < 0: use c.s at run time.
-template <bool FUSED, bool DOWN, int SS = -1>
+template <bool FUSED, bool DOWN>
 __device__ __forceinline__ void adjoint_plane(Consumer& c, const float* __restrict__ TP, bool prefetch_seam,
                                               const float* seam_ptr, int64_t field, int64_t zstep, int64_t off,
                                               float* __restrict__ dst, float* mirror, const float* __restrict__ hbase,
@@ -92,24 +72,18 @@ __device__ __forceinline__ void adjoint_plane(Consumer& c, const float* __restri
                                               float2 (&seam_next)[2], float (&aacc)[2], MonoAcc macc,
                                               const Inject<float>& inj, int64_t inj_row, int xq) {
   const float* P = c.P;
-  const uint32_t cs = SS >= 0 ? uint32_t(SS) : c.s;
-#if PERCNN_BWD_EARLY_H
-  // stored state of this step: issued BEFORE the wait for the ring (it does not depend on it), L2-prefetched one plane ahead
+  const uint32_t cs = c.s;
+  // stored state of this step: issued BEFORE the wait for the ring (it does not depend on it: ~740 -> 707 us per 512^3
+  // step), L2-prefetched one plane ahead
   const float4 hu = ldg128(hbase + off);
   const float4 hv = ldg128(hbase + off + field);
-#endif
   mbar_wait(&c.full[cs], c.parity);   // plane k has landed; planes k-4 .. k-1 are still resident
   const float2 seam_u = seam_next[0], seam_v = seam_next[1];
   if (prefetch_seam) {
     ldg_f2_if(c.is_seam, seam_ptr, seam_next[0]);
     ldg_f2_if(c.is_seam, seam_ptr + field, seam_next[1]);
   }
-#if !PERCNN_BWD_EARLY_H
-  // stored state of this step: from global memory, L2-prefetched one plane ahead
-  const float4 hu = ldg128(hbase + off);
-  const float4 hv = ldg128(hbase + off + field);
-#endif
-  if (PERCNN_BWD_PREFETCH && prefetch_next && (c.lane & 7) == 0) {
+  if (prefetch_next && (c.lane & 7) == 0) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(hbase + off + zstep));
     asm volatile("prefetch.global.L2 [%0];" ::"l"(hbase + off + zstep + field));
     if (gadd != nullptr) {
@@ -191,11 +165,11 @@ __device__ __forceinline__ void adjoint_plane(Consumer& c, const float* __restri
     const float2 el = EL, eh = EH;                                                                  \
     const float2 tu = fma2(guh, eh, __fmul2_rn(gul, el));                                           \
     const float2 tv = fma2(gvh, eh, __fmul2_rn(gvl, el));                                           \
-    PERCNN_MACC(M) = __fadd2_rn(PERCNN_MACC(M), make_float2(tu.x + tu.y, tv.x + tv.y));             \
+    macc[M] = __fadd2_rn(macc[M], make_float2(tu.x + tu.y, tv.x + tv.y));                           \
   }
     {
       const float2 tu = __fadd2_rn(gul, guh), tv = __fadd2_rn(gvl, gvh);
-      PERCNN_MACC(0) = __fadd2_rn(PERCNN_MACC(0), make_float2(tu.x + tu.y, tv.x + tv.y));
+      macc[0] = __fadd2_rn(macc[0], make_float2(tu.x + tu.y, tv.x + tv.y));
     }
     PERCNN_MONO(1, ul, uh)
     PERCNN_MONO(2, vl, vh)
@@ -257,13 +231,7 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
     if (FUSED) mbar_init(reinterpret_cast<uint64_t*>(smem_raw + SLAB_HELPER_OFF), 1);   // (sits in the padding before wacc)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  float2* macc_all = reinterpret_cast<float2*>(wacc + 16 * kRedPiK1);   // [10][BWD_THREADS] per-lane monomial sums
   for (int i = threadIdx.x; i < TY * kRedPiK1; i += BWD_THREADS) wacc[i] = 0.0;
-#if !PERCNN_BWD_REG_MONO
-  for (int m = 0; m < 10; ++m) macc_all[m * BWD_THREADS + threadIdx.x] = make_float2(0.f, 0.f);
-#else
-  (void)macc_all;
-#endif
   __syncthreads();
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // see the forward kernel
   const int nitems = total_items(p);
@@ -317,7 +285,6 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
     return;
   }
   if (warp >= p.ty) return;
-#if PERCNN_BWD_ALIGNED_ENTRY
   // An ALIGNED barrier among the consumer warps: every thread of a warp executes it together, which tells the compiler
   // that the warps are converged from here on.  Without it ptxas treats the whole consumer loop as potentially
   // divergent (the role split above branches on threadIdx): loop state lives in vector registers, every LDG / STG
@@ -325,7 +292,6 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
   // 24 BRA.DIV in the kernel without it, 15 and 0 with it, 5 registers fewer, 783 -> 743 us per 512^3 adjoint step
   // (profiles/r02_adjoint_variants.txt).  The forward kernel gets the same guarantee from setmaxnreg.sync.aligned.
   asm volatile("bar.sync 4, %0;" ::"r"(p.ty * 32) : "memory");
-#endif
   Consumer c;
   c.P = c_prep[SLOT].f;
   c.ring = ring;
@@ -345,13 +311,9 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
   float2 seam_next[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
   float aacc[2] = {0.f, 0.f};
   int since_flush = 0;
-#if PERCNN_BWD_REG_MONO
   float2 macc[10];
 #pragma unroll
   for (int m = 0; m < 10; ++m) macc[m] = make_float2(0.f, 0.f);
-#else
-  float2* macc = macc_all + threadIdx.x;
-#endif
   auto flush = [&]() {   // per-lane fp32 partial sums -> per-warp fp64 accumulators (every BWD_FLUSH planes)
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -364,8 +326,8 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
     const float dt = c.P[P_DT];
 #pragma unroll
     for (int m = 0; m < 10; ++m) {
-      float2 t = PERCNN_MACC(m);
-      PERCNN_MACC(m) = make_float2(0.f, 0.f);
+      float2 t = macc[m];
+      macc[m] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) {
         t.x += __shfl_down_sync(0xffffffffu, t.x, off);
@@ -415,21 +377,8 @@ k_gs3d_bwd_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constan
         seam_ptr += zstep;
         int64_t inj_row = -1;
         if (inj_ly >= 0 && zi % x.inj.s == 0) inj_row = (int64_t(zi / x.inj.s) * x.inj.lh + inj_ly) * x.inj.lw;
-#if PERCNN_BWD_STATIC_STAGE
-#define PERCNN_BWD_CASE(S)                                                                                              \
-  case S:                                                                                                               \
-    adjoint_plane<false, DOWN, S>(c, TP, k <= ic.nz + 2, seam_ptr, field, zstep, off, p.dst, nullptr, x.h, x.gadd,      \
-                                  k + 1 < nk, valid, seam_next, aacc, macc, x.inj, inj_row, ic.x0 + 4 * lane);          \
-    break;
-        switch (c.s) {
-          PERCNN_BWD_CASE(0) PERCNN_BWD_CASE(1) PERCNN_BWD_CASE(2) PERCNN_BWD_CASE(3)
-          PERCNN_BWD_CASE(4) PERCNN_BWD_CASE(5) PERCNN_BWD_CASE(6) PERCNN_BWD_CASE(7)
-        }
-#undef PERCNN_BWD_CASE
-#else
         adjoint_plane<false, DOWN>(c, TP, k <= ic.nz + 2, seam_ptr, field, zstep, off, p.dst, nullptr, x.h, x.gadd,
                                    k + 1 < nk, valid, seam_next, aacc, macc, x.inj, inj_row, ic.x0 + 4 * lane);
-#endif
         off += zstep;
         if (FUSED && k == 5 && own_early) slab_signal_inline(1, sync_mode, nbar);   // first boundary pair stored: over to the helper
         zi += DOWN ? -1 : 1;
