@@ -439,6 +439,113 @@ __global__ void __launch_bounds__(kThreads) k_up_corr(Grid ga, Grid gb, int ndim
     }
   }
 }
+// ---- the dominant correlation (3-D, stride 1, A = dL/dh0 with 2 channels, B = the 8 stored activations) on shared-
+// memory tiles: R[f][ci][kz][ky][kx] = sum g[f, z, y, x] mid[ci, z + 2 - kz, y + 2 - ky, x + 2 - kx].
+// A block owns an xy tile (C3_TY x C3_TX cells of A) and a chunk of z planes and MARCHES along z with the last five mid
+// planes of the tile (+2 halo in x and y, zero-filled outside the grid = the transposed conv's zero padding) in a ring
+// in shared memory, so every mid value is loaded once per chunk and then feeds 250 multiply-adds from shared memory.
+// Thread = (ci, kz, ky) x half of the tile rows: it slides along x with a 5-value register window of its mid row
+// and keeps the 5 kx x 2 f sums in registers: 3 LDS (one of them a broadcast) per 10 FFMA.  Row and slot strides are
+// padded (69 / 6625 floats) so that the 32 (ky, kz, ci) rows a warp reads fall into distinct banks.
+// The generic kernel above (one warp per combination, operands from L1) spent 0.58 ms on the 48^3 grid of the
+// script itself and ~20 ms at 256^3, 3 % of the FP32 pipe.
+constexpr int C3_TY = 8, C3_TX = 64, C3_CB = 8, C3_THREADS = 512;
+constexpr int C3_ROWS = C3_TY + 4, C3_STRIDE = C3_TX + 5;                 // 12 rows of 69 floats per channel
+constexpr int C3_SLOT = C3_CB * C3_ROWS * C3_STRIDE + 1;                  // 6625 floats per ring slot
+constexpr int C3_SMEM_FLOATS = 5 * C3_SLOT + 2 * C3_TY * C3_TX;
+__global__ void __launch_bounds__(C3_THREADS, 1) k_up_corr3(Grid ga, Grid gb, int ntx, int nty, int zc, const float* __restrict__ A,
+                                                           const float* __restrict__ B, double* __restrict__ partials) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* ring = reinterpret_cast<float*>(smem_raw);
+  float* gt = ring + 5 * C3_SLOT;                                          // [2][TY][TX]
+  __shared__ double s_half[200 * 10];
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x % (ntx * nty), chunk = blockIdx.x / (ntx * nty);
+  const int x0 = (tile % ntx) * C3_TX, y0 = (tile / ntx) * C3_TY;
+  const int zb = ga.z0 + chunk * zc, ze = min(zb + zc, ga.z0 + ga.nz);     // output planes [zb, ze)
+  const bool worker = tid < 400;
+  const int combo = tid % 200, half = tid / 200;                           // (half 2 = the 112 spare threads)
+  const int ky = combo % 5, kz = (combo / 5) % 5, ci = combo / 25;
+  float acc[2][5];
+#pragma unroll
+  for (int f = 0; f < 2; ++f)
+#pragma unroll
+    for (int k = 0; k < 5; ++k) acc[f][k] = 0.f;
+  float gsum = 0.f;                                                        // threads 400, 401: sum of g[f] over the tile
+  auto load_mid_plane = [&](int zp) {                                      // global plane zp -> ring slot zp mod 5
+    float* slot = ring + ((zp % 5 + 5) % 5) * C3_SLOT;
+    const bool zok = zp >= 0 && zp < gb.D;
+    for (int e = tid; e < C3_CB * C3_ROWS * (C3_TX + 4); e += C3_THREADS) {
+      const int mx = e % (C3_TX + 4);
+      const int my = (e / (C3_TX + 4)) % C3_ROWS;
+      const int c = e / ((C3_TX + 4) * C3_ROWS);
+      const int gx = x0 - 2 + mx, gy = y0 - 2 + my;
+      float v = 0.f;
+      if (zok && gx >= 0 && gx < gb.W && gy >= 0 && gy < gb.H) v = __ldg(B + int64_t(c) * gb.cstride + at(gb, zp, gy, gx));
+      slot[(c * C3_ROWS + my) * C3_STRIDE + mx] = v;
+    }
+  };
+  for (int zp = zb - 2; zp < zb + 2; ++zp) load_mid_plane(zp);             // warm-up: planes z-2 .. z+1 of the first output plane
+  for (int z = zb; z < ze; ++z) {
+    load_mid_plane(z + 2);
+    for (int e = tid; e < 2 * C3_TY * C3_TX; e += C3_THREADS) {
+      const int rx = e % C3_TX, ry = (e / C3_TX) % C3_TY, f = e / (C3_TX * C3_TY);
+      const int gx = x0 + rx, gy = y0 + ry;
+      gt[e] = (gx < ga.W && gy < ga.H) ? __ldg(A + int64_t(f) * ga.cstride + at(ga, z, gy, gx)) : 0.f;
+    }
+    __syncthreads();
+    if (worker) {
+      const int zs = z + 2 - kz;                                           // mid plane of this thread's tap
+      const float* mslot = ring + ((zs % 5 + 5) % 5) * C3_SLOT + ci * C3_ROWS * C3_STRIDE;
+#pragma unroll 1
+      for (int r = 0; r < C3_TY / 2; ++r) {
+        const int ry = half * (C3_TY / 2) + r;
+        const float* mrow = mslot + (ry + 4 - ky) * C3_STRIDE;             // mid row y + 2 - ky; element j <-> x0 - 2 + j
+        const float* g0 = gt + ry * C3_TX;
+        const float* g1 = g0 + C3_TY * C3_TX;
+        // window w[j] = mid[x + j - 2 .. ], tap kx reads mid[x + 2 - kx] = mrow[rx + 4 - kx]
+        float w0 = mrow[0], w1 = mrow[1], w2 = mrow[2], w3 = mrow[3];
+#pragma unroll 4
+        for (int rx = 0; rx < C3_TX; ++rx) {
+          const float w4 = mrow[rx + 4];
+          const float a0 = g0[rx], a1 = g1[rx];
+          acc[0][0] = fmaf(a0, w4, acc[0][0]); acc[1][0] = fmaf(a1, w4, acc[1][0]);   // kx = 0 -> mrow[rx + 4]
+          acc[0][1] = fmaf(a0, w3, acc[0][1]); acc[1][1] = fmaf(a1, w3, acc[1][1]);
+          acc[0][2] = fmaf(a0, w2, acc[0][2]); acc[1][2] = fmaf(a1, w2, acc[1][2]);
+          acc[0][3] = fmaf(a0, w1, acc[0][3]); acc[1][3] = fmaf(a1, w1, acc[1][3]);
+          acc[0][4] = fmaf(a0, w0, acc[0][4]); acc[1][4] = fmaf(a1, w0, acc[1][4]);   // kx = 4 -> mrow[rx]
+          w0 = w1; w1 = w2; w2 = w3; w3 = w4;
+        }
+      }
+    } else if (tid < 402) {
+      const float* gf = gt + (tid - 400) * C3_TY * C3_TX;
+      float t = 0.f;
+      for (int e = 0; e < C3_TY * C3_TX; ++e) t += gf[e];
+      gsum += t;
+    }
+    __syncthreads();                                                       // the slot of plane z - 2 and the g tile are rewritten next
+  }
+  // fold the two row halves in fp64 and store this block's partial vector
+  const int NS = 2 * C3_CB * 125;
+  double* out = partials + size_t(blockIdx.x) * (NS + 2);
+  if (worker && half == 1) {
+#pragma unroll
+    for (int f = 0; f < 2; ++f)
+#pragma unroll
+      for (int k = 0; k < 5; ++k) s_half[combo * 10 + f * 5 + k] = double(acc[f][k]);
+  }
+  __syncthreads();
+  if (worker && half == 0) {
+#pragma unroll
+    for (int f = 0; f < 2; ++f)
+#pragma unroll
+      for (int kx = 0; kx < 5; ++kx)
+        out[(f * C3_CB + ci) * 125 + (kz * 5 + ky) * 5 + kx] = double(acc[f][kx]) + s_half[combo * 10 + f * 5 + kx];
+  } else if (tid >= 400 && tid < 402) {
+    out[NS + (tid - 400)] = double(gsum);
+  }
+}
+
 __global__ void __launch_bounds__(256) k_up_fold(const double* __restrict__ partials, int nblocks, int n, double* __restrict__ sums) {
   // 32 sums per block; eight thread groups stride over the partial vectors (coalesced along the sums, eight loads in
   // flight per sum instead of one serial chain of L2 round trips), then a fixed-order fold of the eight

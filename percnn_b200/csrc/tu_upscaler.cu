@@ -1,5 +1,8 @@
 // Translation unit: the initial-state generator ("upscaler"), its adjoint and the IC loss.
 // Stand-alone entry points (no plan): percnn_upscaler_sizes / _fwd / _bwd, percnn_mse_fwd / _bwd.
+#include <cstdlib>
+#include <type_traits>
+
 #include "kernels_upscaler.cuh"
 #include "plan.h"
 
@@ -151,6 +154,28 @@ int corr(const Grid& ga, const Grid& gb, int ndim, int S, int CA, int CB, int si
   return PERCNN_OK;
 }
 
+// The dominant correlation (3-D, stride 1, dL/dh0 x the 8 stored activations, fp32) on shared-memory tiles.
+int corr3(const Grid& ga, const Grid& gb, const float* A, const float* B, int n, double* partials, double* sums, cudaStream_t st) {
+  const int ntx = (ga.W + C3_TX - 1) / C3_TX, nty = (ga.H + C3_TY - 1) / C3_TY;
+  int zc = 1;                                         // planes per chunk: as few as keeps the block count <= kCorrMaxVB
+  while (int64_t(ntx) * nty * ((ga.nz + zc - 1) / zc) > kCorrMaxVB) ++zc;
+  const int nblocks = ntx * nty * ((ga.nz + zc - 1) / zc);
+  const size_t smem = size_t(C3_SMEM_FLOATS) * sizeof(float);
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    if (cudaFuncSetAttribute(k_up_corr3, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+      return fail(PERCNN_ERR_CUDA, "cudaFuncSetAttribute(k_up_corr3) failed");
+    attr_set[dev] = true;
+  }
+  k_up_corr3<<<nblocks, C3_THREADS, smem, st>>>(ga, gb, ntx, nty, zc, A, B, partials);
+  PERCNN_CUDA(cudaGetLastError());
+  k_up_fold<<<(n + 31) / 32, 256, 0, st>>>(partials, nblocks, n, sums);
+  PERCNN_CUDA(cudaGetLastError());
+  return PERCNN_OK;
+}
+
 template <typename T, int NDIM, int C>
 int bwd_t(const UpGeom& u, const T* raw, const T* low, const T* mid, const T* g, T* gp, int accumulate, char* ws, cudaStream_t st) {
   T* prep = reinterpret_cast<T*>(ws + u.off_prep);
@@ -184,7 +209,15 @@ int bwd_t(const UpGeom& u, const T* raw, const T* low, const T* mid, const T* g,
       kg<<<blocks_for(tiles), kThreads, smg, st>>>(u.own, u.out, u.act, prep, mid_own, g, gm, u.mid.cstride);
     }
     PERCNN_CUDA(cudaGetLastError());
-    if (int rc = corr<T>(u.out, u.mid, u.ndim, u.S2, 2, C, 0, g, mid, u.n2, partials, sums2, st)) return rc;
+    if constexpr (std::is_same<T, float>::value && NDIM == 3 && C == C3_CB) {
+      if (u.S2 == 1 && !getenv("PERCNN_UP_GENERIC_CORR")) {
+        if (int rc = corr3(u.out, u.mid, g, mid, u.n2, partials, sums2, st)) return rc;
+      } else if (int rc = corr<T>(u.out, u.mid, u.ndim, u.S2, 2, C, 0, g, mid, u.n2, partials, sums2, st)) {
+        return rc;
+      }
+    } else if (int rc = corr<T>(u.out, u.mid, u.ndim, u.S2, 2, C, 0, g, mid, u.n2, partials, sums2, st)) {
+      return rc;
+    }
   }
   if (int rc = corr<T>(u.own, u.low, u.ndim, 2, C, 2, 0, gm, low, u.n1, partials, sums1, st)) return rc;
   k_up_finish<T><<<32, 256, 0, st>>>(raw, sums1, sums2, C, u.K, u.layers, gp, accumulate);
