@@ -23,7 +23,7 @@ struct UpGeom {
 
 size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
-int up_geom(const percnn_upscaler_t* d, UpGeom* u) {
+int up_geom(const percnn_upscaler_t* d, UpGeom* u, bool need_device = true) {
   if (!d) return fail(PERCNN_ERR_INVALID, "null upscaler descriptor");
   if (d->ndim != 2 && d->ndim != 3) return fail(PERCNN_ERR_INVALID, "ndim must be 2 or 3");
   if (d->dtype != PERCNN_F32 && d->dtype != PERCNN_F64) return fail(PERCNN_ERR_INVALID, "dtype must be f32 or f64");
@@ -34,7 +34,7 @@ int up_geom(const percnn_upscaler_t* d, UpGeom* u) {
   for (int i = 0; i < 3; ++i)
     if (d->low_extent[i] < 1 || d->low_extent[i] > (1 << 14)) return fail(PERCNN_ERR_INVALID, "bad low-resolution extents");
   if (d->ndim == 2 && d->low_extent[0] != 1) return fail(PERCNN_ERR_INVALID, "2-D needs low_extent[0] == 1");
-  if (!percnn_device_ok(d->device)) return fail(PERCNN_ERR_NO_DEVICE, "no sm_100 CUDA device with this ordinal");
+  if (need_device && !percnn_device_ok(d->device)) return fail(PERCNN_ERR_NO_DEVICE, "no sm_100 CUDA device with this ordinal");
   const bool three = d->ndim == 3;
   u->ndim = d->ndim;
   u->C = d->channels;
@@ -257,7 +257,7 @@ extern "C" {
 int percnn_upscaler_sizes(const percnn_upscaler_t* d, int64_t* nparams, int64_t* mid_elems, int64_t* out_extent,
                           size_t* ws_bytes) {
   UpGeom u;
-  if (int rc = up_geom(d, &u)) return rc;
+  if (int rc = up_geom(d, &u, /*need_device=*/false)) return rc;   // pure host arithmetic: usable for planning without a GPU
   if (nparams) *nparams = u.raw.total;
   if (mid_elems) *mid_elems = u.mid_elems;
   if (out_extent) {

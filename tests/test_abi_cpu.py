@@ -232,3 +232,44 @@ def test_stage3_burgers_checkpoint_with_stale_keys_loads():
     del sd["crnn_cell.C1_u"]
     with pytest.raises(RuntimeError):
         model.load_state_dict(sd)
+
+
+def test_upscaler_slab_geometry_partitions_the_grid():
+    """percnn_upscaler_sizes is host arithmetic (no device needed): for every rank count the per-rank activation tapes
+    must cover what that rank's output planes read (2 planes of halo, clipped at the global border) and the output
+    extents / parameter counts must match the reference's layers (GS3D:41-56: 2 -> 8 -> 8 -> 2, kernels of 125)."""
+    import ctypes
+    from percnn_b200 import _lib
+    L = _lib.lib()
+
+    def sizes(low, z0=0, nz=0, stride2=1, ndim=3, channels=8, layers=2):
+        d = _lib.Upscaler()
+        d.ndim, d.dtype, d.channels, d.act, d.layers, d.stride2, d.device = ndim, _lib.F32, channels, 0, layers, stride2, 0
+        ext = (1,) + tuple(low) if ndim == 2 else tuple(low)
+        for i in range(3):
+            d.low_extent[i] = ext[i]
+        d.out_z0, d.out_nz, d.out_field_stride = z0, nz, 0
+        npar, mid, ws = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_size_t()
+        out = (ctypes.c_int64 * 3)()
+        rc = L.percnn_upscaler_sizes(ctypes.byref(d), ctypes.byref(npar), ctypes.byref(mid), out, ctypes.byref(ws))
+        return rc, npar.value, mid.value, tuple(out), ws.value
+
+    rc, npar, mid, out, ws = sizes((24, 24, 24))
+    assert rc == 0 and out == (48, 48, 48)
+    assert npar == 2 * 8 * 125 + 8 + 8 * 8 * 125 + 8 + 2 * 8 + 2          # GS3D:45-52
+    assert mid == 8 * 48 ** 3 and ws > 0
+    for world in (2, 3, 4, 6, 8):
+        nz = 48 // world
+        for r in range(world):
+            rc, _, mid_r, _, _ = sizes((24, 24, 24), z0=r * nz, nz=nz)
+            assert rc == 0
+            lo, hi = max(r * nz - 2, 0), min(r * nz + nz + 2, 48)          # stride-1 second layer: planes z-2 .. z+2
+            assert mid_r == 8 * (hi - lo) * 48 * 48, (world, r)
+    # GS2D (two stride-2 layers): 25^2 -> 100^2, and the one-layer Stage-1 net: 50^2 -> 100^2 with 16 channels
+    assert sizes((25, 25), stride2=2, ndim=2)[3] == (1, 100, 100)
+    rc, npar, mid, out, _ = sizes((50, 50), ndim=2, channels=16, layers=1)
+    assert rc == 0 and out == (1, 100, 100) and npar == 2 * 16 * 25 + 16 + 2 * 16 + 2 and mid == 16 * 100 * 100
+    # rejected: a plane range that does not lie in the grid, slab ranges for 2-D nets, bad channel counts
+    assert sizes((24, 24, 24), z0=40, nz=16)[0] != 0
+    assert sizes((25, 25), z0=0, nz=10, ndim=2, stride2=2)[0] != 0
+    assert sizes((24, 24, 24), channels=12)[0] != 0
