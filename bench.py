@@ -526,13 +526,21 @@ def run_ours(args):
         # end-to-end: each rank uploads its slab from pinned host memory and downloads the final slab
         h_h = slab.interior().cpu().pin_memory()
         out_h = torch.empty_like(h_h).pin_memory()
+
+        def e2e_once():
+            slab.set_state_from_host(h_h)          # two async H2D copies straight into the slab buffer + ghost exchange
+            slab.run(ROLLOUT_STEPS)
+            slab.interior_to_host(out_h)           # two async D2H copies
+            barrier()
+
+        e2e_once()                                 # warm-up of this path (the N = 1 leg warms its host path too)
+        e2e_reps = max(1, min(args.steps, 3))
         barrier()
         t0 = time.perf_counter()
-        slab.set_state(h_h.to(dev, non_blocking=True))
-        slab.run(ROLLOUT_STEPS)
-        out_h.copy_(slab.interior(), non_blocking=True)
-        barrier()
-        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        for _ in range(e2e_reps):
+            e2e_once()
+        e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_reps)
+        assert torch.isfinite(out_h).all()
         e2e = {"value": ROLLOUT_STEPS / e2e_s, "unit": "timesteps/s", "h2d_bytes_per_step": int(h_h.numel() * 4) * world,
                "d2h_bytes_per_step": int(out_h.numel() * 4) * world, "api": "percnn_b200.halo.SlabRollout (per-rank pinned slabs)"}
         extra["halo"] = slab.describe()

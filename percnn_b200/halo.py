@@ -189,10 +189,27 @@ class SlabRollout:
         self._extra_launches = 0
 
     # -- state ----------------------------------------------------------------------------------
+    def set_state_from_host(self, host: torch.Tensor) -> None:
+        """Like set_state, from a (pinned) HOST tensor [2][nz][H][W]: each field's planes are one contiguous block of the
+        slab buffer, so the upload is two asynchronous copies straight into place (no staging tensor, no second pass)."""
+        b = self.bufs[self.cur]
+        for f in range(2):
+            b[f, 2:self.nz + 2].copy_(host[f], non_blocking=True)
+        self._publish_state()
+
+    def interior_to_host(self, host: torch.Tensor) -> None:
+        """The current slab into a (pinned) host tensor [2][nz][H][W]: two asynchronous copies; synchronise before reading."""
+        b = self.bufs[self.cur]
+        for f in range(2):
+            host[f].copy_(b[f, 2:self.nz + 2], non_blocking=True)
+
     def set_state(self, interior: torch.Tensor) -> None:
         """interior: [2][nz][H][W] slab of the global field (planes z0 .. z0+nz)."""
         b = self.bufs[self.cur]
         b[:, 2:self.nz + 2].copy_(interior)
+        self._publish_state()
+
+    def _publish_state(self) -> None:
         self._exchange_blocking(self.cur)
         if self.transport == "fused":
             # ghosts of the current buffer are valid up to the current epoch on every rank

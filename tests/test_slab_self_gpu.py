@@ -138,3 +138,25 @@ def test_time_blocked_slab_rollout_is_bitwise_equal(shape, k, steps, monkeypatch
     err = float((slab.interior() - ref[2 * steps + 1]).abs().max() / ref[2 * steps + 1].abs().max())
     assert err <= 2e-6, err
     assert slab.error_word() == 0
+
+
+def test_host_upload_and_download_of_a_slab():
+    """set_state_from_host / interior_to_host (the end-to-end leg of bench.py at N > 1): same state and ghosts as set_state."""
+    cell = _cell()
+    shape = (24, 32, 128)
+    h0 = _state(shape, 12)
+    slab = halo.SlabRollout(cell, shape, DEV, 0, 1, transport="fused")
+    host = h0.cpu().pin_memory()
+    slab.set_state_from_host(host)
+    assert torch.equal(slab.interior(), h0)
+    b = slab.bufs[slab.cur]
+    assert torch.equal(b[:, 0:2], h0[:, -2:]) and torch.equal(b[:, 26:28], h0[:, 0:2])
+    slab.run(4)
+    out = torch.empty_like(host).pin_memory()
+    slab.interior_to_host(out)
+    torch.cuda.synchronize()
+    assert torch.equal(out, slab.interior().cpu())
+    slab2 = halo.SlabRollout(cell, shape, DEV, 0, 1, transport="fused")
+    slab2.set_state(h0)
+    slab2.run(4)
+    assert torch.equal(out, slab2.interior().cpu())
