@@ -70,9 +70,14 @@ def test_rcnn_forward_and_gradients_match_the_reference_class(alias):
 
 
 def _get_ic_loss_gs2d(model):
-    """GS2D:331-338"""
-    init_state_bicubic = F.interpolate(model.init_state_low, (100, 100), mode="bicubic")
-    return nn.MSELoss()(model.UpconvBlock(model.init_state_low), init_state_bicubic)
+    """GS2D:331-338 through the drop-in of the same name (fused upscaler + fused MSE); the stock formulation on the same
+    model must agree (it differs only in who computes the mean)."""
+    loss = gs2d.get_ic_loss(model)
+    with torch.no_grad():
+        init_state_bicubic = F.interpolate(model.init_state_low, (100, 100), mode="bicubic")
+        stock = nn.MSELoss()(model.UpconvBlock(model.init_state_low), init_state_bicubic)
+    assert abs(loss.item() - stock.item()) <= 2e-6 * abs(stock.item())
+    return loss
 
 
 def test_train_loop_of_train_2drd_reproduces_the_reference_loss_trajectory(tmp_path):
